@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: atom-steps/s of FP64 Lennard-Jones force + integrate.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+Prints ONE JSON line (rank 0).  Workloads (BASELINE.json configs):
+  lj32k     (default, configs[1]) LJ fluid N=32 000, rc=2.5, VelocityVerlet(0.005), all-pairs kernel
+  lj1m      configs[3] size: LJ fluid N=1 000 188, cell list, VelocityVerlet
+  replicas  configs[2]: 1M DoubleWell LangevinInertia replicas (replica-steps/s)
+For --gpus N > 1 (launched by torch.distributed.run) the LJ workloads are atom-decomposed with an
+all-gather of positions each step, the replicas are sharded with no communication.
+
+value     device-resident throughput (state in HBM when the timed region starts)
+e2e       the same step through the public Python API with HOST arrays: every step re-binds
+          pos/vel/force from page-locked host memory (H2D inside the timed region) and reads
+          pos/vel/force/v_pot back (D2H)
+roofline  the dominant kernel against the FP64 pipe (all-pairs, cells) or HBM (replicas)
+cpu_baseline  the CPU oracle (NumPy restatement of the reference, 1 core) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+SINGLE = {0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}}
+RC, RHO = 2.5, 0.8
+WORKLOADS = {
+    "lj32k": dict(rep=20, method="allpairs", dt=0.005, unit="atom-steps/s"),
+    "lj256k": dict(rep=40, method="cells", dt=0.005, unit="atom-steps/s"),
+    "lj1m": dict(rep=63, method="cells", dt=0.005, unit="atom-steps/s"),
+    "replicas": dict(n=1_000_000, dt=0.002, unit="replica-steps/s"),
+}
+
+
+def lj_inputs(rep):
+    """Jittered FCC fluid of BASELINE.md section 3 (density 0.8, jitter 0.05, seeds 3 and 1)."""
+    from turtlemd_b200.tools import generate_lattice
+
+    pos, size = generate_lattice("fcc", [rep] * 3, density=RHO)
+    pos = pos + 0.05 * (2.0 * np.random.default_rng(3).random(pos.shape) - 1.0)
+    vel = np.random.default_rng(1).standard_normal(pos.shape)
+    vel -= vel.mean(axis=0)
+    vel *= math.sqrt(0.8 / (np.sum(vel * vel) / (3 * len(pos) - 3)))  # T = 0.8, as generate_maxwell_velocities
+    return pos, vel, size
+
+
+def algorithmic_flops(n, method):
+    """21 flop per pair check + 36 per pair inside the cut-off (FMA = 2)."""
+    hits = n * (4.0 / 3.0) * math.pi * RC**3 * RHO / 2.0
+    checks = n * (n - 1) / 2.0 if method == "allpairs" else n * 27.0 * RC**3 * RHO / 2.0
+    return 21.0 * checks + 36.0 * hits
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons}
+
+
+def dist_setup(gpus):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def timed(fn, steps, world):
+    """Barrier + sync, `steps` calls of fn timed with CUDA events, max over ranks -> seconds."""
+    import torch
+
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    return sec
+
+
+# ---- the measured arms ---------------------------------------------------------------------------------
+
+
+def bench_lj(args, cfg, rank, world):
+    import ctypes as C
+
+    import torch
+
+    from turtlemd_b200 import _device, _lib
+    from turtlemd_b200.integrators import VelocityVerlet
+    from turtlemd_b200.potentials import LennardJonesCut
+    from turtlemd_b200.system import Box, Particles, System
+
+    pos, vel, size = lj_inputs(cfg["rep"])
+    n = len(pos)
+    box = Box(low=size[:, 0], high=size[:, 1])
+    pot = LennardJonesCut(dim=3, shift=True, method=cfg["method"])
+    pot.set_parameters(SINGLE)
+    system = System(box, Particles.from_arrays(pos, vel=vel), [pot])
+    integ = VelocityVerlet(cfg["dt"])
+    if world > 1:
+        from turtlemd_b200.parallel import AtomDecomposition
+
+        stepper = AtomDecomposition(system, integ)
+        step = stepper.step
+        stepper.prepare()
+        launches_per_step = stepper.launches_per_step
+    else:
+        system.evaluate(7)
+        step = lambda: integ(system)  # noqa: E731
+        launches_per_step = 6 if cfg["method"] == "allpairs" else None
+    for _ in range(args.warmup):
+        step()
+    with ClockSampler(torch.cuda.current_device()) as clocks:
+        sec = timed(step, args.steps, world)
+    value = n * args.steps / sec
+
+    out = {
+        "metric": "atom-steps/sec (FP64 LJ force+integrate)", "value": value, "unit": cfg["unit"],
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"LJ fluid N={n} jittered FCC rho=0.8, rc=2.5 sigma, shifted, "
+                               f"VelocityVerlet dt={cfg['dt']}, {cfg['method']} kernel",
+                   "n_atoms": n, "parallelism": f"atom-decomposition x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs (0.75 MB of positions) are L2-resident by nature of the workload; "
+                         "the kernel is FP64-pipe bound, no L2 flush between steps"},
+        "clocks": clocks.summary(),
+    }
+    if rank != 0:
+        return None
+
+    # ---- single-GPU extras: roofline of the dominant kernel, e2e, CPU baseline ---------------------
+    if world == 1:
+        lib = _lib.load()
+        tf, ms = C.c_double(0), C.c_double(0)
+        _lib.check(lib.tmd_bench_dfma(5, C.byref(tf), C.byref(ms)))
+        peak = tf.value
+        evaluate = lambda: system.evaluate(7)  # noqa: E731  (wrap + pair kernel + finish + reduce)
+        for _ in range(3):
+            evaluate()
+        ksec = timed(evaluate, args.steps, 1) / args.steps
+        flops = algorithmic_flops(n, cfg["method"])
+        achieved = flops / ksec / 1e12
+        out["roofline"] = {
+            "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None,
+            "kernel": "lj_allpairs_kernel<3,7>" if cfg["method"] == "allpairs" else "lj_cells_kernel",
+            "algorithmic_flops_per_launch": flops, "launch_ms": ksec * 1e3,
+            "peak_source": "DFMA-only micro-benchmark (tmd_bench_dfma) run in this process; "
+                           "MEASURED_PEAKS.json has no FP64 entry (nominal 37.2 TFLOP/s)",
+        }
+        out["gpu_launches"] = (launches_per_step or 0) * args.steps
+
+        # e2e: host arrays every step through the public API
+        hp, hv, hf = (_device.pinned_array(pos.shape) for _ in range(3))
+        part = system.particles
+        np.copyto(hp, part.pos)
+        np.copyto(hv, part.vel)
+        np.copyto(hf, part.force)
+
+        def e2e_step():
+            part.pos, part.vel, part.force = hp, hv, hf  # re-bind host arrays: device copies are stale
+            integ(system)
+            _ = part.pos, part.vel, part.force, part.v_pot  # read back into the same page-locked arrays
+
+        for _ in range(2):
+            e2e_step()
+        esteps = max(3, min(args.steps, 20))
+        esec = timed(e2e_step, esteps, 1)
+        out["e2e"] = {"value": n * esteps / esec, "unit": cfg["unit"],
+                      "h2d_bytes_per_step": 3 * pos.nbytes, "d2h_bytes_per_step": 3 * pos.nbytes + 80,
+                      "ms_per_step": esec / esteps * 1e3,
+                      "api": "VelocityVerlet.integration_step(system) with particles.pos/vel/force re-bound "
+                             "from page-locked host arrays and read back every step"}
+        out["cpu_baseline"] = cpu_baseline_lj(pos, size, n, cfg["method"])
+    return out
+
+
+def cpu_baseline_lj(pos, size, n, method, budget_s=15.0):
+    """The NumPy oracle (restated reference row loop, 1 core) on a strided sample of rows."""
+    from oracle import turtle_oracle as to
+
+    length = size[:, 1] - size[:, 0]
+    table, _ = to.lj_tables(SINGLE)
+    tidx = np.zeros(n, dtype=int)
+    lj1, lj2, lj3, lj4, offset, rcut2 = table
+    stride = max(1, n // 640)
+    rows = np.arange(0, n - 1, stride)
+    checks, t0 = 0, time.perf_counter()
+    pot = 0.0
+    for i in rows:  # the body of lj_potential_and_force for the sampled rows
+        delta, rsq, k = to._row(pos, tidx, int(i), length, 1.0 / length, [True] * 3, rcut2)
+        checks += n - int(i) - 1
+        if len(k):
+            r2inv = 1.0 / rsq[k]
+            r6inv = r2inv**3
+            pot += np.sum(r6inv * (lj3[0, 0] * r6inv - lj4[0, 0]) - offset[0, 0])
+            flj = r2inv * r6inv * (lj1[0, 0] * r6inv - lj2[0, 0])
+            fij = np.einsum("i,ij->ij", flj, delta[k])
+            np.einsum("ij,ik->jk", fij, delta[k])
+        if time.perf_counter() - t0 > budget_s:
+            break
+    sec = time.perf_counter() - t0
+    full = sec * (n * (n - 1) / 2.0) / checks  # the reference is all-pairs whatever the GPU method
+    return {"value": n / full, "unit": "atom-steps/s", "cores": 1, "kind": "port",
+            "sample": f"NumPy oracle row loop on {checks:.3g} of {n * (n - 1) / 2:.3g} pair checks "
+                      f"(every {stride}th row) in {sec:.1f} s, scaled to one full step; host has {os.cpu_count()} cores",
+            "pair_checks_per_s": checks / sec}
+
+
+def bench_replicas(args, cfg, rank, world):
+    import ctypes as C
+
+    import torch
+
+    from turtlemd_b200 import _device, _lib
+    from turtlemd_b200.integrators import LangevinInertia
+    from turtlemd_b200.philox import PhiloxNormal
+    from turtlemd_b200.potentials import DoubleWell
+    from turtlemd_b200.system import Box, Particles, System
+
+    n_global = cfg["n"] * world  # weak scaling: 1M replicas per GPU
+    n, first = cfg["n"], rank * cfg["n"]
+    x0 = np.full((n, 1), -1.0)
+    system = System(Box(periodic=[False]), Particles.from_arrays(x0), [DoubleWell(a=1.0, b=2.0, c=0.0)])
+    system.evaluate(7)
+    integ = LangevinInertia(timestep=cfg["dt"], gamma=0.3, beta=1.0 / 0.07, rgen=PhiloxNormal(key=0))
+    inner = 10  # integrator steps per launch of the fused kernel
+    step = lambda: integ.run(system, inner, first=first, n_global=n_global)  # noqa: E731
+    for _ in range(args.warmup):
+        step()
+    with ClockSampler(torch.cuda.current_device()) as clocks:
+        sec = timed(step, args.steps, world)
+    value = n_global * inner * args.steps / sec
+    out = {
+        "metric": "replica-steps/sec (FP64 DoubleWell LangevinInertia)", "value": value, "unit": cfg["unit"],
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{cfg['n']} independent 1-D DoubleWell(1,2,0) LangevinInertia replicas per GPU, "
+                               f"dt={cfg['dt']}, gamma=0.3, beta=1/0.07; one bench step = {inner} integrator steps "
+                               "in one fused kernel", "replicas_per_gpu": n, "parallelism": f"replica sharding x{world}"},
+        "clocks": clocks.summary(), "gpu_launches": 2 * args.steps,
+    }
+    if rank != 0:
+        return None
+    bytes_per_launch = 48.0 * n  # x, v, F read + written once per launch
+    out["roofline"] = {"bound": "hbm", "achieved": bytes_per_launch / (sec / args.steps) / 1e9,
+                       "peak": peak_hbm(), "unit": "GB/s", "traffic": None,
+                       "note": "compute-bound by Philox + log/sincos at 10 steps per launch; see DESIGN.md"}
+    out["roofline"]["frac"] = out["roofline"]["achieved"] / out["roofline"]["peak"]
+    del C, _device, _lib
+    return out
+
+
+def peak_hbm():
+    path = REPO / "MEASURED_PEAKS.json"
+    if path.exists():
+        return json.loads(path.read_text())["hbm_gbs"]
+    return 6650.0
+
+
+def bench_reference(args, cfg, rank, world):
+    """--impl reference: the CPU oracle (NumPy port of the reference's row loop), rank 0 only."""
+    if rank != 0:
+        return None
+    if "rep" not in cfg:
+        return {"impl": "reference", "unavailable": "reference arm is implemented for the LJ workloads"}
+    pos, vel, size = lj_inputs(cfg["rep"])
+    n = len(pos)
+    samples = []
+    for it in range(args.warmup + args.steps):
+        base = cpu_baseline_lj(pos, size, n, cfg["method"], budget_s=1.0 if n > 4000 else 5.0)
+        if it >= args.warmup:
+            samples.append(base)
+    value = statistics.mean(s["value"] for s in samples)
+    base = dict(samples[-1], value=value)
+    return {
+        "impl": "reference", "metric": "atom-steps/sec (FP64 LJ force+integrate)", "value": value,
+        "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * n / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"LJ fluid N={n} jittered FCC rho=0.8, rc=2.5 sigma, shifted, VelocityVerlet "
+                               "(reference algorithm: all-pairs row loop)", "n_atoms": n},
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="lj32k", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        out = bench_reference(args, cfg, rank, int(os.environ.get("WORLD_SIZE", "1")))
+    else:
+        rank, world, _ = dist_setup(args.gpus)
+        out = (bench_replicas if args.workload == "replicas" else bench_lj)(args, cfg, rank, world)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+            dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,268 @@
+/*
+ * turtlemd_b200 -- C ABI of the B200-native TurtleMD hot path.
+ *
+ * One shared library (libturtlemd_b200.so, built from turtlemd_b200/csrc/ for
+ * sm_100a) exports everything below with C linkage.  Plain pointers and sizes
+ * only; no torch / numpy types.  Every function returns a tmd_status
+ * (0 = TMD_OK); tmd_last_error() gives the text of the last failure on the
+ * calling thread.  There is NO CPU fallback: without a CUDA device every
+ * compute entry point returns TMD_ERR_NO_DEVICE.
+ *
+ * Two families of entry points:
+ *
+ *   tmd_host_*   take HOST buffers laid out exactly like the reference's NumPy
+ *                arrays (pos/vel/force (N,d) C-order float64, ptype (N,) int64,
+ *                virial (d,d) float64).  They are what a reference maintainer
+ *                binds behind Potential.force()/potential()/potential_and_force()
+ *                and MDIntegrator.integration_step(): copy in, launch, copy out.
+ *
+ *   tmd_*        (no "host") take DEVICE pointers + a cudaStream_t (as void*),
+ *                never synchronise and never allocate on the hot path (scratch
+ *                comes from a per-device arena that only grows).  The Python
+ *                package keeps the particle arrays resident in HBM and calls
+ *                these; so does tmd_md_run().
+ *
+ * Reference = infretis/turtlemd 2023.3.1; citations are file:line in its tree.
+ *
+ * Array conventions
+ *   pos, vel, force : double[n*dim], row-major (n, dim), dim in {1,2,3}
+ *   imass           : double[n]            (reference: (n,1), system/particles.py:44)
+ *   tidx            : int32[n]  dense type index 0..ntypes-1 (the host wrapper
+ *                     maps the reference's arbitrary int64 ptype values onto it)
+ *   table           : double[6*T*T] = lj1, lj2, lj3, lj4, offset, rcut2, each (T,T);
+ *                     the values LennardJonesCut.set_parameters computes
+ *                     (potentials/lennardjones.py:94-115)
+ *   vw              : double[10] = { V, W[0][0..2], W[1][0..2], W[2][0..2] } ; the
+ *                     (dim,dim) virial is the top-left block of the 3x3
+ */
+#ifndef TURTLEMD_B200_H
+#define TURTLEMD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMD_ABI_VERSION 1
+
+typedef enum tmd_status {
+    TMD_OK = 0,
+    TMD_ERR_INVALID = 1,     /* bad argument (dim, sizes, null pointer, unknown flag) */
+    TMD_ERR_CUDA = 2,        /* a CUDA runtime call failed; see tmd_last_error()       */
+    TMD_ERR_NO_DEVICE = 3,   /* no usable CUDA device: the product has no CPU path     */
+    TMD_ERR_UNSUPPORTED = 4, /* valid in the reference but outside the hot path (e.g. ntypes > TMD_MAX_TYPES) */
+    TMD_ERR_NOMEM = 5
+} tmd_status;
+
+/* what an evaluation should produce / how it combines with what is already there */
+#define TMD_WANT_V 1u        /* potential energy  -> vw[0]                                      */
+#define TMD_WANT_F 2u        /* forces            -> force[]                                    */
+#define TMD_WANT_W 4u        /* virial            -> vw[1..9]                                   */
+#define TMD_ACCUMULATE 8u    /* add to force[] / vw[] instead of overwriting (2nd, 3rd potential of a System) */
+#define TMD_V_STANDALONE 16u /* LJ only: r6inv = 1/rsq^3 as LennardJonesCut.potential() does
+                                (lennardjones.py:172) instead of (1/rsq)^3 (:254-255)           */
+
+#define TMD_MAX_TYPES 8      /* particle types per LJ table on the device path */
+
+typedef void *tmd_stream_t;  /* a cudaStream_t; NULL = the legacy default stream */
+
+/* Orthorhombic box as Box/BoxBase store it (system/box.py:140-158).
+ * Non-periodic directions: periodic=0; length/ilength are then ignored
+ * (the reference keeps inf / 0 there).                                                         */
+typedef struct tmd_box {
+    int32_t dim;
+    int32_t periodic[3];
+    double length[3];
+    double ilength[3];       /* the STORED reciprocal 1/length, multiplied with as box.py:402 does */
+} tmd_box;
+
+/* ---------------------------------------------------------------- library / device ---------- */
+int tmd_abi_version(void);
+const char *tmd_last_error(void);
+const char *tmd_status_string(int status);
+int tmd_device_count(int *count);
+int tmd_set_device(int device);
+/* name[<=256]; sm = 10*major+minor; bytes of HBM; number of SMs */
+int tmd_device_info(int device, char *name, int *sm, size_t *total_mem, int *num_sms);
+int tmd_stream_synchronize(tmd_stream_t stream);
+
+/* device memory + copies for bindings that do not bring their own allocator */
+int tmd_malloc(void **dptr, size_t bytes);
+int tmd_free(void *dptr);
+int tmd_memset_async(void *dptr, int value, size_t bytes, tmd_stream_t stream);
+int tmd_memcpy_h2d_async(void *dptr, const void *hptr, size_t bytes, tmd_stream_t stream);
+int tmd_memcpy_d2h_async(void *hptr, const void *dptr, size_t bytes, tmd_stream_t stream);
+int tmd_memcpy_d2d_async(void *dst, const void *src, size_t bytes, tmd_stream_t stream);
+/* page-lock an existing host range (e.g. the NumPy arrays of a Particles object) */
+int tmd_host_register(void *hptr, size_t bytes);
+int tmd_host_unregister(void *hptr);
+/* peer access for the atom-decomposed multi-GPU path (cudaIpc*, 64-byte handles) */
+int tmd_ipc_get_handle(void *dptr, unsigned char handle[64]);
+int tmd_ipc_open_handle(const unsigned char handle[64], void **dptr);
+int tmd_ipc_close_handle(void *dptr);
+
+/* ---------------------------------------------------------------- pair potentials ----------- */
+
+/* K1. LennardJonesCut.potential_and_force / .force / .potential
+ * (potentials/lennardjones.py:145-273) with Box.pbc_dist_matrix fused
+ * (system/box.py:384-403): tiled all-pairs FP64, every one of the N(N-1)/2 pairs is
+ * distance-checked.  Deterministic (no atomics).  first/count select the rows this call
+ * computes forces for (atom decomposition: rank g passes its own slab and gets V and W for
+ * that slab's share; first=0,count=n is the whole system).                                      */
+int tmd_lj_allpairs(const double *pos, const int32_t *tidx, int64_t n, const tmd_box *box,
+                    const double *table, int32_t ntypes, uint32_t flags,
+                    int64_t first, int64_t count,
+                    double *force, double *vw, tmd_stream_t stream);
+
+/* K2+K3. Same contract, O(N): bins a wrapped copy of pos into cells of edge >= max rcut
+ * (counting sort), then walks the 3^dim stencil.  The API-visible pos is left unwrapped, as
+ * the reference integrators leave it (integrators.py:90).  Returns TMD_ERR_UNSUPPORTED when a
+ * periodic direction holds fewer than 3 cells (then only tmd_lj_allpairs matches the
+ * reference's single-nearest-image rule); tmd_lj_cells_usable() tells in advance.               */
+int tmd_lj_cells_usable(int64_t n, const tmd_box *box, const double *table, int32_t ntypes, int *usable);
+int tmd_lj_cells(const double *pos, const int32_t *tidx, int64_t n, const tmd_box *box,
+                 const double *table, int32_t ntypes, uint32_t flags,
+                 int64_t first, int64_t count,
+                 double *force, double *vw, tmd_stream_t stream);
+
+/* K4. DoubleWell.potential / .force (potentials/well.py:65-81): V = sum a x^4 - b (x-c)^2 over
+ * ALL n*dim coordinates, F = -4 a x^3 + 2 b (x - c), virial = 0.                                */
+int tmd_doublewell(const double *pos, int64_t n, int32_t dim, double a, double b, double c,
+                   uint32_t flags, double *force, double *vw, tmd_stream_t stream);
+
+/* K5. DoubleWellPair.potential / .force (potentials/well.py:230-286), Box.pbc_dist fused
+ * (system/box.py:370-382, strict '>').  No cut-off.  idx0[n0] / idx1[n1] are the (ascending)
+ * indices of the atoms of types[0] / types[1]; same_type != 0 means types[0]==types[1] and
+ * idx1 is ignored.  rwidth, width2, height are the derived parameters of set_parameters
+ * (well.py:206-212).                                                                             */
+int tmd_dwpair(const double *pos, int64_t n, const tmd_box *box,
+               const int32_t *idx0, int32_t n0, const int32_t *idx1, int32_t n1, int32_t same_type,
+               double rwidth, double width2, double height, uint32_t flags,
+               double *force, double *vw, tmd_stream_t stream);
+
+/* ---------------------------------------------------------------- integrators --------------- */
+/* All element-wise over the flat n*dim array; arithmetic order follows the NumPy expressions
+ * so that, given identical forces, the updates are bit-identical to the reference's.           */
+
+/* VelocityVerlet (integrators.py:84-94): v += (dt/2 * F) * imass ; x += dt * v                  */
+int tmd_vv_kick_drift(double *pos, double *vel, const double *force, const double *imass,
+                      int64_t n, int32_t dim, double dt, tmd_stream_t stream);
+/* ... second half kick: v += (dt/2 * F) * imass                                                  */
+int tmd_vv_kick(double *vel, const double *force, const double *imass,
+                int64_t n, int32_t dim, double dt, tmd_stream_t stream);
+/* last kick of step k and first kick + drift of step k+1 in one pass (both roundings kept)     */
+int tmd_vv_kick_kick_drift(double *pos, double *vel, const double *force, const double *imass,
+                           int64_t n, int32_t dim, double dt, tmd_stream_t stream);
+
+/* Verlet (integrators.py:53-68).  first_call != 0 initialises prev = x - v*dt first (:56-57). */
+int tmd_verlet_step(double *pos, double *vel, double *prev, const double *force, const double *imass,
+                    int64_t n, int32_t dim, double dt, int32_t first_call, tmd_stream_t stream);
+
+/* Counter-based noise: "tmd-normal-v1" = Philox4x64-10 laid out like numpy.random.Philox(key)
+ * + a fixed-arithmetic Box-Muller.  Draw number q of the stream is independent of
+ * who asks for it, so any sharding of the particles reproduces the same trajectory.            */
+typedef struct tmd_rng {
+    uint64_t key;            /* Philox key word 0 (word 1 = 0), = numpy Philox(key=...)          */
+    uint64_t offset;         /* index of this step's first normal in the stream                  */
+} tmd_rng;
+
+/* LangevinOverdamped (integrators.py:151-163), the part between force() and potential():
+ *   xi = sigma_i * z[offset + (first+i)*dim + k] ;  x += bddt_i * F + xi ;  v = xi
+ * sigma_i = sqrt(2 dt imass_i/(beta gamma)), bddt_i = dt*imass_i/gamma (:137-149) are computed
+ * in-kernel.  noise != NULL: use these host-drawn normals (n*dim, already scaled by sigma,
+ * i.e. the array rgen.normal returned) instead of the in-kernel stream.                         */
+int tmd_langevin_overdamped(double *pos, double *vel, const double *force, const double *imass,
+                            int64_t n, int32_t dim, double dt, double gamma, double beta,
+                            const tmd_rng *rng, int64_t first, const double *noise,
+                            tmd_stream_t stream);
+
+/* Scalar constants of LangevinInertia.initiate_parameters (integrators.py:223-263).  The
+ * per-particle ones follow in-kernel from imass_i:  a2_i = a2f*imass_i, b1_i = b1f*imass_i,
+ * b2_i = b2f*imass_i, sig_r2 = ((dt*imass_i)/beta_gamma)*kfac, sig_v2 = (one_minus_e2*imass_i)/beta,
+ * cov_rv = (imass_i/beta_gamma)*one_minus_e_sq and the 2x2 Cholesky factor L of
+ * [[sig_r2, cov_rv], [cov_rv, sig_v2]] (:249-262).  The Python host fills this struct with NumPy
+ * (same expressions as the reference); tmd_langevin_inertia_constants() is the libm version.    */
+typedef struct tmd_langevin_consts {
+    double c0;             /* exp(-gamma dt)                       */
+    double a1;             /* c1*dt                                */
+    double a2f;            /* c2*dt**2                             */
+    double b1f;            /* (c1-c2)*dt                           */
+    double b2f;            /* c2*dt                                */
+    double dt;
+    double beta;
+    double beta_gamma;     /* beta*gamma                           */
+    double kfac;           /* 2 - (3 - 4 e + e**2)/(gamma dt)      */
+    double one_minus_e2;   /* 1 - e**2                             */
+    double one_minus_e_sq; /* (1 - e)**2                           */
+} tmd_langevin_consts;
+int tmd_langevin_inertia_constants(double dt, double gamma, double beta, tmd_langevin_consts *out);
+
+/* LangevinInertia (integrators.py:265-282), part 1 (before force()):
+ *   (n0, n1) = z[offset + (first+i)*2*dim + 2k + {0,1}]
+ *   x += (a1 v + a2_i F) + L00_i n0 ;  v' = (c0 v + b1_i F) + (L10_i n0 + L11_i n1)
+ * noise_pos/noise_vel != NULL: host-drawn pos_rand / vel_rand arrays instead (any duck-typed
+ * rgen, e.g. numpy default_rng or the reference tests' FakeRandomGenerator).                    */
+int tmd_langevin_inertia_pre(double *pos, double *vel, const double *force, const double *imass,
+                             int64_t n, int32_t dim, const tmd_langevin_consts *consts,
+                             const tmd_rng *rng, int64_t first,
+                             const double *noise_pos, const double *noise_vel,
+                             tmd_stream_t stream);
+/* ... part 2 (after force()): v = v' + b2_i * F                                                  */
+int tmd_langevin_inertia_post(double *vel, const double *force, const double *imass,
+                              int64_t n, int32_t dim, const tmd_langevin_consts *consts,
+                              tmd_stream_t stream);
+
+/* Fused replica kernel (config "1M independent DoubleWell Langevin replicas"): nsteps full
+ * LangevinInertia steps of a system whose only potential is DoubleWell, state in registers,
+ * force recomputed in-kernel.  On return force[] and vw[0] hold F and V of the final positions
+ * exactly as nsteps reference steps would leave particles.force / particles.v_pot.  The rank
+ * holds replicas first .. first+n-1 of n_global; the noise of replica i does not depend on the
+ * sharding.                                                                                      */
+int tmd_langevin_inertia_doublewell(double *pos, double *vel, double *force, const double *imass,
+                                    int64_t n, int32_t dim, double a, double b, double c,
+                                    const tmd_langevin_consts *consts,
+                                    const tmd_rng *rng, int64_t first, int64_t n_global,
+                                    int32_t nsteps, double *vw, tmd_stream_t stream);
+
+/* fill out[count] with normals offset .. offset+count-1 of the stream (host-twin tests) */
+int tmd_philox_normal_fill(double *out, int64_t count, const tmd_rng *rng, tmd_stream_t stream);
+/* same numbers computed on the HOST by the same source (no device needed) */
+int tmd_host_philox_normal_fill(double *out, int64_t count, uint64_t key, uint64_t offset);
+int tmd_host_philox_raw_fill(uint64_t *out, int64_t count, uint64_t key, uint64_t offset);
+
+/* ---------------------------------------------------------------- observables (next) */
+/* kinetic energy tensor 0.5 sum m v(x)v (system/particles.py:156-168) -> kin[9] (3x3 block)   */
+int tmd_kinetic_tensor(const double *vel, const double *mass, int64_t n, int32_t dim,
+                       double *kin, tmd_stream_t stream);
+
+/* ---------------------------------------------------------------- host-buffer plug-in API ---- */
+/* LennardJonesCut.{potential_and_force,force,potential}(system) with the reference's own
+ * arrays: pos (n,dim) f64, ptype (n,) int64 already mapped to 0..ntypes-1, outputs force
+ * (n,dim), vw[10].  method: 0 = choose (cells when usable and n >= 4096), 1 = all-pairs,
+ * 2 = cells.  Synchronous.                                                                       */
+int tmd_host_lj(const double *pos, const int64_t *tidx, int64_t n, const tmd_box *box,
+                const double *table, int32_t ntypes, uint32_t flags,
+                int32_t method, double *force, double *vw);
+int tmd_host_doublewell(const double *pos, int64_t n, int32_t dim, double a, double b, double c,
+                        uint32_t flags, double *force, double *vw);
+int tmd_host_dwpair(const double *pos, const int64_t *ptype, int64_t n, const tmd_box *box,
+                    int64_t type0, int64_t type1, double rwidth, double width2, double height,
+                    uint32_t flags, double *force, double *vw);
+/* One VelocityVerlet.integration_step(system) for a single-LJ-potential System, host arrays in
+ * and out (pos, vel, force updated in place; vw[10] out).                                       */
+int tmd_host_vv_lj_step(double *pos, double *vel, double *force, const double *imass,
+                        const int64_t *tidx, int64_t n, const tmd_box *box,
+                        const double *table, int32_t ntypes, int32_t method, double dt, double *vw);
+
+/* ---------------------------------------------------------------- measurement helpers -------- */
+/* FP64 pipe peak: DFMA-only kernel on every SM; returns achieved TFLOP/s (FMA = 2 flop).        */
+int tmd_bench_dfma(int32_t repeats, double *tflops, double *milliseconds);
+/* STREAM-style copy of `bytes` bytes; returns GB/s counting read + write.                       */
+int tmd_bench_copy(size_t bytes, int32_t repeats, double *gbs, double *milliseconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TURTLEMD_B200_H */

@@ -1,0 +1,542 @@
+"""GPU parity: the CUDA path (through the C ABI) against golden fixtures and the CPU oracle.
+
+Tolerances (BASELINE.json north_star): forces / potential energy / virial to 1e-10 relative
+(norm-wise, max|a-b|/max|b|, see SURVEY.md section 4 on why not element-wise), 10-step
+trajectories to 1e-8, RNG draws bit-exact.
+"""
+from __future__ import annotations
+
+import glob
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden, rel_norm
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+TRAJ_TOL = 1e-8
+
+LJ_CASES = sorted(p.split("/")[-1] for p in glob.glob(str(GOLDEN / "lj_*.npz")))
+SINGLE = {0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}}
+
+
+def _pkg():
+    import turtlemd_b200.integrators as integrators
+    from turtlemd_b200.potentials import DoubleWell, DoubleWellPair, LennardJonesCut
+    from turtlemd_b200.simulation import MDSimulation
+    from turtlemd_b200.system import Box, Particles, System
+
+    return dict(integrators=integrators, DoubleWell=DoubleWell, DoubleWellPair=DoubleWellPair,
+                LennardJonesCut=LennardJonesCut, MDSimulation=MDSimulation, Box=Box,
+                Particles=Particles, System=System)
+
+
+def _lj_params_for(name):
+    two = {0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}, 1: {"sigma": 1.2, "epsilon": 0.7, "rcut": 3.0}}
+    three = dict(two)
+    three[2] = {"sigma": 0.9, "epsilon": 1.3, "rcut": 2.2}
+    three[(0, 2)] = {"sigma": 1.1, "epsilon": 0.5, "rcut": 2.0}
+    if "two_types_geometric" in name:
+        return two, dict(mixing="geometric", shift=True)
+    if "two_types_arithmetic" in name:
+        return two, dict(mixing="arithmetic", shift=False)
+    if "three_types" in name:
+        return three, dict(mixing="sixthpower", shift=True)
+    if "wca" in name:
+        return {0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.0 ** (1.0 / 6.0)}}, dict(shift=True)
+    return SINGLE, dict(shift=True)
+
+
+def _lj_system(g, name, method="allpairs"):
+    k = _pkg()
+    params, kw = _lj_params_for(name)
+    box = k["Box"](low=g["low"], high=g["high"], periodic=[bool(p) for p in g["periodic"]])
+    part = k["Particles"].from_arrays(g["pos"], ptype=g["ptype"])
+    pot = k["LennardJonesCut"](dim=g["pos"].shape[1], method=method, **kw)
+    pot.set_parameters(params)
+    return k["System"](box=box, particles=part, potentials=[pot]), pot
+
+
+@pytest.mark.parametrize("name", LJ_CASES)
+def test_lj_plugin_boundary_matches_reference(name):
+    g = load_golden(name)
+    system, pot = _lj_system(g, name)
+    # the dense table the kernel consumes == the reference's dictionaries
+    _, table, _ = pot._tables(system.particles)
+    assert np.array_equal(np.nan_to_num(table, nan=-1.0), np.nan_to_num(g["table"], nan=-1.0))
+    v, f, w = pot.potential_and_force(system)
+    assert abs(v - g["v_pf"]) <= TOL * abs(g["v_pf"])
+    assert rel_norm(f, g["f_pf"]) < TOL
+    assert rel_norm(w, g["w_pf"]) < TOL
+    f2, w2 = pot.force(system)
+    assert rel_norm(f2, g["f_f"]) < TOL and rel_norm(w2, g["w_f"]) < TOL
+    assert np.array_equal(f2, f)  # force() and potential_and_force() share the arithmetic
+    assert abs(pot.potential(system) - g["v_p"]) <= TOL * abs(g["v_p"])
+
+
+@pytest.mark.parametrize("name", ["lj_fcc_864.npz", "lj_two_types_geometric.npz", "lj_fcc_256_unwrapped.npz"])
+def test_lj_resident_path_equals_plugin_path(name):
+    g = load_golden(name)
+    system, pot = _lj_system(g, name)
+    v, f, w = pot.potential_and_force(system)
+    v2, f2, w2 = system.potential_and_force()
+    assert v2 == v and np.array_equal(f2, f) and np.array_equal(w2, w)
+    assert isinstance(v2, float)
+    f3, w3 = system.force()
+    assert np.array_equal(f3, f) and np.array_equal(w3, w)
+    assert system.particles.v_pot == v  # force() leaves v_pot alone
+    vp = system.potential()
+    assert abs(vp - g["v_p"]) <= TOL * abs(g["v_p"])
+    assert np.array_equal(system.particles.virial, w)
+
+
+def test_lj_deterministic_and_newton():
+    g = load_golden("lj_fcc_4000.npz")
+    system, pot = _lj_system(g, "lj_fcc_4000.npz")
+    v, f, w = pot.potential_and_force(system)
+    v2, f2, w2 = pot.potential_and_force(system)
+    assert v == v2 and np.array_equal(f, f2) and np.array_equal(w, w2)  # no atomics: bit-reproducible
+    assert np.max(np.abs(f.sum(axis=0))) < 1e-9 * np.max(np.abs(f))
+    assert rel_norm(w, w.T) < 1e-12
+
+
+def test_lj_reference_known_answers():
+    """tests/potentials/test_lennardjones.py:16-43,186-220 of the reference."""
+    k = _pkg()
+    kat = load_golden("reference_kats.npz")
+    part = k["Particles"](dim=3)
+    for xyz in ([1.0, 1.0, 1.0], [1.5, 1.0, 1.0], [1.5, 1.5, 1.0]):
+        part.add_particle(name="Ar", pos=np.array(xyz), mass=1.0, ptype=0)
+    system = k["System"](k["Box"](high=np.array([10, 10, 10])), part)
+    pot = k["LennardJonesCut"](dim=3, shift=True, mixing="geometric")
+    pot.set_parameters(SINGLE)
+    assert pot.potential(system) == pytest.approx(float(kat["lj_vpot"]))
+    f, w = pot.force(system)
+    assert f == pytest.approx(kat["lj_force"]) and w == pytest.approx(kat["lj_virial"])
+    v, f, w = pot.potential_and_force(system)
+    assert v == pytest.approx(float(kat["lj_vpot"])) and f == pytest.approx(kat["lj_force"])
+    pot0 = k["LennardJonesCut"](dim=3, shift=True)
+    pot0.set_parameters({0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 0.0}})
+    assert pot0.potential(system) == 0.0
+    # a type pair without parameters raises KeyError like the reference's dict lookup
+    part.add_particle(name="X", pos=np.array([3.0, 3.0, 3.0]), mass=1.0, ptype=5)
+    with pytest.raises(KeyError):
+        pot.potential(system)
+
+
+@pytest.mark.parametrize("name", ["doublewell_1d_11.npz", "doublewell_3d_257.npz"])
+def test_doublewell(name):
+    k = _pkg()
+    g = load_golden(name)
+    a, b, c = (float(x) for x in g["abc"])
+    dim = g["pos"].shape[1]
+    system = k["System"](k["Box"](periodic=[False] * dim), k["Particles"].from_arrays(g["pos"]),
+                         [k["DoubleWell"](a=a, b=b, c=c)])
+    pot = system.potentials[0]
+    v = pot.potential(system)
+    f, w = pot.force(system)
+    assert abs(v - g["v"]) <= TOL * abs(g["v"])
+    assert rel_norm(f, g["f"]) < TOL and np.array_equal(w, g["w"])
+    v2, f2, w2 = system.potential_and_force()
+    assert v2 == v and np.array_equal(f2, f) and np.array_equal(w2, np.zeros((dim, dim)))
+
+
+@pytest.mark.parametrize("types", ["11", "12", "02"])
+def test_doublewell_pair(types):
+    k = _pkg()
+    g = load_golden(f"dwpair_108_types{types}.npz")
+    system = k["System"](k["Box"](low=g["low"], high=g["high"]),
+                         k["Particles"].from_arrays(g["pos"], ptype=g["ptype"]))
+    pot = k["DoubleWellPair"](types=tuple(int(t) for t in g["types"]))
+    pot.set_parameters({"rzero": float(g["rzero"]), "height": float(g["height"]), "width": float(g["width"])})
+    v = pot.potential(system)
+    f, w = pot.force(system)
+    assert abs(v - g["v"]) <= TOL * abs(g["v"])
+    assert rel_norm(f, g["f"]) < TOL and rel_norm(w, g["w"]) < TOL
+    v2, f2, w2 = pot.potential_and_force(system)
+    assert v2 == v and np.array_equal(f2, f)
+    system.potentials = [pot]
+    v3, f3, w3 = system.potential_and_force()
+    assert v3 == v and np.array_equal(f3, f) and np.array_equal(w3, w)
+
+
+def test_doublewell_pair_reference_known_answers():
+    """tests/potentials/test_wellwca.py:12-45,87-110 of the reference."""
+    k = _pkg()
+    kat = load_golden("reference_kats.npz")
+
+    def make(pos):
+        part = k["Particles"](dim=3)
+        for xyz, name, ptype in zip(pos, ("Ar1", "Ar2", "X", "X"), (0, 0, 1, 1)):
+            part.add_particle(pos=xyz, mass=1.0, name=name, ptype=ptype)
+        return k["System"](k["Box"](high=[10, 10, 10]), part)
+
+    pot = k["DoubleWellPair"](types=(0, 0))
+    pot.set_parameters({"rzero": 1.0, "width": 0.25, "height": 6.0})
+    assert pot.min_max() == (1.0, 1.5, 1.25)
+    sys1 = make([[1.0, 1.0, 1.0], [2.25, 1.0, 1.0], [1.0, 2.0, 1.0], [1.0, 3.25, 1.0]])
+    assert pot.potential(sys1) == pytest.approx(6)
+    sys2 = make([[1.0, 1.0, 1.0], [1.2, 1.2, 1.2], [1.0, 2.0, 1.0], [1.0, 3.25, 1.0]])
+    f, w = pot.force(sys2)
+    assert f[0] == pytest.approx(kat["dwp_force"]) and f[1] == pytest.approx(-kat["dwp_force"])
+    assert np.all(f[2:] == 0.0) and w == pytest.approx(kat["dwp_virial"])
+    v, f2, w2 = pot.potential_and_force(sys2)
+    assert v == pytest.approx(float(kat["dwp_vpot"])) and f2 == pytest.approx(f)
+
+
+# ---- trajectories --------------------------------------------------------------------------------
+
+
+def _traj_system(g, potentials):
+    k = _pkg()
+    if "low" in g:
+        box = k["Box"](low=g["low"], high=g["high"])
+    else:
+        box = k["Box"](periodic=[False] * g["pos0"].shape[1])
+    part = k["Particles"].from_arrays(g["pos0"], vel=g["vel0"], mass=g["mass"], ptype=g["ptype"])
+    return k["System"](box=box, particles=part, potentials=potentials)
+
+
+def _lj(rc=2.5, types=(0,)):
+    k = _pkg()
+    pot = k["LennardJonesCut"](dim=3, shift=True)
+    pot.set_parameters({t: {"sigma": 1.0, "epsilon": 1.0, "rcut": rc} for t in types})
+    return pot
+
+
+def _assert_frame(system, g, frame, tol=TRAJ_TOL):
+    p = system.particles
+    assert rel_norm(p.pos, g["pos"][frame]) < tol, f"pos, frame {frame}"
+    assert rel_norm(p.vel, g["vel"][frame]) < tol, f"vel, frame {frame}"
+    assert rel_norm(p.force, g["force"][frame]) < tol, f"force, frame {frame}"
+    if not np.isnan(g["v_pot"][frame]):
+        assert abs(p.v_pot - g["v_pot"][frame]) <= tol * max(1.0, abs(g["v_pot"][frame]))
+    assert rel_norm(p.virial, g["virial"][frame]) < tol or np.max(np.abs(g["virial"][frame])) == 0.0
+
+
+@pytest.mark.parametrize("name", ["traj_vv_lj_108.npz", "traj_vv_lj_256_masses.npz"])
+def test_velocity_verlet_through_mdsimulation(name):
+    k = _pkg()
+    g = load_golden(name)
+    system = _traj_system(g, [_lj()])
+    sim = k["MDSimulation"](system, k["integrators"].VelocityVerlet(float(g["dt"])), 10)
+    frames = 0
+    for frame, sysi in enumerate(sim.run()):
+        _assert_frame(sysi, g, frame)
+        frames += 1
+    assert frames == 11
+
+
+def test_velocity_verlet_multi_step_run_is_bit_identical():
+    k = _pkg()
+    g = load_golden("traj_vv_lj_256_masses.npz")
+    a = _traj_system(g, [_lj()])
+    b = _traj_system(g, [_lj()])
+    a.potential_and_force()
+    b.potential_and_force()
+    integ = k["integrators"].VelocityVerlet(float(g["dt"]))
+    for _ in range(10):
+        integ(a)
+    integ.run(b, 10)
+    assert np.array_equal(a.particles.pos, b.particles.pos)
+    assert np.array_equal(a.particles.vel, b.particles.vel)
+    _assert_frame(b, g, 10)
+
+
+def test_verlet_trajectory():
+    k = _pkg()
+    g = load_golden("traj_verlet_lj_108.npz")
+    system = _traj_system(g, [_lj()])
+    integ = k["integrators"].Verlet(float(g["dt"]))
+    assert integ.previous_pos is None
+    sim = k["MDSimulation"](system, integ, 10)
+    for frame, sysi in enumerate(sim.run()):
+        _assert_frame(sysi, g, frame)
+        if frame > 0:
+            assert rel_norm(integ.previous_pos, g["pos"][frame - 1]) < TRAJ_TOL
+
+
+def test_dimer_in_solvent_trajectory():
+    k = _pkg()
+    g = load_golden("traj_vv_dimer_108.npz")
+    rc = float(g["rc"])
+    dw = k["DoubleWellPair"](types=(1, 1))
+    dw.set_parameters({"rzero": rc, "height": 6.0, "width": 0.25})
+    system = _traj_system(g, [_lj(rc=rc, types=(0, 1)), dw])
+    sim = k["MDSimulation"](system, k["integrators"].VelocityVerlet(float(g["dt"])), 10)
+    for frame, sysi in enumerate(sim.run()):
+        _assert_frame(sysi, g, frame)
+
+
+@pytest.mark.parametrize("dim", [1, 2])
+@pytest.mark.parametrize("kind", ["inertia", "overdamped"])
+@pytest.mark.parametrize("draws", ["in_kernel", "host_twin"])
+def test_langevin_doublewell_replicas(kind, dim, draws):
+    """The reference, fed the Philox twin, produced the fixture; the kernels must retrace it."""
+    k = _pkg()
+    from oracle.philox_ref import OraclePhiloxNormal
+    from turtlemd_b200.philox import PhiloxNormal
+
+    g = load_golden(f"traj_langevin_{kind}_{dim}d_64.npz")
+    a, b, c = (float(x) for x in g["abc"])
+    system = _traj_system(g, [k["DoubleWell"](a=a, b=b, c=c)])
+    system.potential_and_force()
+    # in_kernel: PhiloxNormal selects the device stream.  host_twin: an object the package does
+    # not know (the oracle's twin) -> draws happen on the host exactly like in the reference.
+    rgen = PhiloxNormal(key=int(g["key"])) if draws == "in_kernel" else OraclePhiloxNormal(key=int(g["key"]))
+    dt, gamma, beta = float(g["dt"]), float(g["gamma"]), float(g["beta"])
+    I = k["integrators"]
+    integ = (I.LangevinInertia(timestep=dt, gamma=gamma, beta=beta, rgen=rgen) if kind == "inertia"
+             else I.LangevinOverdamped(timestep=dt, gamma=gamma, rgen=rgen, beta=beta))
+    for frame in range(11):
+        _assert_frame(system, g, frame)
+        integ(system)
+    assert rgen.position == 10 * 64 * dim * (2 if kind == "inertia" else 1)
+
+
+def test_langevin_fused_multi_step_equals_single_steps():
+    k = _pkg()
+    from turtlemd_b200.philox import PhiloxNormal
+
+    g = load_golden("traj_langevin_inertia_1d_64.npz")
+    a, b, c = (float(x) for x in g["abc"])
+    dt, gamma, beta = float(g["dt"]), float(g["gamma"]), float(g["beta"])
+    system = _traj_system(g, [k["DoubleWell"](a=a, b=b, c=c)])
+    system.potential_and_force()
+    integ = k["integrators"].LangevinInertia(timestep=dt, gamma=gamma, beta=beta, rgen=PhiloxNormal(int(g["key"])))
+    integ.run(system, 10)
+    _assert_frame(system, g, 10)
+    # sharded: two halves with global offsets reproduce the same replicas bit for bit
+    full_pos = system.particles.pos.copy()
+    for first, count in ((0, 40), (40, 24)):
+        sl = slice(first, first + count)
+        sub = dict(pos0=g["pos0"][sl], vel0=g["vel0"][sl], mass=g["mass"][sl], ptype=g["ptype"][sl])
+        shard = _traj_system(sub, [k["DoubleWell"](a=a, b=b, c=c)])
+        shard.potential_and_force()
+        integ = k["integrators"].LangevinInertia(timestep=dt, gamma=gamma, beta=beta,
+                                                 rgen=PhiloxNormal(int(g["key"])))
+        integ.run(shard, 10, first=first, n_global=64)
+        assert np.array_equal(shard.particles.pos, full_pos[sl])
+
+
+def test_langevin_inertia_lj_trajectory():
+    k = _pkg()
+    from turtlemd_b200.philox import PhiloxNormal
+
+    g = load_golden("traj_langevin_inertia_lj_108.npz")
+    system = _traj_system(g, [_lj()])
+    system.potential_and_force()
+    integ = k["integrators"].LangevinInertia(timestep=float(g["dt"]), gamma=float(g["gamma"]),
+                                             beta=float(g["beta"]), rgen=PhiloxNormal(int(g["key"])))
+    for frame in range(11):
+        _assert_frame(system, g, frame)
+        integ(system)
+
+
+def test_langevin_numpy_generator_host_draw_path():
+    """default_rng draws on the host, as in the reference; compare with the oracle fed the same generator."""
+    k = _pkg()
+    from oracle import turtle_oracle as to
+
+    g = load_golden("traj_langevin_inertia_1d_64.npz")
+    a, b, c = (float(x) for x in g["abc"])
+    dt, gamma, beta = float(g["dt"]), float(g["gamma"]), float(g["beta"])
+    system = _traj_system(g, [k["DoubleWell"](a=a, b=b, c=c)])
+    system.potential_and_force()
+    integ = k["integrators"].LangevinInertia(timestep=dt, gamma=gamma, beta=beta, rgen=np.random.default_rng(123))
+    ff = to.ForceField(np.array([np.inf]), np.zeros(1), [False], [("dw", (a, b, c))])
+    st = to.State(g["pos0"], g["vel0"], g["mass"])
+    to._eval_all(ff, st)
+    stepper = to.InertiaStepper(dt, gamma, beta, np.random.default_rng(123))
+    for _ in range(5):
+        integ(system)
+        stepper.step(st, ff)
+    assert rel_norm(system.particles.pos, st.pos) < TRAJ_TOL
+    assert rel_norm(system.particles.vel, st.vel) < TRAJ_TOL
+
+
+def test_reference_integrator_series():
+    """tests/test_integrators.py:410-562 of the reference (one particle, DoubleWell(1,2,0), dt=0.002)."""
+    k = _pkg()
+    I = k["integrators"]
+    kat = load_golden("reference_kats.npz")
+
+    class FakeRandom:
+        def __init__(self, table, seed):
+            self.table, self.seed = list(table), seed
+
+        def normal(self, loc=0.0, scale=1.0, size=None):
+            out = np.zeros(size)
+            flat = out.reshape(-1)
+            for n in range(flat.size):
+                if self.seed >= len(self.table):
+                    self.seed = 0
+                flat[n] = self.table[self.seed]
+                self.seed += 1
+            return out
+
+    def make():
+        system = k["System"](box=k["Box"](periodic=[False]), particles=k["Particles"](dim=1),
+                             potentials=[k["DoubleWell"](a=1.0, b=2.0, c=0.0)])
+        system.particles.add_particle(pos=np.array([-1.0]), vel=np.array([0.78008020]), name="Ar", mass=1.0, ptype=0)
+        return system
+
+    system, integ = make(), I.VelocityVerlet(timestep=0.002)
+    for i in range(21):
+        assert system.particles.pos[0][0] == pytest.approx(kat["vv_pos"][i])
+        assert system.particles.vel[0][0] == pytest.approx(kat["vv_vel"][i])
+        integ(system)
+    system, integ = make(), I.Verlet(timestep=0.002)
+    prev = np.copy(system.particles.pos)
+    for i in range(5):
+        integ.integration_step(system)
+        assert system.particles.pos[0][0] == pytest.approx(kat["verlet_pos"][i])
+        assert system.particles.vel[0][0] == pytest.approx(kat["verlet_vel"][i])
+        assert prev == pytest.approx(integ.previous_pos)
+        prev = np.copy(system.particles.pos)
+    system = make()
+    integ = I.LangevinOverdamped(timestep=0.002, gamma=0.3, rgen=FakeRandom(kat["fake_table"], 1), beta=1.0)
+    for i in range(51):
+        assert system.particles.pos[0][0] == pytest.approx(kat["over_pos"][i])
+        assert system.particles.vel[0][0] == pytest.approx(kat["over_vel"][i])
+        integ(system)
+    # LangevinInertia with the module-level multivariate_normal monkeypatched (tests/test_integrators.py:552-557)
+    system = make()
+    integ = I.LangevinInertia(timestep=0.002, gamma=0.3, rgen=FakeRandom(kat["fake_table"], 1), beta=1.0)
+
+    def fake_mvn(rgen, mean, cho, dim):
+        norm = rgen.normal(loc=0.0, scale=1.0, size=2 * dim).reshape(dim, 2)
+        return 0.01 * (np.array([mean] * dim) + norm)
+
+    original = I.multivariate_normal
+    I.multivariate_normal = fake_mvn
+    try:
+        for i in range(51):
+            assert system.particles.pos[0][0] == pytest.approx(kat["inertia_pos"][i])
+            assert system.particles.vel[0][0] == pytest.approx(kat["inertia_vel"][i])
+            integ(system)
+    finally:
+        I.multivariate_normal = original
+
+
+def test_reference_md_trajectory_fixture():
+    """tests/simulation/test_mdsimulation.py:98-141 of the reference: md-traj.npy, thermo series."""
+    k = _pkg()
+    from turtlemd_b200.tools import generate_lattice
+
+    kat = load_golden("reference_kats.npz")
+    xyz, size = generate_lattice("fcc", [3, 3, 3], density=0.9)
+    box = k["Box"](low=size[:, 0], high=size[:, 1])
+    part = k["Particles"](dim=box.dim)
+    for pos in xyz:
+        part.add_particle(pos=pos, mass=1.0, name="Ar", ptype=0)
+    part.vel = kat["md_vel"]
+    system = k["System"](box=box, particles=part, potentials=[_lj()])
+    sim = k["MDSimulation"](system, k["integrators"].VelocityVerlet(timestep=0.002), 10)
+    count = 0
+    for i, sysi in enumerate(sim.run()):
+        th = sysi.thermo(boltzmann=1)
+        assert th["temperature"] == pytest.approx(kat["md_temperature"][i])
+        assert th["pressure"] == pytest.approx(kat["md_pressure"][i])
+        assert th["ekin"] == pytest.approx(kat["md_ekin"][i])
+        assert th["vpot"] == pytest.approx(kat["md_vpot"][i])
+        assert sysi.particles.pos == pytest.approx(kat["md_traj"][i][:, :3])
+        assert sysi.particles.vel == pytest.approx(kat["md_traj"][i][:, 3:])
+        count += 1
+    assert count == 11 and sim.cycle["stepno"] == 10
+
+
+def test_host_edits_are_seen_by_the_next_step():
+    """In-place writes into handed-out arrays and rebinding both reach the device (hard part 1)."""
+    k = _pkg()
+    g = load_golden("traj_vv_lj_108.npz")
+    a = _traj_system(g, [_lj()])
+    b = _traj_system(g, [_lj()])
+    integ = k["integrators"].VelocityVerlet(float(g["dt"]))
+    for system in (a, b):
+        system.potential_and_force()
+        integ(system)
+    a.particles.pos[3, 1] += 0.01          # in-place element write
+    a.particles.vel = a.particles.vel * 0.5  # rebinding
+    pos_b = b.particles.pos.copy()
+    pos_b[3, 1] += 0.01
+    b.particles.pos = pos_b
+    b.particles.vel *= 0.5                  # in-place on the handed-out array
+    for system in (a, b):
+        system.potential_and_force()
+        integ(system)
+    assert np.array_equal(a.particles.pos, b.particles.pos)
+    assert np.array_equal(a.particles.vel, b.particles.vel)
+    assert not np.array_equal(a.particles.pos, g["pos"][2])
+
+
+# ---- RNG ---------------------------------------------------------------------------------------------
+
+
+def test_philox_device_stream_is_bit_exact():
+    import ctypes as C
+
+    from oracle import philox_ref as pr
+    from turtlemd_b200 import _device, _lib
+    from turtlemd_b200.philox import PhiloxNormal
+
+    _device.require_cuda()
+    for key, offset, count in ((0, 0, 4096), (2024, 7, 1001), (2**63 + 11, 10**12 + 1, 513)):
+        out = _device.empty(count)
+        rng = _lib.Rng(key, offset)
+        _lib.call("tmd_philox_normal_fill", _device.dptr(out), count, C.byref(rng), _device.stream_ptr())
+        dev = out.cpu().numpy()
+        assert np.array_equal(dev, PhiloxNormal(key, offset).peek(count))      # device == host twin (same source)
+        assert np.array_equal(dev, pr.normals(key, offset, count))             # == independent NumPy oracle
+    raw = PhiloxNormal(99).raw(64)
+    assert np.array_equal(raw, np.random.Philox(key=99).random_raw(64))        # == NumPy's bit generator
+
+
+# ---- sizes of the benchmark configs --------------------------------------------------------------------
+
+
+def _fluid(rep, seed=3):
+    from turtlemd_b200.tools import generate_lattice
+
+    pos, size = generate_lattice("fcc", [rep] * 3, density=0.8)
+    pos = pos + 0.05 * (2.0 * np.random.default_rng(seed).random(pos.shape) - 1.0)
+    return pos, size
+
+
+def test_lj_16k_against_oracle():
+    from oracle import turtle_oracle as to
+
+    k = _pkg()
+    pos, size = _fluid(16)
+    system = k["System"](k["Box"](low=size[:, 0], high=size[:, 1]), k["Particles"].from_arrays(pos), [_lj()])
+    v, f, w = system.potentials[0].potential_and_force(system)
+    length = size[:, 1] - size[:, 0]
+    table, _ = to.lj_tables(SINGLE)
+    vo, fo, wo = to.lj_potential_and_force(pos, np.zeros(len(pos), dtype=int), length, 1.0 / length, [True] * 3, table)
+    assert abs(v - vo) <= TOL * abs(vo) and rel_norm(f, fo) < TOL and rel_norm(w, wo) < TOL
+
+
+def test_lj_32k_benchmark_size_properties():
+    """Config #2 (N=32 000 all-pairs): sampled rows vs the oracle + size-independent properties."""
+    from oracle import turtle_oracle as to
+
+    k = _pkg()
+    pos, size = _fluid(20)
+    assert len(pos) == 32000
+    length = size[:, 1] - size[:, 0]
+    box = k["Box"](low=size[:, 0], high=size[:, 1])
+    system = k["System"](box, k["Particles"].from_arrays(pos), [_lj()])
+    v, f, w = system.potentials[0].potential_and_force(system)
+    rows = np.random.default_rng(5).choice(len(pos), 200, replace=False)
+    table, _ = to.lj_tables(SINGLE)
+    fr, vr = to.lj_rows(pos, np.zeros(len(pos), dtype=int), length, 1.0 / length, [True] * 3, table, rows)
+    assert rel_norm(f[rows], fr) < TOL
+    assert np.max(np.abs(f.sum(axis=0))) < 1e-9 * np.max(np.abs(f))      # Newton's third law
+    assert rel_norm(w, w.T) < 1e-12                                        # symmetric virial
+    # translation by whole box vectors + a rigid shift must not change anything beyond rounding
+    shifted = pos + np.array([3.0, -2.0, 1.0]) * length + 0.123
+    system2 = k["System"](box, k["Particles"].from_arrays(shifted), [_lj()])
+    v2, f2, w2 = system2.potentials[0].potential_and_force(system2)
+    assert abs(v2 - v) <= 1e-9 * abs(v) and rel_norm(f2, f) < 1e-9

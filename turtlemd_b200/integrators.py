@@ -1,0 +1,356 @@
+"""Time integrators (API of ``turtlemd/integrators.py``) over the CUDA kernels.
+
+Every ``integration_step`` enqueues element-wise kernels on the device-resident
+particle arrays and calls :meth:`System.evaluate` for the force field; nothing
+is copied to the host unless the caller reads ``particles.pos`` etc.
+
+Random numbers (``LangevinOverdamped``, ``LangevinInertia``):
+
+* ``rgen`` is a :class:`turtlemd_b200.philox.PhiloxNormal` (or ``rgen=None`` for
+  ``LangevinInertia``, which then uses key = ``seed``): the normals are generated
+  inside the kernel from the counter-based stream; the twin object is advanced
+  by the number of draws the reference would have made.
+* any other object with ``.normal(loc, scale, size)`` (``numpy`` generators, the
+  reference tests' ``FakeRandomGenerator``): the draws are made on the host
+  exactly like the reference makes them (same calls, same order, through the
+  module-level ``multivariate_normal`` looked up at call time), uploaded, and
+  the same kernels consume them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from abc import ABC, abstractmethod
+
+import numpy as np
+from numpy.random import Generator
+
+from . import _device, _lib
+from .philox import PhiloxNormal
+from .potentials.well import DoubleWell
+
+LOGGER = logging.getLogger(__name__)
+LOGGER.addHandler(logging.NullHandler())
+
+_ALL = _lib.WANT_V | _lib.WANT_F | _lib.WANT_W
+
+
+def _arrays(system):
+    """Device tensors (pos, vel, force, imass) and (n, dim) of a system."""
+    _device.require_cuda()
+    part = system.particles
+    n, dim = part._pos.shape
+    return part, n, dim, part._pos.device(), part._vel.device(), part._force.device(), part._imass_device()
+
+
+class MDIntegrator(ABC):
+    """Base class (integrators.py:15-33)."""
+
+    def __init__(self, timestep: float, description: str, dynamics: str):
+        self.timestep = timestep
+        self.description = description
+        self.dynamics = dynamics
+
+    @abstractmethod
+    def integration_step(self, system):
+        """Advance the system one time step."""
+
+    def __call__(self, system):
+        return self.integration_step(system)
+
+
+class Verlet(MDIntegrator):
+    """Position Verlet (integrators.py:36-68); ``previous_pos`` lives on the integrator."""
+
+    def __init__(self, timestep: float):
+        super().__init__(timestep=timestep, description="Verlet integrator", dynamics="NVE")
+        self.timestep_squared = self.timestep**2
+        self.half_idt = 0.5 / self.timestep
+        self._prev = None
+
+    @property
+    def previous_pos(self):
+        return None if self._prev is None else self._prev.host()
+
+    @previous_pos.setter
+    def previous_pos(self, value):
+        self._prev = None if value is None else _device.Mirror(np.asarray(value))
+
+    def integration_step(self, system):
+        part, n, dim, pos, vel, force, imass = _arrays(system)
+        first = self._prev is None
+        if first:
+            self._prev = _device.Mirror(np.zeros(part._pos.shape))
+            prev = self._prev.device_uninitialised(n * dim)
+        else:
+            prev = self._prev.device()
+        _lib.call("tmd_verlet_step", _device.dptr(pos), _device.dptr(vel), _device.dptr(prev),
+                  _device.dptr(force), _device.dptr(imass), n, dim, float(self.timestep),
+                  1 if first else 0, _device.stream_ptr())
+        part._pos.written_on_device()
+        part._vel.written_on_device()
+        self._prev.written_on_device()
+        system.evaluate(_ALL)
+
+
+class VelocityVerlet(MDIntegrator):
+    """Velocity Verlet (integrators.py:71-94)."""
+
+    def __init__(self, timestep: float):
+        super().__init__(timestep=timestep, description="Velocity Verlet integrator", dynamics="NVE")
+        self.half_timestep = self.timestep * 0.5
+
+    def integration_step(self, system):
+        part, n, dim, pos, vel, force, imass = _arrays(system)
+        dt, stream = float(self.timestep), _device.stream_ptr()
+        _lib.call("tmd_vv_kick_drift", _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
+                  _device.dptr(imass), n, dim, dt, stream)
+        part._pos.written_on_device()
+        part._vel.written_on_device()
+        system.evaluate(_ALL)
+        _lib.call("tmd_vv_kick", _device.dptr(vel), _device.dptr(part._force.device()),
+                  _device.dptr(imass), n, dim, dt, stream)
+
+    def run(self, system, steps: int):
+        """``steps`` integration steps without touching the host in between.
+
+        The last half kick of one step and the first half kick + drift of the next are fused into
+        one pass (both roundings kept, so the trajectory is bit-identical to ``steps`` single calls).
+        """
+        if steps <= 0:
+            return
+        part, n, dim, pos, vel, force, imass = _arrays(system)
+        dt, stream = float(self.timestep), _device.stream_ptr()
+        args = (_device.dptr(pos), _device.dptr(vel), _device.dptr(force), _device.dptr(imass), n, dim, dt, stream)
+        _lib.call("tmd_vv_kick_drift", *args)
+        part._pos.written_on_device()
+        part._vel.written_on_device()
+        for _ in range(steps - 1):
+            system.evaluate(_ALL)
+            _lib.call("tmd_vv_kick_kick_drift", _device.dptr(pos), _device.dptr(vel),
+                      _device.dptr(part._force.device()), _device.dptr(imass), n, dim, dt, stream)
+        system.evaluate(_ALL)
+        _lib.call("tmd_vv_kick", _device.dptr(vel), _device.dptr(part._force.device()),
+                  _device.dptr(imass), n, dim, dt, stream)
+
+
+def _is_device_stream(rgen) -> bool:
+    return isinstance(rgen, PhiloxNormal)
+
+
+class LangevinOverdamped(MDIntegrator):
+    """Overdamped Langevin / Brownian dynamics (integrators.py:97-163)."""
+
+    def __init__(self, timestep: float, gamma: float, rgen: Generator, beta: float):
+        super().__init__(timestep=timestep, description="Langevin overdamped integrator", dynamics="stochastic")
+        self.gamma = gamma
+        self.sigma = 0.0
+        self.rgen = rgen
+        self.bddt = 0.0
+        self.beta = beta
+        self._initiate = True
+
+    def initiate_parameters(self, system):
+        """sigma and dt/(m gamma) per particle (integrators.py:137-149); the kernel re-derives them from imass."""
+        if self._initiate:
+            imass = system.particles.imass
+            self.sigma = np.sqrt(2.0 * self.timestep * imass / (self.beta * self.gamma))
+            self.bddt = self.timestep * imass / self.gamma
+            self._initiate = False
+
+    def integration_step(self, system):
+        self.initiate_parameters(system)
+        system.evaluate(_lib.WANT_F | _lib.WANT_W)
+        part, n, dim, pos, vel, force, imass = _arrays(system)
+        rng, noise = None, None
+        if _is_device_stream(self.rgen):
+            rng = _lib.Rng(self.rgen.key, self.rgen.position)
+            self.rgen.advance(n * dim)
+        else:
+            rands = self.rgen.normal(loc=0.0, scale=self.sigma, size=part._vel.shape)
+            noise = _device.to_device(np.asarray(rands, dtype=np.float64))
+        _lib.call("tmd_langevin_overdamped", _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
+                  _device.dptr(imass), n, dim, float(self.timestep), float(self.gamma), float(self.beta),
+                  C.byref(rng) if rng is not None else None, 0,
+                  _device.dptr(noise) if noise is not None else None, _device.stream_ptr())
+        part._pos.written_on_device()
+        part._vel.written_on_device()
+        system.evaluate(_lib.WANT_V | _lib.V_STANDALONE)
+
+
+class LangevinParameter:
+    """Constants of the Langevin integrator (integrators.py:166-177).
+
+    ``mean`` / ``cov`` / ``cho`` are per-particle lists in the reference; here they are built on
+    first access from stacked arrays (a million-element Python list is not something the device
+    path should pay for).
+    """
+
+    def __init__(self):
+        self.c0 = 0.0
+        self.a1 = 0.0
+        self.a2 = np.zeros(1)
+        self.b1 = np.zeros(1)
+        self.b2 = np.zeros(1)
+        self._cov = None
+        self._lists = None
+
+    def _materialise(self):
+        if self._lists is None:
+            if self._cov is None:
+                self._lists = ([], [], [])
+            else:
+                cho = np.linalg.cholesky(self._cov)
+                self._lists = ([np.zeros(2) for _ in self._cov], list(self._cov), list(cho))
+        return self._lists
+
+    @property
+    def mean(self):
+        return self._materialise()[0]
+
+    @property
+    def cov(self):
+        return self._materialise()[1]
+
+    @property
+    def cho(self):
+        return self._materialise()[2]
+
+
+class LangevinInertia(MDIntegrator):
+    """Langevin dynamics with inertia (integrators.py:180-297)."""
+
+    def __init__(self, timestep: float, gamma: float, beta: float, rgen: Generator | None = None, seed: int = 0):
+        super().__init__(timestep=timestep, description="Langevin overdamped integrator", dynamics="stochastic")
+        self.gamma = gamma
+        # reference: default_rng(seed) (PCG64 + ziggurat, a sequential stream).  Here the default
+        # is the counter-based stream with key = seed: same distribution, different numbers.
+        self.rgen = PhiloxNormal(key=seed) if rgen is None else rgen
+        self.beta = beta
+        self._initiate = True
+        self.param = LangevinParameter()
+        self._consts = None
+
+    def initiate_parameters(self, system):
+        """c0, a1, a2, b1, b2 and the noise covariance per particle (integrators.py:223-263)."""
+        if not self._initiate:
+            return
+        dt = self.timestep
+        gamma_dt = self.gamma * dt
+        exp_gdt = np.exp(-gamma_dt)
+        c_0 = exp_gdt
+        c_1 = (1.0 - c_0) / gamma_dt
+        c_2 = (1.0 - c_1) / gamma_dt
+        imasses = system.particles.imass
+        par = self.param
+        par.c0 = c_0
+        par.a1 = c_1 * dt
+        par.a2 = c_2 * dt**2 * imasses
+        par.b1 = (c_1 - c_2) * dt * imasses
+        par.b2 = c_2 * dt * imasses
+        kfac = 2.0 - (3.0 - 4.0 * exp_gdt + exp_gdt**2) / gamma_dt
+        im = imasses[:, 0]
+        sig_r2 = (dt * im / (self.beta * self.gamma)) * kfac
+        sig_v2 = (1.0 - exp_gdt**2) * im / self.beta
+        cov_rv = (im / (self.beta * self.gamma)) * (1.0 - exp_gdt) ** 2
+        cov = np.empty((len(im), 2, 2))
+        cov[:, 0, 0] = sig_r2
+        cov[:, 0, 1] = cov_rv
+        cov[:, 1, 0] = cov_rv
+        cov[:, 1, 1] = sig_v2
+        par._cov = cov
+        par._lists = None
+        consts = _lib.LangevinConsts()
+        consts.c0 = c_0
+        consts.a1 = par.a1
+        consts.a2f = c_2 * dt**2
+        consts.b1f = (c_1 - c_2) * dt
+        consts.b2f = c_2 * dt
+        consts.dt = dt
+        consts.beta = self.beta
+        consts.beta_gamma = self.beta * self.gamma
+        consts.kfac = kfac
+        consts.one_minus_e2 = 1.0 - exp_gdt**2
+        consts.one_minus_e_sq = (1.0 - exp_gdt) ** 2
+        self._consts = consts
+        self._initiate = False
+
+    def draw_random_numbers(self, system):
+        """Host draw of (pos_rand, vel_rand), particle-major like the reference (integrators.py:284-297)."""
+        self.initiate_parameters(system)
+        particles = system.particles
+        shape = particles._pos.shape
+        dim = particles.dim
+        pos_rand = np.zeros(shape)
+        vel_rand = np.zeros(shape)
+        import sys
+
+        draw = sys.modules[__name__].multivariate_normal  # looked up at call time: tests monkeypatch it
+        for i, (meani, choi) in enumerate(zip(self.param.mean, self.param.cho)):
+            randxv = draw(self.rgen, meani, choi, dim)
+            pos_rand[i] = randxv[:, 0]
+            vel_rand[i] = randxv[:, 1]
+        return pos_rand, vel_rand
+
+    def _fusable(self, system) -> bool:
+        pots = system.potentials
+        return _is_device_stream(self.rgen) and len(pots) == 1 and type(pots[0]) is DoubleWell
+
+    def integration_step(self, system):
+        self.initiate_parameters(system)
+        if self._fusable(system):
+            return self.run(system, 1)
+        part, n, dim, pos, vel, force, imass = _arrays(system)
+        stream = _device.stream_ptr()
+        rng, npos, nvel = None, None, None
+        if _is_device_stream(self.rgen):
+            rng = _lib.Rng(self.rgen.key, self.rgen.position)
+            self.rgen.advance(2 * n * dim)
+        else:
+            pos_rand, vel_rand = self.draw_random_numbers(system)
+            npos, nvel = _device.to_device(pos_rand), _device.to_device(vel_rand)
+        _lib.call("tmd_langevin_inertia_pre", _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
+                  _device.dptr(imass), n, dim, C.byref(self._consts),
+                  C.byref(rng) if rng is not None else None, 0,
+                  _device.dptr(npos) if npos is not None else None,
+                  _device.dptr(nvel) if nvel is not None else None, stream)
+        part._pos.written_on_device()
+        part._vel.written_on_device()
+        system.evaluate(_lib.WANT_F | _lib.WANT_W)
+        _lib.call("tmd_langevin_inertia_post", _device.dptr(vel), _device.dptr(part._force.device()),
+                  _device.dptr(imass), n, dim, C.byref(self._consts), stream)
+        system.evaluate(_lib.WANT_V | _lib.V_STANDALONE)
+
+    def run(self, system, steps: int, first: int = 0, n_global: int | None = None):
+        """``steps`` steps in ONE kernel for a DoubleWell-only system with the in-kernel stream.
+
+        ``first`` / ``n_global``: this process holds replicas ``first .. first+n-1`` of an ensemble
+        of ``n_global`` (replica sharding over GPUs); the noise of a replica depends only on its
+        global index and the step, never on the sharding.
+        """
+        self.initiate_parameters(system)
+        if not self._fusable(system):
+            for _ in range(steps):
+                self.integration_step(system)
+            return
+        part, n, dim, pos, vel, force, imass = _arrays(system)
+        n_global = n if n_global is None else n_global
+        pot = system.potentials[0]
+        vw = part._vw_buffer()
+        rng = _lib.Rng(self.rgen.key, self.rgen.position)
+        _lib.call("tmd_langevin_inertia_doublewell", _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
+                  _device.dptr(imass), n, dim, *pot._abc(), C.byref(self._consts), C.byref(rng), first,
+                  n_global, steps, _device.dptr(vw), _device.stream_ptr())
+        self.rgen.advance(2 * n_global * dim * steps)
+        part._pos.written_on_device()
+        part._vel.written_on_device()
+        part._force.written_on_device()
+        part.virial = np.zeros((dim, dim))  # DoubleWell.force returns a zero virial (well.py:80-81)
+        part._vw_fresh.add("v_pot")
+
+
+def multivariate_normal(rgen: Generator, mean: np.ndarray, cho: np.ndarray, dim: int) -> np.ndarray:
+    """``dim`` draws from N(mean, cho cho^T) given the Cholesky factor (integrators.py:300-315)."""
+    norm = rgen.normal(loc=0.0, scale=1.0, size=2 * dim)
+    norm = norm.reshape(dim, 2)
+    return np.array([mean] * dim) + norm @ cho.T
