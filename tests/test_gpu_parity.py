@@ -540,3 +540,114 @@ def test_lj_32k_benchmark_size_properties():
     system2 = k["System"](box, k["Particles"].from_arrays(shifted), [_lj()])
     v2, f2, w2 = system2.potentials[0].potential_and_force(system2)
     assert abs(v2 - v) <= 1e-9 * abs(v) and rel_norm(f2, f) < 1e-9
+
+
+# ---- cell list (K2/K3) ----------------------------------------------------------------------------------
+
+
+def test_lj_cells_against_reference_fixture():
+    """N=4000 (6 cells per direction): the cell-list kernel against the reference's own numbers."""
+    g = load_golden("lj_fcc_4000.npz")
+    system, pot = _lj_system(g, "lj_fcc_4000.npz", method="cells")
+    v, f, w = pot.potential_and_force(system)
+    assert abs(v - g["v_pf"]) <= TOL * abs(g["v_pf"])
+    assert rel_norm(f, g["f_pf"]) < TOL and rel_norm(w, g["w_pf"]) < TOL
+    v2, f2, w2 = pot.potential_and_force(system)
+    assert v2 == v and np.array_equal(f2, f) and np.array_equal(w2, w)  # atomics only rank atoms; sums are ordered
+    vr, fr, wr = system.potential_and_force()
+    assert vr == v and np.array_equal(fr, f)
+    assert abs(system.potential() - g["v_pf"]) <= TOL * abs(g["v_pf"])
+
+
+def test_lj_cells_small_box_is_refused():
+    g = load_golden("lj_fcc_256.npz")
+    system, pot = _lj_system(g, "lj_fcc_256.npz", method="cells")
+    with pytest.raises(NotImplementedError):
+        pot.potential_and_force(system)
+    g = load_golden("lj_slab_256.npz")
+    system, pot = _lj_system(g, "lj_slab_256.npz", method="auto")  # falls back to all-pairs
+    v, f, w = pot.potential_and_force(system)
+    assert rel_norm(f, g["f_pf"]) < TOL
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_lj_cells_equals_allpairs_multitype_unwrapped(dim):
+    k = _pkg()
+    from turtlemd_b200.tools import generate_lattice
+
+    rng = np.random.default_rng(71 + dim)
+    if dim == 3:
+        pos, size = generate_lattice("fcc", [12, 12, 12], density=0.8)
+    else:
+        pos, size = generate_lattice("sq2", [64, 64], density=0.7)
+    length = size[:, 1] - size[:, 0]
+    pos = pos + 0.06 * (2.0 * rng.random(pos.shape) - 1.0) + rng.integers(-2, 3, size=pos.shape) * length
+    ptype = rng.integers(0, 3, size=len(pos))
+    params = {0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}, 1: {"sigma": 1.1, "epsilon": 0.8, "rcut": 2.8},
+              2: {"sigma": 0.9, "epsilon": 1.2, "rcut": 2.2}}
+    out = {}
+    for method in ("allpairs", "cells"):
+        pot = k["LennardJonesCut"](dim=dim, shift=True, mixing="arithmetic", method=method)
+        pot.set_parameters(params)
+        system = k["System"](k["Box"](low=size[:, 0], high=size[:, 1]),
+                             k["Particles"].from_arrays(pos, ptype=ptype), [pot])
+        out[method] = pot.potential_and_force(system)
+    (va, fa, wa), (vc, fc, wc) = out["allpairs"], out["cells"]
+    assert abs(vc - va) <= TOL * abs(va) and rel_norm(fc, fa) < TOL and rel_norm(wc, wa) < TOL
+
+
+def test_lj_row_slabs_add_up():
+    """Atom decomposition: forces of a slab of rows + V/W shares sum to the whole (both kernels)."""
+    import ctypes as C
+
+    from turtlemd_b200 import _device, _lib
+
+    g = load_golden("lj_fcc_4000.npz")
+    for method, fn in (("allpairs", "tmd_lj_allpairs"), ("cells", "tmd_lj_cells")):
+        system, pot = _lj_system(g, "lj_fcc_4000.npz", method=method)
+        v, f, w = pot.potential_and_force(system)
+        _, table, _ = pot._tables(system.particles)
+        box = system.box.to_abi()
+        pos = _device.to_device(g["pos"])
+        force = _device.zeros(g["pos"].size)
+        vw_sum = np.zeros(10)
+        for first, count in ((0, 1500), (1500, 1), (1501, 2499)):
+            vw = _device.zeros(10)
+            _lib.call(fn, _device.dptr(pos), None, 4000, C.byref(box), _lib.hptr(table), 1, 7, first, count,
+                      _device.dptr(force), _device.dptr(vw), _device.stream_ptr())
+            vw_sum += vw.cpu().numpy()
+        assert rel_norm(force.cpu().numpy().reshape(-1, 3), f) < 1e-13
+        assert abs(vw_sum[0] - v) <= 1e-12 * abs(v)
+        assert rel_norm(vw_sum[1:].reshape(3, 3), w) < 1e-12
+
+
+def test_lj_1m_cells_sampled_rows_and_properties():
+    """Config #4 size (N = 1 000 188): sampled rows against the oracle, Newton, symmetric virial."""
+    from oracle import turtle_oracle as to
+
+    k = _pkg()
+    pos, size = _fluid(63)
+    assert len(pos) == 1000188
+    length = size[:, 1] - size[:, 0]
+    pot = k["LennardJonesCut"](dim=3, shift=True, method="cells")
+    pot.set_parameters(SINGLE)
+    system = k["System"](k["Box"](low=size[:, 0], high=size[:, 1]), k["Particles"].from_arrays(pos), [pot])
+    v, f, w = system.potential_and_force()
+    rows = np.random.default_rng(9).choice(len(pos), 48, replace=False)
+    table, _ = to.lj_tables(SINGLE)
+    fr, vr = to.lj_rows(pos, np.zeros(len(pos), dtype=int), length, 1.0 / length, [True] * 3, table, rows)
+    assert rel_norm(f[rows], fr) < TOL
+    assert np.max(np.abs(f.sum(axis=0))) < 1e-8 * np.max(np.abs(f))
+    assert rel_norm(w, w.T) < 1e-12
+    # energy per atom of the jittered fluid is an intensive quantity: compare with the 32k system
+    pos32, size32 = _fluid(20)
+    system32 = k["System"](k["Box"](low=size32[:, 0], high=size32[:, 1]), k["Particles"].from_arrays(pos32), [_lj()])
+    v32 = system32.potential()
+    assert abs(v / len(pos) - v32 / len(pos32)) < 2e-2 * abs(v32 / len(pos32))
+    # ten VelocityVerlet steps conserve energy and keep the centre of mass at rest
+    system.particles.vel = np.random.default_rng(2).standard_normal(pos.shape) * 0.5
+    system.particles.vel -= system.particles.vel.mean(axis=0)
+    e0 = v + 0.5 * np.sum(system.particles.vel**2)
+    k["integrators"].VelocityVerlet(0.002).run(system, 10)
+    e1 = system.particles.v_pot + 0.5 * np.sum(system.particles.vel**2)
+    assert abs(e1 - e0) < 2e-5 * abs(e0)

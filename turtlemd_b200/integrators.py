@@ -110,6 +110,7 @@ class VelocityVerlet(MDIntegrator):
         system.evaluate(_ALL)
         _lib.call("tmd_vv_kick", _device.dptr(vel), _device.dptr(part._force.device()),
                   _device.dptr(imass), n, dim, dt, stream)
+        part._vel.written_on_device()
 
     def run(self, system, steps: int):
         """``steps`` integration steps without touching the host in between.
@@ -129,9 +130,12 @@ class VelocityVerlet(MDIntegrator):
             system.evaluate(_ALL)
             _lib.call("tmd_vv_kick_kick_drift", _device.dptr(pos), _device.dptr(vel),
                       _device.dptr(part._force.device()), _device.dptr(imass), n, dim, dt, stream)
+            part._pos.written_on_device()
+            part._vel.written_on_device()
         system.evaluate(_ALL)
         _lib.call("tmd_vv_kick", _device.dptr(vel), _device.dptr(part._force.device()),
                   _device.dptr(imass), n, dim, dt, stream)
+        part._vel.written_on_device()
 
 
 def _is_device_stream(rgen) -> bool:
@@ -319,6 +323,7 @@ class LangevinInertia(MDIntegrator):
         system.evaluate(_lib.WANT_F | _lib.WANT_W)
         _lib.call("tmd_langevin_inertia_post", _device.dptr(vel), _device.dptr(part._force.device()),
                   _device.dptr(imass), n, dim, C.byref(self._consts), stream)
+        part._vel.written_on_device()
         system.evaluate(_lib.WANT_V | _lib.V_STANDALONE)
 
     def run(self, system, steps: int, first: int = 0, n_global: int | None = None):

@@ -46,7 +46,7 @@ class System:
                 particles.v_pot = 0
             return False
         _device.require_cuda()
-        size = particles._pos.peek().size
+        size = int(np.prod(particles._pos.shape))
         pos = particles._pos.device()
         force = particles._force.device_uninitialised(size) if flags & _lib.WANT_F else None
         vw = particles._vw_buffer()
