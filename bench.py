@@ -4,8 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
 Prints ONE JSON line (rank 0).  Workloads (BASELINE.json configs):
-  lj32k     (default, configs[1]) LJ fluid N=32 000, rc=2.5, VelocityVerlet(0.005), all-pairs kernel
-  lj1m      configs[3] size: LJ fluid N=1 000 188, cell list, VelocityVerlet
+  lj1m      (default; the size BASELINE.json's metric is quoted at) LJ fluid N=1 000 188, rc=2.5,
+            VelocityVerlet(0.005), Verlet neighbour list over a cell grid
+  lj32k     configs[1]: LJ fluid N=32 000, all-pairs kernel
+  lj1m_cells  same as lj1m with the stateless cell-list kernel
   replicas  configs[2]: 1M DoubleWell LangevinInertia replicas (replica-steps/s)
 For --gpus N > 1 (launched by torch.distributed.run) the LJ workloads are atom-decomposed with an
 all-gather of positions each step, the replicas are sharded with no communication.
@@ -39,8 +41,9 @@ SINGLE = {0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}}
 RC, RHO = 2.5, 0.8
 WORKLOADS = {
     "lj32k": dict(rep=20, method="allpairs", dt=0.005, unit="atom-steps/s"),
-    "lj256k": dict(rep=40, method="cells", dt=0.005, unit="atom-steps/s"),
-    "lj1m": dict(rep=63, method="cells", dt=0.005, unit="atom-steps/s"),
+    "lj256k": dict(rep=40, method="nlist", dt=0.005, unit="atom-steps/s"),
+    "lj1m": dict(rep=63, method="nlist", dt=0.005, unit="atom-steps/s"),
+    "lj1m_cells": dict(rep=63, method="cells", dt=0.005, unit="atom-steps/s"),
     "replicas": dict(n=1_000_000, dt=0.002, unit="replica-steps/s"),
 }
 
@@ -58,7 +61,9 @@ def lj_inputs(rep):
 
 
 def algorithmic_flops(n, method):
-    """21 flop per pair check + 36 per pair inside the cut-off (FMA = 2)."""
+    """21 flop per pair check + 36 per pair inside the cut-off (FMA = 2).  The pair
+    checks are those of the reference algorithm (all pairs) for lj32k and of a half-stencil cell list
+    with edge rc for the O(N) methods, whatever the kernel actually does."""
     hits = n * (4.0 / 3.0) * math.pi * RC**3 * RHO / 2.0
     checks = n * (n - 1) / 2.0 if method == "allpairs" else n * 27.0 * RC**3 * RHO / 2.0
     return 21.0 * checks + 36.0 * hits
@@ -176,11 +181,12 @@ def bench_lj(args, cfg, rank, world):
     else:
         system.evaluate(7)
         step = lambda: integ(system)  # noqa: E731
-        launches_per_step = 6 if cfg["method"] == "allpairs" else None
     for _ in range(args.warmup):
         step()
+    launches0 = _lib.launch_count()
     with ClockSampler(torch.cuda.current_device()) as clocks:
         sec = timed(step, args.steps, world)
+    launches = _lib.launch_count() - launches0
     value = n * args.steps / sec
 
     out = {
@@ -193,7 +199,7 @@ def bench_lj(args, cfg, rank, world):
                    "n_atoms": n, "parallelism": f"atom-decomposition x{world}" if world > 1 else "single GPU",
                    "l2": "inputs (0.75 MB of positions) are L2-resident by nature of the workload; "
                          "the kernel is FP64-pipe bound, no L2 flush between steps"},
-        "clocks": clocks.summary(),
+        "clocks": clocks.summary(), "gpu_launches": launches,
     }
     if rank != 0:
         return None
@@ -204,21 +210,28 @@ def bench_lj(args, cfg, rank, world):
         tf, ms = C.c_double(0), C.c_double(0)
         _lib.check(lib.tmd_bench_dfma(5, C.byref(tf), C.byref(ms)))
         peak = tf.value
-        evaluate = lambda: system.evaluate(7)  # noqa: E731  (wrap + pair kernel + finish + reduce)
+        # the force evaluation alone, positions unchanged (for nlist: gather/check + traversal, no rebuild)
+        evaluate = lambda: system.evaluate(7)  # noqa: E731
         for _ in range(3):
             evaluate()
         ksec = timed(evaluate, args.steps, 1) / args.steps
         flops = algorithmic_flops(n, cfg["method"])
         achieved = flops / ksec / 1e12
+        kernel = {"allpairs": "lj_allpairs_kernel<3,7>", "cells": "lj_cells_kernel<3>",
+                  "nlist": "nl_force_kernel<3,true>"}[cfg["method"]]
         out["roofline"] = {
             "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None,
-            "kernel": "lj_allpairs_kernel<3,7>" if cfg["method"] == "allpairs" else "lj_cells_kernel",
+            "traffic": None, "kernel": kernel,
             "algorithmic_flops_per_launch": flops, "launch_ms": ksec * 1e3,
+            "step_frac": flops / (sec / args.steps) / 1e12 / peak,
+            "note": "algorithmic flops = SURVEY.md 8(d): 21 per pair check of a half-stencil cell list (all pairs "
+                    "for lj32k) + 36 per pair inside the cut-off; launch_ms = one whole force evaluation "
+                    "(all kernels of System.evaluate), step_frac = the same flops over the full timed step",
             "peak_source": "DFMA-only micro-benchmark (tmd_bench_dfma) run in this process; "
                            "MEASURED_PEAKS.json has no FP64 entry (nominal 37.2 TFLOP/s)",
         }
-        out["gpu_launches"] = (launches_per_step or 0) * args.steps
+        if cfg["method"] == "nlist":
+            out["config"]["nlist"] = dict(pot.nlist_stats(), skin=pot.skin)
 
         # e2e: host arrays every step through the public API
         hp, hv, hf = (_device.pinned_array(pos.shape) for _ in range(3))
@@ -361,7 +374,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="lj32k", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="lj1m", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = WORKLOADS[args.workload]

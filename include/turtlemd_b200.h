@@ -87,6 +87,8 @@ int tmd_set_device(int device);
 /* name[<=256]; sm = 10*major+minor; bytes of HBM; number of SMs */
 int tmd_device_info(int device, char *name, int *sm, size_t *total_mem, int *num_sms);
 int tmd_stream_synchronize(tmd_stream_t stream);
+/* kernels this library has launched so far in this process (all devices, all streams) */
+int tmd_launch_count(int64_t *launches);
 
 /* device memory + copies for bindings that do not bring their own allocator */
 int tmd_malloc(void **dptr, size_t bytes);
@@ -123,6 +125,27 @@ int tmd_lj_allpairs(const double *pos, const int32_t *tidx, int64_t n, const tmd
  * reference's single-nearest-image rule); tmd_lj_cells_usable() tells in advance.               */
 int tmd_lj_cells_usable(int64_t n, const tmd_box *box, const double *table, int32_t ntypes, int *usable);
 int tmd_lj_cells(const double *pos, const int32_t *tidx, int64_t n, const tmd_box *box,
+                 const double *table, int32_t ntypes, uint32_t flags,
+                 int64_t first, int64_t count,
+                 double *force, double *vw, tmd_stream_t stream);
+
+/* K2+K3 with a persistent Verlet neighbour list (the fast large-N path).  The handle keeps the
+ * per-atom candidate lists (all pairs within rcut+skin at build time) and reuses them while no
+ * atom has moved more than skin/2 since the build; the displacement check, the rebuild and the
+ * traversal are all stream-ordered (no host round trip).  Forces are those of the full evaluation:
+ * the list is an acceleration structure, not an approximation, and a row whose list outgrew its
+ * capacity is evaluated from the cells instead (slow, still exact).  Same box requirements as
+ * tmd_lj_cells with rcut+skin as the cell edge (tmd_lj_nlist_usable).  One handle per
+ * (system, potential, device); not thread-safe.                                                  */
+typedef struct tmd_nlist tmd_nlist;
+int tmd_nlist_create(tmd_nlist **out, double skin);
+int tmd_nlist_destroy(tmd_nlist *nl);
+int tmd_lj_nlist_usable(int64_t n, const tmd_box *box, const double *table, int32_t ntypes, double skin,
+                        int *usable);
+/* builds done / calls made / rows that outgrew the list capacity (cumulative over builds; they
+ * take the slow exact path).  Synchronises the device.                                           */
+int tmd_nlist_stats(tmd_nlist *nl, int64_t *builds, int64_t *calls, int32_t *overflow);
+int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t n, const tmd_box *box,
                  const double *table, int32_t ntypes, uint32_t flags,
                  int64_t first, int64_t count,
                  double *force, double *vw, tmd_stream_t stream);

@@ -293,7 +293,7 @@ def test_langevin_doublewell_replicas(kind, dim, draws):
     for frame in range(11):
         _assert_frame(system, g, frame)
         integ(system)
-    assert rgen.position == 10 * 64 * dim * (2 if kind == "inertia" else 1)
+    assert rgen.position == 11 * 64 * dim * (2 if kind == "inertia" else 1)  # 11 steps were taken
 
 
 def test_langevin_fused_multi_step_equals_single_steps():
@@ -596,6 +596,134 @@ def test_lj_cells_equals_allpairs_multitype_unwrapped(dim):
     assert abs(vc - va) <= TOL * abs(va) and rel_norm(fc, fa) < TOL and rel_norm(wc, wa) < TOL
 
 
+# ---- Verlet neighbour list (the large-N path) ---------------------------------------------------------------
+
+
+def test_lj_nlist_against_reference_fixture():
+    """N=4000: the neighbour-list path (device-resident System methods) against the reference's numbers."""
+    g = load_golden("lj_fcc_4000.npz")
+    system, pot = _lj_system(g, "lj_fcc_4000.npz", method="nlist")
+    v, f, w = system.potential_and_force()
+    assert abs(v - g["v_pf"]) <= TOL * abs(g["v_pf"])
+    assert rel_norm(f, g["f_pf"]) < TOL and rel_norm(w, g["w_pf"]) < TOL
+    v2, f2, w2 = system.potential_and_force()  # second call reuses the list
+    assert v2 == v and np.array_equal(f2, f) and np.array_equal(w2, w)
+    f3, w3 = system.force()
+    assert np.array_equal(f3, f) and rel_norm(w3, g["w_pf"]) < TOL
+    assert abs(system.potential() - g["v_pf"]) <= TOL * abs(g["v_pf"])
+    stats = pot.nlist_stats()
+    assert stats["builds"] == 1 and stats["calls"] == 4 and stats["slow_rows"] == 0
+    # host-array plug-in call of the same potential object (stateless cells kernel) agrees
+    vh, fh, wh = pot.potential_and_force(system)
+    assert abs(vh - v) <= 1e-13 * abs(v) and rel_norm(fh, f) < 1e-13 and rel_norm(wh, w) < 1e-12
+
+
+def test_lj_nlist_small_box_is_refused():
+    g = load_golden("lj_fcc_256.npz")
+    system, pot = _lj_system(g, "lj_fcc_256.npz", method="nlist")
+    with pytest.raises(NotImplementedError):
+        system.potential_and_force()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_lj_nlist_equals_allpairs_multitype_unwrapped(dim):
+    """Three types with different cut-offs, coordinates several boxes away from the origin cell."""
+    k = _pkg()
+    from turtlemd_b200.tools import generate_lattice
+
+    rng = np.random.default_rng(171 + dim)
+    if dim == 3:
+        pos, size = generate_lattice("fcc", [12, 12, 12], density=0.8)
+    else:
+        pos, size = generate_lattice("sq2", [64, 64], density=0.7)
+    length = size[:, 1] - size[:, 0]
+    pos = pos + 0.06 * (2.0 * rng.random(pos.shape) - 1.0) + rng.integers(-2, 3, size=pos.shape) * length
+    ptype = rng.integers(0, 3, size=len(pos))
+    params = {0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}, 1: {"sigma": 1.1, "epsilon": 0.8, "rcut": 2.8},
+              2: {"sigma": 0.9, "epsilon": 1.2, "rcut": 2.2}}
+    out = {}
+    for method in ("allpairs", "nlist"):
+        pot = k["LennardJonesCut"](dim=dim, shift=True, mixing="arithmetic", method=method, skin=0.25)
+        pot.set_parameters(params)
+        system = k["System"](k["Box"](low=size[:, 0], high=size[:, 1]),
+                             k["Particles"].from_arrays(pos, ptype=ptype), [pot])
+        out[method] = system.potential_and_force()
+    (va, fa, wa), (vc, fc, wc) = out["allpairs"], out["nlist"]
+    assert abs(vc - va) <= TOL * abs(va) and rel_norm(fc, fa) < TOL and rel_norm(wc, wa) < TOL
+    assert rel_norm(wc, wc.T) == 0.0
+
+
+def test_lj_nlist_trajectory_rebuilds_and_matches_allpairs():
+    """60 VelocityVerlet steps of a hot fluid: the list is rebuilt on the device several times and the
+    trajectory stays on the all-pairs one (1e-8 after 60 steps; chaos amplifies the 1e-16 differences)."""
+    k = _pkg()
+    pos, size = _fluid(10)  # N = 4000
+    vel = np.random.default_rng(4).standard_normal(pos.shape) * 1.2
+    vel -= vel.mean(axis=0)
+    out = {}
+    for method in ("allpairs", "nlist"):
+        pot = k["LennardJonesCut"](dim=3, shift=True, method=method, skin=0.3)
+        pot.set_parameters(SINGLE)
+        system = k["System"](k["Box"](low=size[:, 0], high=size[:, 1]),
+                             k["Particles"].from_arrays(pos, vel=vel), [pot])
+        system.potential_and_force()
+        integ = k["integrators"].VelocityVerlet(0.004)
+        for _ in range(6):
+            integ.run(system, 10)
+        out[method] = (system.particles.pos.copy(), system.particles.vel.copy(), system.particles.v_pot,
+                       system.particles.virial.copy(), pot.nlist_stats())
+    (xa, va, ea, wa, _), (xn, vn, en, wn, stats) = out["allpairs"], out["nlist"]
+    assert rel_norm(xn, xa) < TRAJ_TOL and rel_norm(vn, va) < 1e-6
+    assert abs(en - ea) <= 1e-8 * abs(ea) and rel_norm(wn, wa) < 1e-7
+    assert stats["calls"] == 61 and 2 <= stats["builds"] < 40, stats
+
+
+def test_lj_nlist_list_overflow_takes_the_exact_slow_path():
+    """Half of the box empty, the other half at twice the mean density: most lists outgrow the capacity
+    (sized from the mean density) and those rows are evaluated from the cells -- same numbers."""
+    k = _pkg()
+    from turtlemd_b200.tools import generate_lattice
+
+    pos, size = generate_lattice("fcc", [8, 8, 16], density=1.0)
+    pos = pos + 0.04 * (2.0 * np.random.default_rng(8).random(pos.shape) - 1.0)
+    size = size.copy()
+    size[2, 1] *= 2.6  # the lattice fills the lower 38 % of the box
+    out = {}
+    for method in ("allpairs", "nlist"):
+        pot = k["LennardJonesCut"](dim=3, shift=True, method=method, skin=0.4)
+        pot.set_parameters(SINGLE)
+        system = k["System"](k["Box"](low=size[:, 0], high=size[:, 1]), k["Particles"].from_arrays(pos), [pot])
+        out[method] = system.potential_and_force() + (pot.nlist_stats(),)
+    (va, fa, wa, _), (vn, fn, wn, stats) = out["allpairs"], out["nlist"]
+    assert stats["slow_rows"] > 100, stats
+    assert abs(vn - va) <= TOL * abs(va) and rel_norm(fn, fa) < TOL and rel_norm(wn, wa) < TOL
+
+
+def test_lj_nlist_follows_host_edits_and_box_changes():
+    """Positions rewritten on the host (teleporting atoms) and a rescaled box both invalidate the list."""
+    k = _pkg()
+    pos, size = _fluid(10)
+    pot = k["LennardJonesCut"](dim=3, shift=True, method="nlist")
+    pot.set_parameters(SINGLE)
+    ref = k["LennardJonesCut"](dim=3, shift=True, method="allpairs")
+    ref.set_parameters(SINGLE)
+    box = k["Box"](low=size[:, 0], high=size[:, 1])
+    system = k["System"](box, k["Particles"].from_arrays(pos), [pot])
+    system.potential_and_force()
+    rng = np.random.default_rng(12)
+    moved = pos.copy()
+    moved[rng.choice(len(pos), 50, replace=False)] += rng.uniform(-3.0, 3.0, size=(50, 3))
+    system.particles.pos = moved
+    v, f, w = system.potential_and_force()
+    vr, fr, wr = ref.potential_and_force(system)
+    assert abs(v - vr) <= TOL * abs(vr) and rel_norm(f, fr) < TOL and rel_norm(w, wr) < TOL
+    system.box = k["Box"](low=size[:, 0], high=size[:, 1] * 1.03)
+    v, f, w = system.potential_and_force()
+    vr, fr, wr = ref.potential_and_force(system)
+    assert abs(v - vr) <= TOL * abs(vr) and rel_norm(f, fr) < TOL and rel_norm(w, wr) < TOL
+    assert pot.nlist_stats()["builds"] == 3
+
+
 def test_lj_row_slabs_add_up():
     """Atom decomposition: forces of a slab of rows + V/W shares sum to the whole (both kernels)."""
     import ctypes as C
@@ -603,8 +731,8 @@ def test_lj_row_slabs_add_up():
     from turtlemd_b200 import _device, _lib
 
     g = load_golden("lj_fcc_4000.npz")
-    for method, fn in (("allpairs", "tmd_lj_allpairs"), ("cells", "tmd_lj_cells")):
-        system, pot = _lj_system(g, "lj_fcc_4000.npz", method=method)
+    for method, fn in (("allpairs", "tmd_lj_allpairs"), ("cells", "tmd_lj_cells"), ("nlist", "tmd_lj_nlist")):
+        system, pot = _lj_system(g, "lj_fcc_4000.npz", method="cells" if method == "nlist" else method)
         v, f, w = pot.potential_and_force(system)
         _, table, _ = pot._tables(system.particles)
         box = system.box.to_abi()
@@ -613,15 +741,23 @@ def test_lj_row_slabs_add_up():
         vw_sum = np.zeros(10)
         for first, count in ((0, 1500), (1500, 1), (1501, 2499)):
             vw = _device.zeros(10)
-            _lib.call(fn, _device.dptr(pos), None, 4000, C.byref(box), _lib.hptr(table), 1, 7, first, count,
+            handle = ()
+            if method == "nlist":  # one list per slab, as one rank of an atom decomposition keeps
+                h = C.c_void_p()
+                _lib.call("tmd_nlist_create", C.byref(h), 0.3)
+                handle = (h,)
+            _lib.call(fn, *handle, _device.dptr(pos), None, 4000, C.byref(box), _lib.hptr(table), 1, 7, first, count,
                       _device.dptr(force), _device.dptr(vw), _device.stream_ptr())
             vw_sum += vw.cpu().numpy()
+            if handle:
+                _lib.call("tmd_nlist_destroy", handle[0])
         assert rel_norm(force.cpu().numpy().reshape(-1, 3), f) < 1e-13
         assert abs(vw_sum[0] - v) <= 1e-12 * abs(v)
         assert rel_norm(vw_sum[1:].reshape(3, 3), w) < 1e-12
 
 
-def test_lj_1m_cells_sampled_rows_and_properties():
+@pytest.mark.parametrize("method", ["cells", "nlist"])
+def test_lj_1m_sampled_rows_and_properties(method):
     """Config #4 size (N = 1 000 188): sampled rows against the oracle, Newton, symmetric virial."""
     from oracle import turtle_oracle as to
 
@@ -629,7 +765,7 @@ def test_lj_1m_cells_sampled_rows_and_properties():
     pos, size = _fluid(63)
     assert len(pos) == 1000188
     length = size[:, 1] - size[:, 0]
-    pot = k["LennardJonesCut"](dim=3, shift=True, method="cells")
+    pot = k["LennardJonesCut"](dim=3, shift=True, method=method)
     pot.set_parameters(SINGLE)
     system = k["System"](k["Box"](low=size[:, 0], high=size[:, 1]), k["Particles"].from_arrays(pos), [pot])
     v, f, w = system.potential_and_force()

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "tmd_set_device": [C.c_int],
     "tmd_device_info": [C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int)],
     "tmd_stream_synchronize": [_P],
+    "tmd_launch_count": [C.POINTER(_I64)],
     "tmd_malloc": [C.POINTER(_P), C.c_size_t],
     "tmd_free": [_P],
     "tmd_memset_async": [_P, C.c_int, C.c_size_t, _P],
@@ -80,6 +81,11 @@ PROTOTYPES = {
     "tmd_lj_allpairs": [_P, _P, _I64, _BOX, _P, _I32, _U32, _I64, _I64, _P, _P, _P],
     "tmd_lj_cells_usable": [_I64, _BOX, _P, _I32, C.POINTER(C.c_int)],
     "tmd_lj_cells": [_P, _P, _I64, _BOX, _P, _I32, _U32, _I64, _I64, _P, _P, _P],
+    "tmd_nlist_create": [C.POINTER(_P), _D],
+    "tmd_nlist_destroy": [_P],
+    "tmd_lj_nlist_usable": [_I64, _BOX, _P, _I32, _D, C.POINTER(C.c_int)],
+    "tmd_nlist_stats": [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I32)],
+    "tmd_lj_nlist": [_P, _P, _P, _I64, _BOX, _P, _I32, _U32, _I64, _I64, _P, _P, _P],
     "tmd_doublewell": [_P, _I64, _I32, _D, _D, _D, _U32, _P, _P, _P],
     "tmd_dwpair": [_P, _I64, _BOX, _P, _I32, _P, _I32, _I32, _D, _D, _D, _U32, _P, _P, _P],
     "tmd_vv_kick_drift": [_P, _P, _P, _P, _I64, _I32, _D, _P],
@@ -151,6 +157,13 @@ def check(status: int) -> None:
 
 def call(name: str, *args) -> None:
     check(getattr(load(), name)(*args))
+
+
+def launch_count() -> int:
+    """Kernels launched by the library so far in this process."""
+    n = C.c_int64(0)
+    call("tmd_launch_count", C.byref(n))
+    return n.value
 
 
 def device_count() -> int:

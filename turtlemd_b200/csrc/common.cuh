@@ -59,6 +59,8 @@ enum ArenaSlot {
 };
 int arena_get(ArenaSlot slot, size_t bytes, void **ptr);
 int num_sms();
+// every kernel launch of the library goes through this (tmd_launch_count: bench.py's gpu_launches)
+void count_launch();
 
 static inline cudaStream_t as_stream(tmd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

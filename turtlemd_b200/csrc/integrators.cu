@@ -108,7 +108,7 @@ static int launch_vv(double *pos, double *vel, const double *force, const double
     const Launch l = ew_launch(total);
     const double half = dt * 0.5;  // VelocityVerlet.half_timestep (integrators.py:82)
 #define TMD_VV(D, V)                                                                         \
-    vv_kernel<D, V, KICKS, DRIFT><<<l.blocks, l.threads, 0, stream>>>(pos, vel, force, imass, \
+    ::tmd::count_launch(), vv_kernel<D, V, KICKS, DRIFT><<<l.blocks, l.threads, 0, stream>>>(pos, vel, force, imass, \
                                                                       total, dt, half)
     if (dim == 1) { if (vec) TMD_VV(1, true); else TMD_VV(1, false); }
     else if (dim == 2) { if (vec) TMD_VV(2, true); else TMD_VV(2, false); }
@@ -380,7 +380,7 @@ int tmd_verlet_step(double *pos, double *vel, double *prev, const double *force,
     const double dt2 = dt * dt, half_idt = 0.5 / dt;  // integrators.py:49-50 (timestep**2 == dt*dt in IEEE)
     cudaStream_t s = as_stream(stream);
 #define TMD_VERLET(D, V) \
-    verlet_kernel<D, V><<<l.blocks, l.threads, 0, s>>>(pos, vel, prev, force, imass, total, dt, dt2, half_idt, first_call)
+    ::tmd::count_launch(), verlet_kernel<D, V><<<l.blocks, l.threads, 0, s>>>(pos, vel, prev, force, imass, total, dt, dt2, half_idt, first_call)
     if (dim == 1) { if (vec) TMD_VERLET(1, true); else TMD_VERLET(1, false); }
     else if (dim == 2) { if (vec) TMD_VERLET(2, true); else TMD_VERLET(2, false); }
     else { if (vec) TMD_VERLET(3, true); else TMD_VERLET(3, false); }
@@ -403,7 +403,7 @@ int tmd_langevin_overdamped(double *pos, double *vel, const double *force, const
     const uint64_t q_base = rng ? rng->offset + (uint64_t)first * (uint64_t)dim : 0;
     cudaStream_t s = as_stream(stream);
 #define TMD_OD(D, V, H) \
-    overdamped_kernel<D, V, H><<<l.blocks, l.threads, 0, s>>>(pos, vel, force, imass, total, dt, gamma, beta, key, q_base, noise)
+    ::tmd::count_launch(), overdamped_kernel<D, V, H><<<l.blocks, l.threads, 0, s>>>(pos, vel, force, imass, total, dt, gamma, beta, key, q_base, noise)
 #define TMD_OD_D(D)                                                        \
     do {                                                                   \
         if (noise) { if (vec) TMD_OD(D, true, true); else TMD_OD(D, false, true); } \
@@ -433,7 +433,7 @@ int tmd_langevin_inertia_pre(double *pos, double *vel, const double *force, cons
     const uint64_t q_base = rng ? rng->offset + 2ull * (uint64_t)first * (uint64_t)dim : 0;
     cudaStream_t s = as_stream(stream);
 #define TMD_IP(D, V, H) \
-    inertia_pre_kernel<D, V, H><<<l.blocks, l.threads, 0, s>>>(pos, vel, force, imass, total, *consts, key, q_base, noise_pos, noise_vel)
+    ::tmd::count_launch(), inertia_pre_kernel<D, V, H><<<l.blocks, l.threads, 0, s>>>(pos, vel, force, imass, total, *consts, key, q_base, noise_pos, noise_vel)
 #define TMD_IP_D(D)                                                            \
     do {                                                                       \
         if (noise_pos) { if (vec) TMD_IP(D, true, true); else TMD_IP(D, false, true); } \
@@ -456,7 +456,7 @@ int tmd_langevin_inertia_post(double *vel, const double *force, const double *im
     const bool vec = aligned16(vel) && aligned16(force);
     const Launch l = ew_launch(total);
     cudaStream_t s = as_stream(stream);
-#define TMD_IPO(D, V) inertia_post_kernel<D, V><<<l.blocks, l.threads, 0, s>>>(vel, force, imass, total, consts->b2f)
+#define TMD_IPO(D, V) ::tmd::count_launch(), inertia_post_kernel<D, V><<<l.blocks, l.threads, 0, s>>>(vel, force, imass, total, consts->b2f)
     if (dim == 1) { if (vec) TMD_IPO(1, true); else TMD_IPO(1, false); }
     else if (dim == 2) { if (vec) TMD_IPO(2, true); else TMD_IPO(2, false); }
     else { if (vec) TMD_IPO(3, true); else TMD_IPO(3, false); }
@@ -485,7 +485,7 @@ int tmd_langevin_inertia_doublewell(double *pos, double *vel, double *force, con
     const uint64_t q_base = rng->offset + 2ull * (uint64_t)first * (uint64_t)dim;
     const uint64_t q_step = 2ull * (uint64_t)n_global * (uint64_t)dim;
 #define TMD_IDW(D) \
-    inertia_doublewell_kernel<D><<<blocks, 256, 0, s>>>(pos, vel, force, imass, total, a, b, c, *consts, rng->key, q_base, q_step, nsteps, partials)
+    ::tmd::count_launch(), inertia_doublewell_kernel<D><<<blocks, 256, 0, s>>>(pos, vel, force, imass, total, a, b, c, *consts, rng->key, q_base, q_step, nsteps, partials)
     if (dim == 1) TMD_IDW(1); else if (dim == 2) TMD_IDW(2); else TMD_IDW(3);
 #undef TMD_IDW
     TMD_CUDA(cudaGetLastError());
@@ -518,7 +518,7 @@ int tmd_philox_normal_fill(double *out, int64_t count, const tmd_rng *rng, tmd_s
     TMD_CHECK(require_device());
     if (count == 0) return TMD_OK;
     const int blocks = (int)((count + 255) / 256);
-    normal_fill_kernel<<<blocks, 256, 0, as_stream(stream)>>>(out, count, rng->key, rng->offset);
+    ::tmd::count_launch(), normal_fill_kernel<<<blocks, 256, 0, as_stream(stream)>>>(out, count, rng->key, rng->offset);
     TMD_CUDA(cudaGetLastError());
     return TMD_OK;
 }
@@ -551,9 +551,9 @@ int tmd_kinetic_tensor(const double *vel, const double *mass, int64_t n, int32_t
     double *partials = nullptr, *vw = nullptr;
     TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)blocks * 10 * sizeof(double), (void **)&partials));
     TMD_CHECK(arena_get(SLOT_MISC, 10 * sizeof(double), (void **)&vw));
-    if (dim == 1) kinetic_kernel<1><<<blocks, 256, 0, s>>>(vel, mass, n, partials);
-    else if (dim == 2) kinetic_kernel<2><<<blocks, 256, 0, s>>>(vel, mass, n, partials);
-    else kinetic_kernel<3><<<blocks, 256, 0, s>>>(vel, mass, n, partials);
+    if (dim == 1) ::tmd::count_launch(), kinetic_kernel<1><<<blocks, 256, 0, s>>>(vel, mass, n, partials);
+    else if (dim == 2) ::tmd::count_launch(), kinetic_kernel<2><<<blocks, 256, 0, s>>>(vel, mass, n, partials);
+    else ::tmd::count_launch(), kinetic_kernel<3><<<blocks, 256, 0, s>>>(vel, mass, n, partials);
     TMD_CUDA(cudaGetLastError());
     TMD_CHECK(launch_reduce_vw(partials, blocks, 0.5, TMD_WANT_W, vw, s));
     TMD_CUDA(cudaMemcpyAsync(kin, vw + 1, 9 * sizeof(double), cudaMemcpyDeviceToDevice, s));

@@ -225,7 +225,7 @@ int launch_lj_finish(const double *partial_f, int n_split, int64_t count, int di
     const int64_t total = count * dim;
     if (total == 0) return TMD_OK;
     const int blocks = (int)((total + 255) / 256);
-    lj_finish_kernel<<<blocks, 256, 0, stream>>>(partial_f, n_split, total, first * dim, flags, force);
+    ::tmd::count_launch(), lj_finish_kernel<<<blocks, 256, 0, stream>>>(partial_f, n_split, total, first * dim, flags, force);
     TMD_CUDA(cudaGetLastError());
     return TMD_OK;
 }
@@ -255,7 +255,7 @@ template <int DIM>
 static int run_allpairs(AllPairsArgs &a, int pmask, int blocks, cudaStream_t s) {
 #define TMD_AP(P)                                                                        \
     case P:                                                                              \
-        if constexpr ((P) < (1 << DIM)) lj_allpairs_kernel<DIM, P><<<blocks, kRows, 0, s>>>(a); \
+        if constexpr ((P) < (1 << DIM)) ::tmd::count_launch(), lj_allpairs_kernel<DIM, P><<<blocks, kRows, 0, s>>>(a); \
         break;
     switch (pmask & ((1 << DIM) - 1)) {
         TMD_AP(0)
@@ -327,9 +327,9 @@ extern "C" int tmd_lj_allpairs(const double *pos, const int32_t *tidx, int64_t n
     a.wrapped = wrapped;
 
     const int wblocks = (int)((n + 255) / 256);
-    if (dim == 1) lj_wrap_kernel<1><<<wblocks, 256, 0, s>>>(pos, n, a.box, pmask, wrapped);
-    else if (dim == 2) lj_wrap_kernel<2><<<wblocks, 256, 0, s>>>(pos, n, a.box, pmask, wrapped);
-    else lj_wrap_kernel<3><<<wblocks, 256, 0, s>>>(pos, n, a.box, pmask, wrapped);
+    if (dim == 1) ::tmd::count_launch(), lj_wrap_kernel<1><<<wblocks, 256, 0, s>>>(pos, n, a.box, pmask, wrapped);
+    else if (dim == 2) ::tmd::count_launch(), lj_wrap_kernel<2><<<wblocks, 256, 0, s>>>(pos, n, a.box, pmask, wrapped);
+    else ::tmd::count_launch(), lj_wrap_kernel<3><<<wblocks, 256, 0, s>>>(pos, n, a.box, pmask, wrapped);
     TMD_CUDA(cudaGetLastError());
 
     if (dim == 1) TMD_CHECK(run_allpairs<1>(a, pmask, blocks, s));

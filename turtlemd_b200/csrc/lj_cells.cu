@@ -21,113 +21,12 @@
 // ~3/4 of the lanes active instead of ~1/7.  One thread owns one atom: no atomics on forces.
 #include <string.h>
 
-#include "lj_common.cuh"
+#include "cell_build.cuh"
 
 namespace tmd {
 
 constexpr int kCellThreads = 128;
 constexpr int kHitCap = 96;  // per-thread candidate list (mean ~52 at rho=0.8, rc=2.5)
-
-struct CellGrid {
-    int nc[3];
-    int ncells;
-    double len[3], ilen[3];
-    double scale[3];  // nc / L
-};
-
-struct CellArgs {
-    const double *pos;
-    const int32_t *tidx;
-    int64_t n, first, count;
-    int ntypes;
-    uint32_t flags;
-    CellGrid grid;
-    int *counts;      // [ncells + 1]
-    int *starts;      // [ncells + 1]
-    int *cell_of;     // [n]
-    int *rank_of;     // [n]
-    int *order;       // [n] slot -> atom
-    int *slot_of;     // [n] atom -> slot
-    double4 *wrapped; // [n] by atom
-    double4 *sorted;  // [n] by slot; .w carries the type index
-    double rc2max;
-    double *force;
-    double *partial_vw;
-    LjTable tab;
-};
-
-template <int DIM>
-__global__ void __launch_bounds__(256) cell_assign_kernel(CellArgs a) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    double x[3] = {0.0, 0.0, 0.0};
-    int c[3] = {0, 0, 0};
-#pragma unroll
-    for (int k = 0; k < DIM; ++k) {
-        const double v = a.pos[i * DIM + k];
-        const double w = fma(-floor(v * a.grid.ilen[k]), a.grid.len[k], v);  // into [0, L) up to rounding
-        int ck = (int)(w * a.grid.scale[k]);
-        ck = ck < 0 ? 0 : (ck >= a.grid.nc[k] ? a.grid.nc[k] - 1 : ck);
-        x[k] = w;
-        c[k] = ck;
-    }
-    const int cell = (c[2] * a.grid.nc[1] + c[1]) * a.grid.nc[0] + c[0];
-    const int t = (a.ntypes > 1) ? a.tidx[i] : 0;
-    a.wrapped[i] = make_double4(x[0], x[1], x[2], __longlong_as_double((long long)t));
-    a.cell_of[i] = cell;
-    a.rank_of[i] = atomicAdd(&a.counts[cell], 1);
-}
-
-// exclusive scan of counts[0..ncells) into starts[0..ncells]; one block
-__global__ void __launch_bounds__(1024) cell_scan_kernel(const int *__restrict__ counts, int *__restrict__ starts,
-                                                         int ncells) {
-    __shared__ int s_sum[1024];
-    const int tid = threadIdx.x;
-    const int per = (ncells + 1023) / 1024;
-    const int lo = tid * per, hi = min(lo + per, ncells);
-    int local = 0;
-    for (int c = lo; c < hi; ++c) local += counts[c];
-    s_sum[tid] = local;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
-        int v = (tid >= off) ? s_sum[tid - off] : 0;
-        __syncthreads();
-        s_sum[tid] += v;
-        __syncthreads();
-    }
-    int run = s_sum[tid] - local;
-    for (int c = lo; c < hi; ++c) {
-        starts[c] = run;
-        run += counts[c];
-    }
-    if (tid == 1023) starts[ncells] = s_sum[1023];
-}
-
-__global__ void __launch_bounds__(256) cell_scatter_kernel(CellArgs a) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    a.order[a.starts[a.cell_of[i]] + a.rank_of[i]] = (int)i;
-}
-
-__global__ void __launch_bounds__(128) cell_sort_kernel(CellArgs a) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.grid.ncells) return;
-    const int lo = a.starts[c], hi = a.starts[c + 1];
-    for (int p = lo + 1; p < hi; ++p) {  // insertion sort, ~13 atoms per cell
-        const int key = a.order[p];
-        int q = p - 1;
-        while (q >= lo && a.order[q] > key) {
-            a.order[q + 1] = a.order[q];
-            --q;
-        }
-        a.order[q + 1] = key;
-    }
-    for (int p = lo; p < hi; ++p) {
-        const int i = a.order[p];
-        a.sorted[p] = a.wrapped[i];
-        a.slot_of[i] = p;
-    }
-}
 
 template <int DIM>
 __global__ void __launch_bounds__(kCellThreads, 4) lj_cells_kernel(const CellArgs a) {
@@ -268,31 +167,6 @@ __global__ void __launch_bounds__(kCellThreads, 4) lj_cells_kernel(const CellArg
     }
 }
 
-static bool make_grid(const tmd_box *box, double rc2max, CellGrid &g) {
-    if (!(rc2max > 0.0)) return false;
-    const double edge = sqrt(rc2max) * (1.0 + 1e-6);  // slack: an atom on a face may land in either cell
-    long long ncells = 1;
-    for (int k = 0; k < 3; ++k) {
-        g.nc[k] = 1;
-        g.len[k] = g.ilen[k] = g.scale[k] = 0.0;
-    }
-    for (int k = 0; k < box->dim; ++k) {
-        if (!box->periodic[k]) return false;
-        const double len = box->length[k];
-        if (!(len > 0.0) || len != len || len > 1e300) return false;
-        const double q = floor(len / edge);
-        if (q < 3.0) return false;  // fewer than 3 cells: the stencil would see an atom twice
-        g.nc[k] = q > 2048.0 ? 2048 : (int)q;
-        g.len[k] = len;
-        g.ilen[k] = box->ilength[k];
-        g.scale[k] = g.nc[k] / len;
-        ncells *= g.nc[k];
-    }
-    if (ncells > (1ll << 30)) return false;
-    g.ncells = (int)ncells;
-    return true;
-}
-
 }  // namespace tmd
 
 using namespace tmd;
@@ -306,7 +180,7 @@ extern "C" int tmd_lj_cells_usable(int64_t n, const tmd_box *box, const double *
     double rc2max = 0.0;
     TMD_CHECK(load_lj_table(table, ntypes, tab, rc2max));
     CellGrid g;
-    if (n >= 2 && n < (1ll << 27) && make_grid(box, rc2max, g)) *usable = 1;
+    if (n >= 2 && n < (1ll << 27) && make_grid(box, sqrt(rc2max), g)) *usable = 1;
     return TMD_OK;
 }
 
@@ -325,7 +199,7 @@ extern "C" int tmd_lj_cells(const double *pos, const int32_t *tidx, int64_t n, c
 
     CellArgs a;
     TMD_CHECK(load_lj_table(table, ntypes, a.tab, a.rc2max));
-    if (n < 2 || n >= (1ll << 27) || !make_grid(box, a.rc2max, a.grid)) {
+    if (n < 2 || n >= (1ll << 27) || !make_grid(box, sqrt(a.rc2max), a.grid)) {
         set_error("tmd_lj_cells: needs a fully periodic box with >= 3 cells of edge rcut per direction "
                   "and 2 <= n < 2^27; use tmd_lj_allpairs");
         return TMD_ERR_UNSUPPORTED;
@@ -356,15 +230,10 @@ extern "C" int tmd_lj_cells(const double *pos, const int32_t *tidx, int64_t n, c
     TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)blocks * 10 * sizeof(double), (void **)&a.partial_vw));
 
     // ---- K2 ----
-    TMD_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)(ncells + 1) * sizeof(int), s));
-    const int nb = (int)((n + 255) / 256);
-    if (dim == 1) cell_assign_kernel<1><<<nb, 256, 0, s>>>(a);
-    else if (dim == 2) cell_assign_kernel<2><<<nb, 256, 0, s>>>(a);
-    else cell_assign_kernel<3><<<nb, 256, 0, s>>>(a);
-    cell_scan_kernel<<<1, 1024, 0, s>>>(a.counts, a.starts, ncells);
-    cell_scatter_kernel<<<nb, 256, 0, s>>>(a);
-    cell_sort_kernel<<<(ncells + 127) / 128, 128, 0, s>>>(a);
-    TMD_CUDA(cudaGetLastError());
+    a.gate = nullptr;
+    a.image = nullptr;
+    a.sortedf = nullptr;
+    TMD_CHECK(launch_cell_build(a, dim, s));
 
     // ---- K3 ----
     const size_t smem = (size_t)kHitCap * kCellThreads * sizeof(unsigned);
@@ -375,9 +244,9 @@ extern "C" int tmd_lj_cells(const double *pos, const int32_t *tidx, int64_t n, c
         else TMD_CUDA(cudaFuncSetAttribute(lj_cells_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[dim - 1] = true;
     }
-    if (dim == 1) lj_cells_kernel<1><<<blocks, kCellThreads, smem, s>>>(a);
-    else if (dim == 2) lj_cells_kernel<2><<<blocks, kCellThreads, smem, s>>>(a);
-    else lj_cells_kernel<3><<<blocks, kCellThreads, smem, s>>>(a);
+    if (dim == 1) ::tmd::count_launch(), lj_cells_kernel<1><<<blocks, kCellThreads, smem, s>>>(a);
+    else if (dim == 2) ::tmd::count_launch(), lj_cells_kernel<2><<<blocks, kCellThreads, smem, s>>>(a);
+    else ::tmd::count_launch(), lj_cells_kernel<3><<<blocks, kCellThreads, smem, s>>>(a);
     TMD_CUDA(cudaGetLastError());
     // every pair was visited from both of its atoms
     return launch_reduce_vw(a.partial_vw, blocks, 0.5, flags, vw, s);

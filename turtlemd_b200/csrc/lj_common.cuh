@@ -55,16 +55,21 @@ struct PairAcc {
 
 // The body of the reference's row loop for ONE pair whose exact rsq passed the cut-off test
 // (lennardjones.py:253-272).  d = r_i - r_j after minimum image.
-template <int DIM>
+// FAST = false: the all-pairs path; r6inv through a compensated cube (tracks NumPy's pow), the full
+//               dim x dim virial accumulated entry by entry like np.einsum("ij,ik->jk") does.
+// FAST = true : the cell / neighbour-list paths, where this body IS the hot loop: plain products,
+//               and only the upper triangle of the (mathematically symmetric) virial -- the caller
+//               mirrors it.  Differences to FAST = false are at the 1e-16 level.
+template <int DIM, bool FAST = false>
 __device__ __forceinline__ void lj_pair(const double (&d)[3], double rsq, double lj1, double lj2, double lj3,
                                         double lj4, double offset, uint32_t flags, PairAcc &acc) {
     double r2inv, r6inv;
     if (flags & TMD_V_STANDALONE) {
         r2inv = 0.0;
-        r6inv = __ddiv_rn(1.0, cube_cr(rsq));  // potential(): 1.0 / rsq**3  (:172)
+        r6inv = __ddiv_rn(1.0, FAST ? (rsq * rsq) * rsq : cube_cr(rsq));  // potential(): 1.0 / rsq**3  (:172)
     } else {
-        r2inv = __ddiv_rn(1.0, rsq);           // :254
-        r6inv = cube_cr(r2inv);                // :255
+        r2inv = __ddiv_rn(1.0, rsq);                            // :254
+        r6inv = FAST ? (r2inv * r2inv) * r2inv : cube_cr(r2inv);  // :255
     }
     if (flags & TMD_WANT_V)                    // r6inv*(lj3*r6inv - lj4) - offset  (:276-282)
         acc.v += __dsub_rn(__dmul_rn(r6inv, __dsub_rn(__dmul_rn(lj3, r6inv), lj4)), offset);
@@ -77,10 +82,17 @@ __device__ __forceinline__ void lj_pair(const double (&d)[3], double rsq, double
             acc.f[a] += fa;                          // :270
             if (flags & TMD_WANT_W) {
 #pragma unroll
-                for (int b = 0; b < DIM; ++b) acc.w[a * 3 + b] = fma(fa, d[b], acc.w[a * 3 + b]);  // :272
+                for (int b = (FAST ? a : 0); b < DIM; ++b) acc.w[a * 3 + b] = fma(fa, d[b], acc.w[a * 3 + b]);  // :272
             }
         }
     }
+}
+
+// FAST accumulates the upper triangle only: copy it down before reducing.
+__device__ __forceinline__ void mirror_virial(PairAcc &acc) {
+    acc.w[3] = acc.w[1];
+    acc.w[6] = acc.w[2];
+    acc.w[7] = acc.w[5];
 }
 
 // force[first+r] (=|+=) sum over splits of partial[s][r], fixed order.

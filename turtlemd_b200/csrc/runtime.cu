@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -36,6 +37,9 @@ int require_device() {
     }
     return TMD_OK;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- arena ---------------------------------------------------------------------------------
 struct Arena {
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(256) reduce_vw_kernel(const double *__restrict
 
 int launch_reduce_vw(const double *partials, int nblocks, double scale, uint32_t flags, double *vw,
                      cudaStream_t stream) {
-    reduce_vw_kernel<<<1, 256, 0, stream>>>(partials, nblocks, scale, flags, vw);
+    ::tmd::count_launch(), reduce_vw_kernel<<<1, 256, 0, stream>>>(partials, nblocks, scale, flags, vw);
     TMD_CUDA(cudaGetLastError());
     return TMD_OK;
 }
@@ -155,6 +159,12 @@ const char *tmd_status_string(int status) {
         case TMD_ERR_NOMEM: return "out of device memory";
         default: return "unknown status";
     }
+}
+
+int tmd_launch_count(int64_t *launches) {
+    TMD_REQUIRE(launches != nullptr, "launches is NULL");
+    *launches = g_launches.load(std::memory_order_relaxed);
+    return TMD_OK;
 }
 
 int tmd_device_count(int *count) {
@@ -270,7 +280,7 @@ int tmd_bench_dfma(int32_t repeats, double *tflops, double *milliseconds) {
     double best = 1e30;
     for (int r = 0; r < repeats + 2; ++r) {
         TMD_CUDA(cudaEventRecord(e0, 0));
-        dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0 + r);
+        ::tmd::count_launch(), dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0 + r);
         TMD_CUDA(cudaEventRecord(e1, 0));
         TMD_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;
@@ -303,7 +313,7 @@ int tmd_bench_copy(size_t bytes, int32_t repeats, double *gbs, double *milliseco
     const int blocks = num_sms() * 16;
     for (int r = 0; r < repeats + 2; ++r) {
         cudaEventRecord(e0, 0);
-        copy_kernel<<<blocks, 256>>>(src, dst, n2);
+        ::tmd::count_launch(), copy_kernel<<<blocks, 256>>>(src, dst, n2);
         cudaEventRecord(e1, 0);
         cudaEventSynchronize(e1);
         float ms = 0.f;

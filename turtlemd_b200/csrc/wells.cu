@@ -142,7 +142,7 @@ int tmd_doublewell(const double *pos, int64_t n, int32_t dim, double a, double b
     if (blocks < 1) blocks = 1;
     double *partials = nullptr;
     TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)blocks * 10 * sizeof(double), (void **)&partials));
-    doublewell_kernel<<<blocks, 256, 0, s>>>(pos, total, a, b, c, flags, force, partials);
+    ::tmd::count_launch(), doublewell_kernel<<<blocks, 256, 0, s>>>(pos, total, a, b, c, flags, force, partials);
     TMD_CUDA(cudaGetLastError());
     // virial = zeros (well.py:80-81): the W partials are all zero, so TMD_WANT_W defines W = 0 (+ old W)
     return launch_reduce_vw(partials, blocks, 1.0, flags, vw, s);
@@ -168,7 +168,7 @@ int tmd_dwpair(const double *pos, int64_t n, const tmd_box *box, const int32_t *
     // the kernel adds into force[] (zeroed above when overwriting)
     const uint32_t kflags = flags | TMD_ACCUMULATE;
 #define TMD_DWP(D) \
-    dwpair_kernel<D><<<blocks, 128, 0, s>>>(pos, bd, idx0, n0, idx1, n1, same_type, rwidth, width2, height, kflags, force, partials)
+    ::tmd::count_launch(), dwpair_kernel<D><<<blocks, 128, 0, s>>>(pos, bd, idx0, n0, idx1, n1, same_type, rwidth, width2, height, kflags, force, partials)
     if (box->dim == 1) TMD_DWP(1); else if (box->dim == 2) TMD_DWP(2); else TMD_DWP(3);
 #undef TMD_DWP
     TMD_CUDA(cudaGetLastError());

@@ -7,11 +7,17 @@ dictionaries); evaluation is the CUDA library:
 * ``potential`` / ``force`` / ``potential_and_force`` take the system's host
   arrays through the host-buffer entry point ``tmd_host_lj`` -- this is the
   plug-in boundary a reference maintainer would bind;
-* ``_launch`` enqueues ``tmd_lj_allpairs`` / ``tmd_lj_cells`` on device-resident
-  arrays for ``System.evaluate`` and the integrators.
+* ``_launch`` enqueues ``tmd_lj_allpairs`` / ``tmd_lj_cells`` / ``tmd_lj_nlist`` on
+  device-resident arrays for ``System.evaluate`` and the integrators.
 
-Extra, optional constructor argument (reference scripts run unchanged without
-it): ``method`` = "auto" | "allpairs" | "cells".
+Extra, optional constructor arguments (reference scripts run unchanged without
+them): ``method`` = "auto" | "allpairs" | "cells" | "nlist" and ``skin`` (the
+Verlet-list margin of the "nlist" method, in length units).  "auto" picks the
+neighbour list for device-resident loops and the stateless cell list for
+one-off host calls when the box holds >= 3 cells per direction and there are at
+least ``CELLS_MIN_ATOMS`` atoms; otherwise all-pairs.  All methods evaluate the
+same pairs (the list is rebuilt on the device whenever an atom moved more than
+skin/2), so the choice changes speed, not results.
 """
 from __future__ import annotations
 
@@ -29,7 +35,8 @@ from .well import host_positions
 LOGGER = logging.getLogger(__name__)
 LOGGER.addHandler(logging.NullHandler())
 
-_METHODS = {"auto": 0, "allpairs": 1, "cells": 2}
+_METHODS = {"auto": 0, "allpairs": 1, "cells": 2, "nlist": 2}  # value = tmd_host_lj method code
+DEFAULT_SKIN = 0.3
 CELLS_MIN_ATOMS = 4096  # "auto": below this the all-pairs kernel is used even when cells would fit
 
 
@@ -37,13 +44,16 @@ class LennardJonesCut(Potential):
     """Lennard-Jones 6-12 potential with a cut-off, per type-pair parameters."""
 
     def __init__(self, dim: int = 3, shift: bool = True, mixing: str = "geometric",
-                 desc: str = "Lennard-Jones pair potential", method: str = "auto"):
+                 desc: str = "Lennard-Jones pair potential", method: str = "auto",
+                 skin: float = DEFAULT_SKIN):
         super().__init__(dim=dim, desc=desc)
         if method not in _METHODS:
             raise ValueError(f'Unknown method "{method}", expected one of {sorted(_METHODS)}')
         self.shift = shift
         self.mixing = mixing
         self.method = method
+        self.skin = float(skin)
+        self._nlist = None  # tmd_nlist handle (device-resident path)
         self._lj1: dict = {}
         self._lj2: dict = {}
         self._lj3: dict = {}
@@ -116,12 +126,53 @@ class LennardJonesCut(Potential):
         self._cache = (ptype, types, table, tidx)
         return types, table, tidx
 
+    def __del__(self):
+        handle, self._nlist = getattr(self, "_nlist", None), None
+        if handle is not None:
+            try:
+                _lib.load().tmd_nlist_destroy(handle)
+            except Exception:  # interpreter shutdown
+                pass
+
+    def _nlist_handle(self):
+        if self._nlist is None:
+            handle = C.c_void_p()
+            _lib.call("tmd_nlist_create", C.byref(handle), self.skin)
+            self._nlist = handle
+        return self._nlist
+
+    def nlist_stats(self) -> dict:
+        """{"builds", "calls", "slow_rows"} of the neighbour list (synchronises); zeros if unused."""
+        builds, calls, slow = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        if self._nlist is not None:
+            _lib.call("tmd_nlist_stats", self._nlist, C.byref(builds), C.byref(calls), C.byref(slow))
+        return {"builds": builds.value, "calls": calls.value, "slow_rows": slow.value}
+
+    def _kernel_for(self, npart, box_abi, table, ntyp) -> str:
+        """Entry point for the device-resident path."""
+        if self.method == "allpairs":
+            return "tmd_lj_allpairs"
+        if self.method == "cells":
+            self._use_cells(npart, box_abi, table, ntyp)
+            return "tmd_lj_cells"
+        usable = C.c_int(0)
+        _lib.call("tmd_lj_nlist_usable", npart, C.byref(box_abi), _lib.hptr(table), ntyp, self.skin,
+                  C.byref(usable))
+        if self.method == "nlist":
+            if not usable.value:
+                raise NotImplementedError(
+                    "neighbour list needs >= 3 cells of edge rcut+skin in every direction and a fully periodic box")
+            return "tmd_lj_nlist"
+        if usable.value and npart >= CELLS_MIN_ATOMS:
+            return "tmd_lj_nlist"
+        return "tmd_lj_cells" if self._use_cells(npart, box_abi, table, ntyp) else "tmd_lj_allpairs"
+
     def _use_cells(self, npart, box_abi, table, ntyp) -> bool:
         if self.method == "allpairs":
             return False
         usable = C.c_int(0)
         _lib.call("tmd_lj_cells_usable", npart, C.byref(box_abi), _lib.hptr(table), ntyp, C.byref(usable))
-        if self.method == "cells":
+        if self.method in ("cells", "nlist"):
             if not usable.value:
                 raise NotImplementedError(
                     "cell list needs >= 3 cells of edge rcut in every direction and a fully periodic box")
@@ -147,9 +198,10 @@ class LennardJonesCut(Potential):
         box_abi = system.box.to_abi()
         tidx_dev = particles._static_device(f"lj_tidx_{id(self)}", tidx, np.int32) if ntyp > 1 else None
         count = npart if count is None else count
-        name = "tmd_lj_cells" if self._use_cells(npart, box_abi, table, ntyp) else "tmd_lj_allpairs"
+        name = self._kernel_for(npart, box_abi, table, ntyp)
+        handle = (self._nlist_handle(),) if name == "tmd_lj_nlist" else ()
         _lib.call(
-            name, _device.dptr(pos), _device.dptr(tidx_dev) if tidx_dev is not None else None, npart,
+            name, *handle, _device.dptr(pos), _device.dptr(tidx_dev) if tidx_dev is not None else None, npart,
             C.byref(box_abi), _lib.hptr(table), ntyp, flags, first, count,
             _device.dptr(force) if force is not None else None, _device.dptr(vw), _device.stream_ptr(),
         )
