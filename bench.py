@@ -167,7 +167,8 @@ def bench_lj(args, cfg, rank, world):
     pos, vel, size = lj_inputs(cfg["rep"])
     n = len(pos)
     box = Box(low=size[:, 0], high=size[:, 1])
-    pot = LennardJonesCut(dim=3, shift=True, method=cfg["method"])
+    extra = {} if args.skin is None else {"skin": args.skin}
+    pot = LennardJonesCut(dim=3, shift=True, method=cfg["method"], **extra)
     pot.set_parameters(SINGLE)
     system = System(box, Particles.from_arrays(pos, vel=vel), [pot])
     integ = VelocityVerlet(cfg["dt"])
@@ -233,6 +234,8 @@ def bench_lj(args, cfg, rank, world):
         if cfg["method"] == "nlist":
             out["config"]["nlist"] = dict(pot.nlist_stats(), skin=pot.skin)
 
+        if args.quick:
+            return out
         # e2e: host arrays every step through the public API
         hp, hv, hf = (_device.pinned_array(pos.shape) for _ in range(3))
         part = system.particles
@@ -375,6 +378,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="lj1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--skin", type=float, default=None, help="neighbour-list skin (default: the package default)")
+    ap.add_argument("--quick", action="store_true", help="tuning runs: skip the e2e and cpu_baseline legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = WORKLOADS[args.workload]

@@ -4,19 +4,20 @@
 // the per-atom candidate lists are kept between calls in a tmd_nlist handle and reused while no
 // atom has moved more than skin/2 since they were built (then every pair closer than rcut is still
 // listed, so forces are those of the full evaluation -- this is an acceleration structure, not an
-// approximation).  Everything is stream-ordered, there is no host round trip:
+// approximation).  Everything is stream-ordered, there is no host round trip.  Per call:
 //
 //   gather    xs[slot] = pos[atom] - image[atom]  (32-byte records in cell order; the lattice
 //   + check   vector `image` is frozen at build time, so coordinates stay continuous between
 //             builds) and, in the same pass, |xs[slot] - build position|^2 > (skin/2)^2 -> flag
-//   build     every kernel returns at once unless the flag is set:
-//             bin a wrapped copy into cells of edge >= rcut+skin (cell_build.cuh), then one thread
-//             per row atom walks its 3^dim cells with a conservative SINGLE-precision distance
-//             filter and appends (neighbour slot | image code << 27) to its list; lists are stored
-//             transposed (entry k of all rows contiguous) so the traversal reads them coalesced
-//   traverse  one thread per row atom: ~75 candidates, 6 FP64 instructions each to the exact
-//             cut-off test (strict rsq < rcut2, lennardjones.py:291-294), ~70 % pass.  Per-thread
-//             force accumulators, no atomics, fixed order -> bit-reproducible.
+//   build     two kernels that return at once unless the flag is set.  (1) one cooperative kernel,
+//             phases separated by grid syncs: bin a wrapped copy into cells (edge >=
+//             (rcut+skin)/H, H = 1), exclusive scan, scatter, per-cell ordering by atom index (so
+//             nothing depends on how the ranking atomics resolved).  (2) one thread per row atom walks
+//             the (2H+1)^dim cells around it with a conservative SINGLE-precision filter and appends
+//             to its row-major list eight entries per 32-byte store, ascending by (stencil row, slot).
+//   traverse  G lanes per row atom, persistent blocks; 6 FP64 instructions per candidate to the exact
+//             cut-off test (strict rsq < rcut2, lennardjones.py:291-294), ~70 % pass.  Per-lane force
+//             accumulators, shuffle reduction in a fixed order, no atomics -> bit-reproducible.
 //
 // Virial.  The reference sums f (x) delta over pairs (lennardjones.py:272).  With delta_ij =
 // x_i - x_j - S_ij (S = the lattice vector of the image) and f_ij = -f_ji this equals
@@ -26,13 +27,65 @@
 //
 // A row whose candidate count exceeds the list capacity is not truncated: its count is stored
 // as-is and the traversal walks the build-time cells for that row instead (slow, exact).
-//
-// FP64-pipe bound; HBM/L2 traffic per atom-step: list indices (~4 B x 75) + records (32 B) + force.
+#include <cooperative_groups.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
 
-#include "cell_build.cuh"
+#include "lj_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace tmd {
+
+constexpr int kNlThreads = 128;
+constexpr unsigned kSlotMask = 0x07FFFFFFu;
+constexpr int kHomeCode = 13;  // (0,0,0) shift
+constexpr int kBinThreads = 256;           // cooperative binning kernel
+constexpr int kScanChunk = kBinThreads * 8;
+
+struct NlGrid {
+    int nc[3];
+    int ncells;
+    int h;            // stencil half width in cells
+    double len[3], ilen[3];
+    double scale[3];  // nc / L
+};
+
+struct NlArgs {
+    const double *pos;
+    const int32_t *tidx;
+    int64_t n, first, count;
+    int ntypes;
+    uint32_t flags;
+    NlGrid grid;
+    int *nlflags;        // [0] rebuild, [1] rows on the slow path, [2] builds, [3] calls
+    int *counts;         // [ncells]     zero between builds
+    int *starts;         // [ncells + 1]
+    int *chunk_sums;     // [ceil(ncells / kScanChunk)]
+    int *cell_of;        // [n] by atom
+    int *rank_of;        // [n] by atom
+    int *order;          // [n] slot -> atom
+    int *order_tmp;      // [n] provisional order of a rebuild
+    int *slot_of;        // [n] atom -> slot
+    double4 *wrapped;    // [n] by atom: wrapped position at build time, .w = type
+    double4 *xb;         // [n] by slot: the same, in cell order (build positions)
+    float4 *xbf;         // [n] by slot: single-precision copy for the list filter
+    double4 *xs;         // [n] by slot: current positions (image removed), .w = type
+    double *image;       // [n*3] by atom: lattice vector removed when wrapping
+    unsigned *entries;   // [rows][cap]
+    int *nneigh;         // [rows]
+    int cap;
+    float reach2f;       // conservative single-precision filter radius^2
+    double half_skin2;
+    double centre[3];
+    double *force;
+    double *partial_vw;
+    LjTable tab;
+};
+
+}  // namespace tmd
 
 struct tmd_nlist {
     double skin;
@@ -43,35 +96,20 @@ struct tmd_nlist {
     double len[3];
     double reach;
     // device memory, owned
-    int *flags;          // [0] rebuild, [1] rows on the slow path, [2] builds, [3] calls
-    unsigned *entries;   // [cap][stride]
-    int *nneigh;         // [stride]
-    int *ints;           // counts, starts, cell_of, rank_of, order, slot_of
-    double4 *wrapped, *sorted, *xs;
-    float4 *sortedf;
-    double *image;       // [n*3]
-    int64_t cap_n, cap_rows, cap_cells;
-    int cap, stride;
-};
-
-namespace tmd {
-
-constexpr int kNlThreads = 128;
-constexpr unsigned kSlotMask = 0x07FFFFFFu;
-constexpr int kHomeCode = 13;  // (0,0,0) shift
-
-struct NlArgs {
-    CellArgs c;
-    const int *gate;
     int *flags;
     unsigned *entries;
     int *nneigh;
-    int cap, stride;
-    float reach2f;       // conservative single-precision filter radius^2
-    double4 *xs;
-    double half_skin2;
-    double centre[3];
+    int *ints;           // counts, starts, chunk_sums, cell_of, rank_of, order, slot_of, order_tmp
+    double4 *wrapped, *xb, *xs;
+    float4 *xbf;
+    double *image;
+    int64_t cap_n, cap_rows, cap_cells;
+    int cap;
+    int build_blocks[3];  // list-kernel grid per dim (0 = not yet queried)
+    int bin_blocks[3];    // cooperative binning grid per dim
 };
+
+namespace tmd {
 
 // 1/x to <= 1 ulp: MUFU.RCP64H seed (2^-23) + two Newton steps.  x is a squared distance inside
 // the cut-off: positive, normal.
@@ -84,17 +122,30 @@ __device__ __forceinline__ double rcp_fast(double x) {
     return fma(r, e, r);
 }
 
+// 32-byte record in one 256-bit load (LDG.E.256 on sm_100a); xs is not written while a traversal runs
+__device__ __forceinline__ double4 ld_record(const double4 *p) {
+    double4 v;
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void st_entries8(unsigned *p, const unsigned (&e)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(e[0]), "r"(e[1]), "r"(e[2]),
+                 "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7])
+                 : "memory");
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(256) nl_gather_check_kernel(const double *__restrict__ pos,
                                                               const double *__restrict__ image,
                                                               const int *__restrict__ order,
-                                                              const double4 *__restrict__ sorted, int64_t n,
+                                                              const double4 *__restrict__ xb, int64_t n,
                                                               double half_skin2, double4 *__restrict__ xs,
                                                               int *flags) {
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n) return;
     const int atom = order[slot];
-    const double4 b = sorted[slot];  // position at build time, .w = type
+    const double4 b = xb[slot];  // position at build time, .w = type
     double x[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < DIM; ++k) x[k] = pos[(int64_t)atom * DIM + k] - image[(int64_t)atom * 3 + k];
@@ -105,173 +156,283 @@ __global__ void __launch_bounds__(256) nl_gather_check_kernel(const double *__re
     if (!(r <= half_skin2)) flags[0] = 1;  // also catches NaN
 }
 
-// after a (gated) build the records ARE the build positions
-static __global__ void __launch_bounds__(256) nl_copy_sorted_kernel(const double4 *__restrict__ sorted,
-                                                                    double4 *__restrict__ xs, int64_t n,
-                                                                    const int *gate) {
-    TMD_GATE(gate)
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot < n) xs[slot] = sorted[slot];
+// ---- stencil walk shared by the list build and the traversal's slow path -------------------------
+// Calls body(jbegin, jend, code) for every run of consecutive slots of the (2H+1)^DIM cells around
+// cell (c0, c1, c2); code = image shift of that run as (sx+1) + 3 (sy+1) + 9 (sz+1).  Cells of one
+// x-row are consecutive in slot order, so a row is one run (up to three where it wraps).
+template <int DIM, typename Body>
+__device__ __forceinline__ void for_each_run(const NlGrid &g, const int *__restrict__ starts, int c0, int c1, int c2,
+                                             Body body) {
+    const int h = g.h;
+    const int hz = DIM > 2 ? h : 0, hy = DIM > 1 ? h : 0;
+    for (int dz = -hz; dz <= hz; ++dz) {
+        int z = c2 + dz, sz = 0;
+        if (z < 0) { z += g.nc[2]; sz = -1; }
+        else if (z >= g.nc[2]) { z -= g.nc[2]; sz = 1; }
+        for (int dy = -hy; dy <= hy; ++dy) {
+            int y = c1 + dy, sy = 0;
+            if (y < 0) { y += g.nc[1]; sy = -1; }
+            else if (y >= g.nc[1]) { y -= g.nc[1]; sy = 1; }
+            const int rowbase = (z * g.nc[1] + y) * g.nc[0];
+            const int yz = 3 * (sy + 1) + 9 * (sz + 1);
+            const int lo = c0 - h, hi = c0 + h;
+            if (lo < 0) body(starts[rowbase + lo + g.nc[0]], starts[rowbase + g.nc[0]], 0 + yz);
+            body(starts[rowbase + (lo < 0 ? 0 : lo)], starts[rowbase + (hi >= g.nc[0] ? g.nc[0] : hi + 1)], 1 + yz);
+            if (hi >= g.nc[0]) body(starts[rowbase], starts[rowbase + hi - g.nc[0] + 1], 2 + yz);
+        }
+    }
 }
 
-struct Stencil {
-    int ncell;
-    unsigned code;
-    float sx, sy, sz;   // shift folded into the row atom (single precision filter)
-};
-
-template <int DIM>
-__device__ __forceinline__ void neighbour_cell(const CellGrid &g, int c0, int c1, int c2, int dx, int dy, int dz,
-                                               int &ncell, int (&sh)[3]) {
-    int nb[3] = {c0 + dx, c1 + dy, c2 + dz};
-    sh[0] = sh[1] = sh[2] = 0;
+// kBinThreads threads; returns the exclusive prefix of v over the block, total = block sum
+__device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp, int &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) {
-        if (nb[k] < 0) { nb[k] += g.nc[k]; sh[k] = -1; }
-        else if (nb[k] >= g.nc[k]) { nb[k] -= g.nc[k]; sh[k] = 1; }
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
     }
-    ncell = (nb[2] * g.nc[1] + nb[1]) * g.nc[0] + nb[0];
-}
-
-template <int DIM>
-__global__ void __launch_bounds__(kNlThreads) nl_build_kernel(const NlArgs a) {
-    TMD_GATE(a.gate)
-    const CellArgs &c = a.c;
-    const int64_t row = (int64_t)blockIdx.x * kNlThreads + threadIdx.x;
-    if (row >= c.count) return;
-    const bool whole = c.first == 0 && c.count == c.n;
-    const int slot = whole ? (int)row : c.slot_of[c.first + row];
-    const int atom = whole ? c.order[slot] : (int)(c.first + row);
-    const float4 me = c.sortedf[slot];
-    const int cell = c.cell_of[atom];
-    const int c0 = cell % c.grid.nc[0], c1 = (cell / c.grid.nc[0]) % c.grid.nc[1],
-              c2 = cell / (c.grid.nc[0] * c.grid.nc[1]);
-    const float lx = (float)c.grid.len[0], ly = (float)c.grid.len[1], lz = (float)c.grid.len[2];
-    const float reach2 = a.reach2f;
-    int cnt = 0;
-    for (int dz = (DIM > 2 ? -1 : 0); dz <= (DIM > 2 ? 1 : 0); ++dz)
-        for (int dy = (DIM > 1 ? -1 : 0); dy <= (DIM > 1 ? 1 : 0); ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                int ncell, sh[3];
-                neighbour_cell<DIM>(c.grid, c0, c1, c2, dx, dy, dz, ncell, sh);
-                const float xs = me.x - sh[0] * lx;
-                const float ys = me.y - sh[1] * ly;
-                const float zs = me.z - sh[2] * lz;
-                const unsigned code = (unsigned)((sh[0] + 1) + 3 * (sh[1] + 1) + 9 * (sh[2] + 1)) << 27;
-                const int jend = c.starts[ncell + 1];
-                for (int j = c.starts[ncell]; j < jend; ++j) {
-                    const float4 q = c.sortedf[j];
-                    float d = xs - q.x;
-                    float r = d * d;
-                    if (DIM > 1) { d = ys - q.y; r = fmaf(d, d, r); }
-                    if (DIM > 2) { d = zs - q.z; r = fmaf(d, d, r); }
-                    if (r < reach2 && j != slot) {
-                        if (cnt < a.cap) a.entries[(size_t)cnt * a.stride + row] = code | (unsigned)j;
-                        ++cnt;
-                    }
-                }
-            }
-    if (cnt > a.cap) atomicAdd(&a.flags[1], 1);  // statistics only: the traversal handles it exactly
-    a.nneigh[row] = cnt;
-}
-
-struct NlAcc {
-    double f[3];
-    double v;
-    double wc[9];   // crossing correction: sum f (x) S, upper triangle used
-    int hits;
-};
-
-// One candidate pair; d = x_i - x_j - S already formed.  SINGLE: one particle type (coefficients in
-// registers, the shift `offset` is applied once per thread from the hit count).
-template <int DIM, bool SINGLE>
-__device__ __forceinline__ void nl_pair(const double (&d)[3], double rsq, double lj1, double lj2, double lj3,
-                                        double lj4, double off, uint32_t flags, NlAcc &acc) {
-    const double r2inv = rcp_fast(rsq);                                  // lennardjones.py:254
-    const double r6inv = (r2inv * r2inv) * r2inv;                        // :255
-    if (flags & TMD_WANT_V) {                                            // :276-282
-        acc.v = fma(r6inv, fma(lj3, r6inv, -lj4), acc.v);
-        if (SINGLE) acc.hits += 1;
-        else acc.v -= off;
-    }
-    if (flags & (TMD_WANT_F | TMD_WANT_W)) {
-        const double flj = (r2inv * r6inv) * fma(lj1, r6inv, -lj2);      // :285-288
+    __syncthreads();  // s_warp may still be read from a previous call
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int before = 0, sum = 0;
 #pragma unroll
-        for (int k = 0; k < DIM; ++k) acc.f[k] = fma(flj, d[k], acc.f[k]);  // :269-270
+    for (int w = 0; w < kBinThreads / 32; ++w) {
+        const int t = s_warp[w];
+        if (w < warp) before += t;
+        sum += t;
     }
+    total = sum;
+    return before + incl - v;
 }
 
-// the rare pair whose neighbour is a periodic image: also feeds the virial correction
-template <int DIM, bool SINGLE>
-__device__ __forceinline__ void nl_pair_crossing(const double (&d)[3], const double (&S)[3], double rsq, double lj1,
-                                                 double lj2, double lj3, double lj4, double off, uint32_t flags,
-                                                 NlAcc &acc) {
-    const double r2inv = rcp_fast(rsq);
-    const double r6inv = (r2inv * r2inv) * r2inv;
-    if (flags & TMD_WANT_V) {
-        acc.v = fma(r6inv, fma(lj3, r6inv, -lj4), acc.v);
-        if (SINGLE) acc.hits += 1;
-        else acc.v -= off;
-    }
-    if (flags & (TMD_WANT_F | TMD_WANT_W)) {
-        const double flj = (r2inv * r6inv) * fma(lj1, r6inv, -lj2);
+// Binning (phases 1-4 of a rebuild) in one cooperative launch; gated on the rebuild flag.
+template <int DIM>
+__global__ void __launch_bounds__(kBinThreads) nl_bin_kernel(const NlArgs a) {
+    if (a.nlflags[0] == 0) return;  // same answer in every block: nobody writes the flag while this kernel runs
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int s_warp[kBinThreads / 32];
+    const NlGrid &g = a.grid;
+    const int tid = threadIdx.x;
+    const int64_t gtid = (int64_t)blockIdx.x * kBinThreads + tid;
+    const int64_t gthreads = (int64_t)gridDim.x * kBinThreads;
+    const int ncells = g.ncells;
+
+    // ---- 1. wrap a copy into the box, cell index, rank inside the cell (atomics) ----
+    for (int64_t i = gtid; i < a.n; i += gthreads) {
+        double x[3] = {0.0, 0.0, 0.0};
+        int c[3] = {0, 0, 0};
 #pragma unroll
         for (int k = 0; k < DIM; ++k) {
-            const double fk = flj * d[k];
-            acc.f[k] += fk;
-#pragma unroll
-            for (int b = k; b < DIM; ++b) acc.wc[k * 3 + b] = fma(fk, S[b], acc.wc[k * 3 + b]);
+            const double v = a.pos[i * DIM + k];
+            const double im = floor(v * g.ilen[k]) * g.len[k];
+            const double w = v - im;  // into [0, L) up to rounding
+            int ck = (int)(w * g.scale[k]);
+            ck = ck < 0 ? 0 : (ck >= g.nc[k] ? g.nc[k] - 1 : ck);
+            x[k] = w;
+            c[k] = ck;
+            a.image[i * 3 + k] = im;
         }
+        const int cell = (c[2] * g.nc[1] + c[1]) * g.nc[0] + c[0];
+        const int t = (a.ntypes > 1) ? a.tidx[i] : 0;
+        a.wrapped[i] = make_double4(x[0], x[1], x[2], __longlong_as_double((long long)t));
+        a.cell_of[i] = cell;
+        a.rank_of[i] = atomicAdd(&a.counts[cell], 1);
+    }
+    grid.sync();
+
+    // ---- 2. exclusive scan of the cell populations (chunk sums, then chunk-local scans) ----
+    const int nchunks = (ncells + kScanChunk - 1) / kScanChunk;
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const int e = ch * kScanChunk + tid * 8;
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mine += (e + k < ncells) ? a.counts[e + k] : 0;
+        int total;
+        block_exclusive_scan(mine, s_warp, total);
+        if (tid == 0) a.chunk_sums[ch] = total;
+    }
+    grid.sync();
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        int part = 0;
+        for (int q = tid; q < ch; q += kBinThreads) part += a.chunk_sums[q];
+        int offset;
+        block_exclusive_scan(part, s_warp, offset);  // offset = sum of all chunks before this one
+        const int e = ch * kScanChunk + tid * 8;
+        int v[8], mine = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[k] = (e + k < ncells) ? a.counts[e + k] : 0;
+            if (e + k < ncells) a.counts[e + k] = 0;  // ready for the next build
+            mine += v[k];
+        }
+        int total;
+        int run = offset + block_exclusive_scan(mine, s_warp, total);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (e + k < ncells) a.starts[e + k] = run;
+            run += v[k];
+        }
+    }
+    if (gtid == 0) a.starts[ncells] = (int)a.n;
+    grid.sync();
+
+    // ---- 3. scatter atoms to a provisional slot inside their cell ----
+    for (int64_t i = gtid; i < a.n; i += gthreads) a.order_tmp[a.starts[a.cell_of[i]] + a.rank_of[i]] = (int)i;
+    grid.sync();
+
+    // ---- 4. final slot = rank by atom index inside the cell (nothing depends on how the atomics
+    //         resolved); write the records ----
+    for (int64_t p = gtid; p < a.n; p += gthreads) {
+        const int i = a.order_tmp[p];
+        const int cell = a.cell_of[i];
+        const int lo = a.starts[cell], hi = a.starts[cell + 1];
+        int rank = 0;
+        for (int q = lo; q < hi; ++q) rank += a.order_tmp[q] < i;
+        const int t = lo + rank;
+        const double4 w = a.wrapped[i];
+        a.order[t] = i;
+        a.slot_of[i] = t;
+        a.xb[t] = w;
+        a.xs[t] = w;
+        a.xbf[t] = make_float4((float)w.x, (float)w.y, (float)w.z, 0.f);
     }
 }
 
-template <int DIM, bool SINGLE>
-__global__ void __launch_bounds__(kNlThreads, 4) nl_force_kernel(const NlArgs a) {
+// Candidate lists (phase 5 of a rebuild): one thread per row atom walks the stencil runs with the
+// single-precision filter and appends to its own row-major list, eight entries (one 32-byte sector,
+// STG.256) at a time; ascending by (stencil row, slot).  Gated on the rebuild flag; persistent grid.
+template <int DIM>
+__global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
+    if (a.nlflags[0] == 0) return;
+    const NlGrid &g = a.grid;
+    const int64_t gthreads = (int64_t)gridDim.x * kNlThreads;
+    const bool whole = a.first == 0 && a.count == a.n;
+    const float lx = (float)g.len[0], ly = (float)g.len[1], lz = (float)g.len[2];
+    const float reach2 = a.reach2f;
+    const int cap = a.cap;
+    for (int64_t row = (int64_t)blockIdx.x * kNlThreads + threadIdx.x; row < a.count; row += gthreads) {
+        const int slot = whole ? (int)row : a.slot_of[a.first + row];
+        const int atom = whole ? a.order[slot] : (int)(a.first + row);
+        const float4 me = a.xbf[slot];
+        const int cell = a.cell_of[atom];
+        const int c0 = cell % g.nc[0], c1 = (cell / g.nc[0]) % g.nc[1], c2 = cell / (g.nc[0] * g.nc[1]);
+        unsigned *list = a.entries + (size_t)row * cap;  // cap is a multiple of 8: rows are 32-byte aligned
+        unsigned e[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // the last eight entries, oldest first
+        int cnt = 0;
+        for_each_run<DIM>(g, a.starts, c0, c1, c2, [&](int jbegin, int jend, int code) {
+            const float xs = me.x - (code % 3 - 1) * lx;
+            const float ys = me.y - ((code / 3) % 3 - 1) * ly;
+            const float zs = me.z - (code / 9 - 1) * lz;
+            const unsigned tag = (unsigned)code << 27;
+            for (int j = jbegin; j < jend; ++j) {
+                const float4 q = a.xbf[j];
+                float d = xs - q.x;
+                float r = d * d;
+                if (DIM > 1) { d = ys - q.y; r = fmaf(d, d, r); }
+                if (DIM > 2) { d = zs - q.z; r = fmaf(d, d, r); }
+                if (r < reach2 && j != slot) {
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) e[k] = e[k + 1];
+                    e[7] = tag | (unsigned)j;
+                    ++cnt;
+                    if ((cnt & 7) == 0 && cnt <= cap) st_entries8(list + cnt - 8, e);  // one full 32-byte sector
+                }
+            }
+        });
+        if (cnt <= cap) {  // the 0..7 entries after the last full batch
+            const int tail = cnt & 7;
+#pragma unroll
+            for (int k = 1; k < 8; ++k)
+                if (tail >= k) list[cnt - k] = e[8 - k];
+        } else {
+            atomicAdd(&a.nlflags[1], 1);  // statistics only: the traversal handles such a row exactly
+        }
+        a.nneigh[row] = cnt;
+    }
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Traversal.  G lanes share one row atom: lane l takes candidates l, l+G, l+2G, ... of its list, so
+// the lanes of a group read consecutive entries (one 32-byte sector) and gather records of
+// nearly consecutive slots.  Blocks are persistent (grid-stride over groups of kNlThreads/G rows): the
+// energy / virial partials stay in registers for the whole kernel and are reduced once.  SINGLE: one
+// particle type (coefficients in registers, the shift `offset` applied once per lane from its hit
+// count).
+template <int DIM, bool SINGLE, int G, int MINB>
+__global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs a) {
     __shared__ double s_tab[SINGLE ? 1 : 6 * kMaxT2];
     __shared__ double s_red[10 * (kNlThreads / 32)];
-    const CellArgs &c = a.c;
+    constexpr int kRowsPerBlock = kNlThreads / G;
     const int tid = threadIdx.x;
-    const int64_t row = (int64_t)blockIdx.x * kNlThreads + tid;
-    const bool valid = row < c.count;
-    const bool whole = c.first == 0 && c.count == c.n;
-    const int ntypes = c.ntypes;
+    const int l = tid % G, grp = tid / G;
+    const bool whole = a.first == 0 && a.count == a.n;
+    const int ntypes = a.ntypes;
     if (!SINGLE) {
-        for (int k = tid; k < 6 * kMaxT2; k += kNlThreads) s_tab[k] = c.tab.c[k / kMaxT2][k % kMaxT2];
+        for (int k = tid; k < 6 * kMaxT2; k += kNlThreads) s_tab[k] = a.tab.c[k / kMaxT2][k % kMaxT2];
         __syncthreads();
     }
-    if (blockIdx.x == 0 && tid == 0) {  // every gated kernel of this call is behind us in the stream
-        if (a.flags[0]) {
-            a.flags[0] = 0;
-            a.flags[2] += 1;
+    if (blockIdx.x == 0 && tid == 0) {  // the gated build of this call is behind us in the stream
+        if (a.nlflags[0]) {
+            a.nlflags[0] = 0;
+            a.nlflags[2] += 1;
         }
-        a.flags[3] += 1;
+        a.nlflags[3] += 1;
     }
-    NlAcc acc;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) acc.f[k] = 0.0;
-    acc.v = 0.0;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) acc.wc[k] = 0.0;
-    acc.hits = 0;
+    const uint32_t flags = a.flags;
+    const double lx = a.grid.len[0], ly = a.grid.len[1], lz = a.grid.len[2];
+    const double lj1 = a.tab.c[0][0], lj2 = a.tab.c[1][0], lj3 = a.tab.c[2][0], lj4 = a.tab.c[3][0],
+                 off = a.tab.c[4][0], rc2 = a.tab.c[5][0];
+    // per-lane totals over all rows of this block: energy, hit count (the shift is applied at the end),
+    // virial (xx xy xz yy yz zz) = 2 F (x) x of the rows this lane leads - sum f (x) S of crossing pairs
+    double vtot = 0.0, wtot[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int hits = 0;
 
-    int atom = 0;
-    double xme[3] = {0.0, 0.0, 0.0};
-    const uint32_t flags = c.flags;
-    const double lx = c.grid.len[0], ly = c.grid.len[1], lz = c.grid.len[2];
-    const double lj1 = c.tab.c[0][0], lj2 = c.tab.c[1][0], lj3 = c.tab.c[2][0], lj4 = c.tab.c[3][0],
-                 off = c.tab.c[4][0], rc2 = c.tab.c[5][0];
-    if (valid) {
-        const int slot = whole ? (int)row : c.slot_of[c.first + row];
-        atom = whole ? c.order[slot] : (int)(c.first + row);
-        const double4 me = a.xs[slot];
-        xme[0] = me.x;
-        xme[1] = me.y;
-        xme[2] = me.z;
+    // Everything a row needs before its first pair can be evaluated; fetched one row ahead so that
+    // the dependent chain (row -> list head -> record) of the NEXT row overlaps this row's arithmetic.
+    struct Row {
+        bool valid;
+        int slot, atom, nn;
+        double4 me;
+        unsigned e0, e1;
+    };
+    auto fetch = [&](int64_t base) {
+        Row r;
+        const int64_t row = base + grp;
+        r.valid = row < a.count;
+        r.slot = !r.valid ? 0 : (whole ? (int)row : a.slot_of[a.first + row]);
+        r.atom = !r.valid ? 0 : (whole ? a.order[r.slot] : (int)(a.first + row));
+        r.me = a.xs[r.slot];
+        r.nn = r.valid ? a.nneigh[row] : 0;
+        r.e0 = r.e1 = 0u;
+        if (r.nn <= a.cap) {
+            const unsigned *list = a.entries + (size_t)row * a.cap;
+            if (l < r.nn) r.e0 = __ldg(list + l);
+            if (l + G < r.nn) r.e1 = __ldg(list + l + G);
+        }
+        return r;
+    };
+
+    // block-uniform trip count: the group shuffles below need every lane of the warp in the loop
+    const int64_t stride = (int64_t)gridDim.x * kRowsPerBlock;
+    Row next = fetch((int64_t)blockIdx.x * kRowsPerBlock);
+    for (int64_t base = (int64_t)blockIdx.x * kRowsPerBlock; base < a.count; base += stride) {
+        const Row cur = next;
+        if (base + stride < a.count) next = fetch(base + stride);
+        const int64_t row = base + grp;
+        const bool valid = cur.valid;
+        const int slot = cur.slot, atom = cur.atom, nn = cur.nn;
+        const double4 me = cur.me;
         const int ti = SINGLE ? 0 : (int)__double_as_longlong(me.w);
-        const int nn = a.nneigh[row];
+        double facc[3] = {0.0, 0.0, 0.0};
 
-        auto candidate = [&](int j, int code) {
-            const double4 q = a.xs[j];
+        auto candidate = [&](const double4 q, int code) {
             double d[3] = {0.0, 0.0, 0.0};
             d[0] = me.x - q.x;
             if (DIM > 1) d[1] = me.y - q.y;
@@ -286,84 +447,115 @@ __global__ void __launch_bounds__(kNlThreads, 4) nl_force_kernel(const NlArgs a)
                 of = s_tab[4 * kMaxT2 + p];
                 r2c = s_tab[5 * kMaxT2 + p];
             }
-            if (code == kHomeCode) {
-                double rsq = d[0] * d[0];
-                if (DIM > 1) rsq = fma(d[1], d[1], rsq);
-                if (DIM > 2) rsq = fma(d[2], d[2], rsq);
-                if (rsq < r2c) nl_pair<DIM, SINGLE>(d, rsq, l1, l2, l3, l4, of, flags, acc);
-            } else {  // the neighbour is a periodic image: only for atoms near a box face
-                double S[3] = {0.0, 0.0, 0.0};
+            double S[3] = {0.0, 0.0, 0.0};
+            const bool crossing = code != kHomeCode;  // the neighbour is a periodic image: atoms near a face only
+            if (crossing) {
                 S[0] = (code % 3 - 1) * lx;
                 if (DIM > 1) S[1] = ((code / 3) % 3 - 1) * ly;
                 if (DIM > 2) S[2] = (code / 9 - 1) * lz;
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) d[k] -= S[k];
-                double rsq = d[0] * d[0];
-                if (DIM > 1) rsq = fma(d[1], d[1], rsq);
-                if (DIM > 2) rsq = fma(d[2], d[2], rsq);
-                if (rsq < r2c) nl_pair_crossing<DIM, SINGLE>(d, S, rsq, l1, l2, l3, l4, of, flags, acc);
+            }
+            double rsq = d[0] * d[0];
+            if (DIM > 1) rsq = fma(d[1], d[1], rsq);
+            if (DIM > 2) rsq = fma(d[2], d[2], rsq);
+            if (rsq < r2c) {                                                     // strict '<' (lennardjones.py:291-294)
+                const double r2inv = rcp_fast(rsq);                              // :254
+                const double r6inv = (r2inv * r2inv) * r2inv;                    // :255
+                if (flags & TMD_WANT_V) {                                        // :276-282
+                    vtot = fma(r6inv, fma(l3, r6inv, -l4), vtot);
+                    if (SINGLE) hits += 1;
+                    else vtot -= of;
+                }
+                if (flags & (TMD_WANT_F | TMD_WANT_W)) {
+                    const double flj = (r2inv * r6inv) * fma(l1, r6inv, -l2);    // :285-288
+                    if (!crossing) {
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) facc[k] = fma(flj, d[k], facc[k]);  // :269-270
+                    } else {
+                        int w = 0;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const double fk = k < DIM ? flj * d[k] : 0.0;
+                            if (k < DIM) facc[k] += fk;
+#pragma unroll
+                            for (int b = k; b < 3; ++b, ++w)
+                                if (b < DIM) wtot[w] = fma(-fk, S[b], wtot[w]);
+                        }
+                    }
+                }
             }
         };
 
         if (nn <= a.cap) {
-            const unsigned *list = a.entries + row;
-            int k = 0;
-            for (; k + 4 <= nn; k += 4) {  // four independent gathers in flight
-                unsigned e[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) e[u] = __ldg(list + (size_t)(k + u) * a.stride);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) candidate((int)(e[u] & kSlotMask), (int)(e[u] >> 27));
-            }
-            for (; k < nn; ++k) {
-                const unsigned e = __ldg(list + (size_t)k * a.stride);
-                candidate((int)(e & kSlotMask), (int)(e >> 27));
+            const unsigned *list = a.entries + (size_t)row * a.cap;
+            // software pipeline: entries two rounds ahead, records one round ahead
+            int k = l;
+            unsigned e0 = cur.e0, e1 = cur.e1;
+            double4 q0 = me;
+            if (k < nn) q0 = ld_record(a.xs + (e0 & kSlotMask));
+            while (k < nn) {
+                const unsigned e2 = k + 2 * G < nn ? __ldg(list + k + 2 * G) : 0u;
+                double4 q1 = me;
+                if (k + G < nn) q1 = ld_record(a.xs + (e1 & kSlotMask));
+                candidate(q0, (int)(e0 >> 27));
+                e0 = e1;
+                e1 = e2;
+                q0 = q1;
+                k += G;
             }
         } else {
             // list capacity exceeded at build time: walk the build-time cells (every pair now inside
             // rcut was inside rcut + skin then, hence in this stencil)
-            const int cell = c.cell_of[atom];
-            const int c0 = cell % c.grid.nc[0], c1 = (cell / c.grid.nc[0]) % c.grid.nc[1],
-                      c2 = cell / (c.grid.nc[0] * c.grid.nc[1]);
-            for (int dz = (DIM > 2 ? -1 : 0); dz <= (DIM > 2 ? 1 : 0); ++dz)
-                for (int dy = (DIM > 1 ? -1 : 0); dy <= (DIM > 1 ? 1 : 0); ++dy)
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        int ncell, sh[3];
-                        neighbour_cell<DIM>(c.grid, c0, c1, c2, dx, dy, dz, ncell, sh);
-                        const int code = (sh[0] + 1) + 3 * (sh[1] + 1) + 9 * (sh[2] + 1);
-                        const int jend = c.starts[ncell + 1];
-                        for (int j = c.starts[ncell]; j < jend; ++j)
-                            if (j != slot) candidate(j, code);
-                    }
+            const int cell = a.cell_of[atom];
+            const int c0 = cell % a.grid.nc[0], c1 = (cell / a.grid.nc[0]) % a.grid.nc[1],
+                      c2 = cell / (a.grid.nc[0] * a.grid.nc[1]);
+            for_each_run<DIM>(a.grid, a.starts, c0, c1, c2, [&](int jbegin, int jend, int code) {
+                for (int j = jbegin + l; j < jend; j += G)
+                    if (j != slot) candidate(a.xs[j], code);
+            });
+        }
+
+        // ---- finish this row: F over the G lanes, then the per-atom virial term on lane 0 ----
+        double f[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) f[k] = group_sum<G>(facc[k]);
+        if (l == 0 && valid) {
+            if (flags & TMD_WANT_F) {
+                double *dst = a.force + (int64_t)atom * DIM;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) dst[k] = (flags & TMD_ACCUMULATE) ? dst[k] + f[k] : f[k];
+            }
+            if (flags & TMD_WANT_W) {
+                const double x[3] = {me.x - a.centre[0], me.y - a.centre[1], me.z - a.centre[2]};
+                int w = 0;
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+#pragma unroll
+                    for (int q = p; q < 3; ++q, ++w)
+                        if (q < DIM) wtot[w] = fma(2.0 * f[p], x[q], wtot[w]);
+            }
         }
     }
 
-    if (valid && (flags & TMD_WANT_F)) {
-        double *dst = c.force + (int64_t)atom * DIM;
-#pragma unroll
-        for (int k = 0; k < DIM; ++k) dst[k] = (flags & TMD_ACCUMULATE) ? dst[k] + acc.f[k] : acc.f[k];
-    }
-    // per-thread share of (V, W) in the "every pair seen from both atoms, halve at the end" convention
+    // per-block share of (V, W) in the "every pair seen from both atoms, halve at the end" convention
     double red[10];
-    red[0] = SINGLE ? acc.v - acc.hits * off : acc.v;
+    red[0] = SINGLE ? vtot - hits * off : vtot;
+    red[1] = wtot[0]; red[2] = wtot[1]; red[3] = wtot[2];
+    red[4] = wtot[1]; red[5] = wtot[3]; red[6] = wtot[4];
+    red[7] = wtot[2]; red[8] = wtot[4]; red[9] = wtot[5];
+    if (!(flags & TMD_WANT_W)) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) red[1 + k] = 0.0;
-    if (flags & TMD_WANT_W) {
-#pragma unroll
-        for (int p = 0; p < DIM; ++p)
-#pragma unroll
-            for (int q = p; q < DIM; ++q)
-                red[1 + p * 3 + q] = fma(2.0 * acc.f[p], xme[q] - a.centre[q], -acc.wc[p * 3 + q]);
-        red[1 + 3] = red[1 + 1];
-        red[1 + 6] = red[1 + 2];
-        red[1 + 7] = red[1 + 5];
+        for (int k = 1; k < 10; ++k) red[k] = 0.0;
     }
     block_sum<10, kNlThreads>(red, s_red);
     if (tid == 0) {
 #pragma unroll
-        for (int k = 0; k < 10; ++k) c.partial_vw[(size_t)blockIdx.x * 10 + k] = red[k];
+        for (int k = 0; k < 10; ++k) a.partial_vw[(size_t)blockIdx.x * 10 + k] = red[k];
     }
 }
+
+// ---- host side -----------------------------------------------------------------------------------
 
 static void nl_release(tmd_nlist *nl) {
     cudaFree(nl->flags);
@@ -371,30 +563,148 @@ static void nl_release(tmd_nlist *nl) {
     cudaFree(nl->nneigh);
     cudaFree(nl->ints);
     cudaFree(nl->wrapped);
-    cudaFree(nl->sorted);
-    cudaFree(nl->sortedf);
+    cudaFree(nl->xb);
+    cudaFree(nl->xbf);
     cudaFree(nl->xs);
     cudaFree(nl->image);
     nl->flags = nullptr;
     nl->entries = nullptr;
     nl->nneigh = nullptr;
     nl->ints = nullptr;
-    nl->wrapped = nl->sorted = nl->xs = nullptr;
-    nl->sortedf = nullptr;
+    nl->wrapped = nl->xb = nl->xs = nullptr;
+    nl->xbf = nullptr;
     nl->image = nullptr;
     nl->cap_n = nl->cap_rows = nl->cap_cells = 0;
-    nl->cap = nl->stride = 0;
+    nl->cap = 0;
 }
 
-static bool nl_grid(const tmd_box *box, double rc2max, double skin, int64_t n, CellGrid &g, double &reach) {
-    reach = sqrt(rc2max) + skin;
-    return n >= 2 && n < (1ll << 27) && make_grid(box, reach, g);
+static int nl_env_int(const char *name, int fallback) {
+    const char *env = getenv(name);
+    return env ? atoi(env) : fallback;
+}
+
+// lanes per row atom in the traversal (TMD_NL_G = 1 | 2 | 4 | 8 | 16 | 32; default 4)
+static int nl_group_lanes() {
+    static int g = 0;
+    if (g == 0) {
+        const int v = nl_env_int("TMD_NL_G", 4);
+        g = (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 4;
+    }
+    return g;
+}
+
+// resident blocks per SM the traversal is compiled for (TMD_NL_MINB = 5 | 6 | 8; default 6)
+static int nl_min_blocks() {
+    static int b = 0;
+    if (b == 0) {
+        const int v = nl_env_int("TMD_NL_MINB", 6);
+        b = (v == 5 || v == 6 || v == 8) ? v : 6;
+    }
+    return b;
+}
+
+// stencil half width: cells of edge >= (rcut + skin) / H (TMD_NL_H = 1 | 2 | 3; default 1).  Finer
+// cells halve the candidates a rebuild tests but cut them into many short runs; measured on B200
+// (N = 1M, rho = 0.8) H = 1 rebuilds fastest and the traversal does not care.
+static int nl_half_width() {
+    static int h = 0;
+    if (h == 0) {
+        const int v = nl_env_int("TMD_NL_H", 1);
+        h = (v >= 1 && v <= 3) ? v : 1;
+    }
+    return h;
+}
+
+// Fine grid for `reach` = rcut + skin: false when the box is not fully periodic or a direction holds
+// fewer than 2H+1 cells (the stencil would then see an atom twice; use tmd_lj_allpairs).
+static bool nl_make_grid(const tmd_box *box, double reach, int64_t n, NlGrid &g) {
+    if (!(reach > 0.0) || n < 2 || n >= (1ll << 27)) return false;
+    const int h = nl_half_width();
+    const double edge = reach / h * (1.0 + 1e-6);  // slack: an atom on a face may land in either cell
+    long long ncells = 1;
+    g.h = h;
+    for (int k = 0; k < 3; ++k) {
+        g.nc[k] = 1;
+        g.len[k] = g.ilen[k] = g.scale[k] = 0.0;
+    }
+    for (int k = 0; k < box->dim; ++k) {
+        if (!box->periodic[k]) return false;
+        const double len = box->length[k];
+        if (!(len > 0.0) || len != len || len > 1e300) return false;
+        const double q = floor(len / edge);
+        if (q < 2.0 * h + 1.0) return false;
+        g.nc[k] = q > 1024.0 ? 1024 : (int)q;
+        g.len[k] = len;
+        g.ilen[k] = box->ilength[k];
+        g.scale[k] = g.nc[k] / len;
+        ncells *= g.nc[k];
+    }
+    if (ncells > (1ll << 28)) return false;
+    g.ncells = (int)ncells;
+    return true;
+}
+
+template <int DIM, int G, int MINB>
+static void nl_launch_force_gb(const NlArgs &a, int blocks, cudaStream_t s) {
+    if (a.ntypes == 1) ::tmd::count_launch(), nl_force_kernel<DIM, true, G, MINB><<<blocks, kNlThreads, 0, s>>>(a);
+    else ::tmd::count_launch(), nl_force_kernel<DIM, false, G, MINB><<<blocks, kNlThreads, 0, s>>>(a);
+}
+
+template <int DIM, int G>
+static void nl_launch_force_g(const NlArgs &a, int blocks, cudaStream_t s) {
+    if (DIM == 3) {  // tuning variants exist for the 3-D kernel only
+        switch (nl_min_blocks()) {
+            case 5: nl_launch_force_gb<DIM, G, 5>(a, blocks, s); return;
+            case 8: nl_launch_force_gb<DIM, G, 8>(a, blocks, s); return;
+            default: break;
+        }
+    }
+    nl_launch_force_gb<DIM, G, 6>(a, blocks, s);
 }
 
 template <int DIM>
 static void nl_launch_force(const NlArgs &a, int blocks, cudaStream_t s) {
-    if (a.c.ntypes == 1) ::tmd::count_launch(), nl_force_kernel<DIM, true><<<blocks, kNlThreads, 0, s>>>(a);
-    else ::tmd::count_launch(), nl_force_kernel<DIM, false><<<blocks, kNlThreads, 0, s>>>(a);
+    if (DIM == 3) {
+        switch (nl_group_lanes()) {
+            case 1: nl_launch_force_g<DIM, 1>(a, blocks, s); return;
+            case 2: nl_launch_force_g<DIM, 2>(a, blocks, s); return;
+            case 8: nl_launch_force_g<DIM, 8>(a, blocks, s); return;
+            case 16: nl_launch_force_g<DIM, 16>(a, blocks, s); return;
+            case 32: nl_launch_force_g<DIM, 32>(a, blocks, s); return;
+            default: break;
+        }
+    }
+    nl_launch_force_g<DIM, 4>(a, blocks, s);
+}
+
+// persistent traversal grid: resident blocks per SM x SMs, never more blocks than row groups
+static int nl_force_blocks(int64_t count, int dim) {
+    const int g = dim == 3 ? nl_group_lanes() : 4;
+    const int64_t groups = (count + (kNlThreads / g) - 1) / (kNlThreads / g);
+    const int64_t want = (int64_t)num_sms() * (dim == 3 ? nl_min_blocks() : 6);
+    return (int)(groups < want ? groups : want);
+}
+
+template <int DIM>
+static int nl_launch_build(tmd_nlist *nl, NlArgs &a, cudaStream_t s) {
+    if (nl->bin_blocks[DIM - 1] == 0) {
+        int per_sm = 0;
+        TMD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nl_bin_kernel<DIM>, kBinThreads, 0));
+        if (per_sm < 1) per_sm = 1;
+        nl->bin_blocks[DIM - 1] = per_sm * num_sms();
+    }
+    if (nl->build_blocks[DIM - 1] == 0) {
+        int per_sm = 0;
+        TMD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nl_list_kernel<DIM>, kNlThreads, 0));
+        if (per_sm < 1) per_sm = 1;
+        nl->build_blocks[DIM - 1] = per_sm * num_sms();
+    }
+    void *args[] = {(void *)&a};
+    ::tmd::count_launch();
+    TMD_CUDA(cudaLaunchCooperativeKernel((const void *)nl_bin_kernel<DIM>, dim3(nl->bin_blocks[DIM - 1]),
+                                         dim3(kBinThreads), args, 0, s));
+    ::tmd::count_launch(), nl_list_kernel<DIM><<<nl->build_blocks[DIM - 1], kNlThreads, 0, s>>>(a);
+    return TMD_OK;
 }
 
 }  // namespace tmd
@@ -441,10 +751,10 @@ int tmd_lj_nlist_usable(int64_t n, const tmd_box *box, const double *table, int3
     TMD_REQUIRE(skin > 0.0, "skin must be positive");
     *usable = 0;
     LjTable tab;
-    double rc2max = 0.0, reach = 0.0;
+    double rc2max = 0.0;
     TMD_CHECK(load_lj_table(table, ntypes, tab, rc2max));
-    CellGrid g;
-    if (nl_grid(box, rc2max, skin, n, g, reach)) *usable = 1;
+    NlGrid g;
+    if (nl_make_grid(box, sqrt(rc2max) + skin, n, g)) *usable = 1;
     return TMD_OK;
 }
 
@@ -463,48 +773,45 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
     const int dim = box->dim;
 
     NlArgs a;
-    CellArgs &c = a.c;
-    TMD_CHECK(load_lj_table(table, ntypes, c.tab, c.rc2max));
-    double reach = 0.0;
-    if (!nl_grid(box, c.rc2max, nl->skin, n, c.grid, reach)) {
-        set_error("tmd_lj_nlist: needs a fully periodic box with >= 3 cells of edge rcut+skin per direction "
-                  "and 2 <= n < 2^27; use tmd_lj_allpairs");
+    double rc2max = 0.0;
+    TMD_CHECK(load_lj_table(table, ntypes, a.tab, rc2max));
+    const double reach = sqrt(rc2max) + nl->skin;
+    if (!nl_make_grid(box, reach, n, a.grid)) {
+        set_error("tmd_lj_nlist: needs a fully periodic box with >= %d cells of edge (rcut+skin)/%d per direction "
+                  "and 2 <= n < 2^27; use tmd_lj_allpairs", 2 * nl_half_width() + 1, nl_half_width());
         return TMD_ERR_UNSUPPORTED;
     }
     if (count == 0) return launch_reduce_vw(nullptr, 0, 0.5, flags, vw, s);
 
     // ---- (re)allocate and decide whether the signature changed ----
     bool fresh = false;
-    const int ncells = c.grid.ncells;
+    const int ncells = a.grid.ncells;
     if (n > nl->cap_n || count > nl->cap_rows || ncells > nl->cap_cells) {
         TMD_CUDA(cudaStreamSynchronize(s));
         nl_release(nl);
         // expected neighbours within reach at this density, +35 % and a floor, rounded to 8
-        double volume = 1.0, lmax = 0.0;
-        for (int k = 0; k < dim; ++k) {
-            volume *= box->length[k];
-            lmax = fmax(lmax, box->length[k]);
-        }
+        double volume = 1.0;
+        for (int k = 0; k < dim; ++k) volume *= box->length[k];
         const double sphere = dim == 3 ? 4.18879020478639 * reach * reach * reach
                                        : (dim == 2 ? 3.14159265358979 * reach * reach : 2.0 * reach);
         int cap = (int)(1.35 * (double)n / volume * sphere) + 24;
         cap = (cap + 7) & ~7;
         if (cap > 1024) cap = 1024;
         nl->cap = cap;
-        nl->stride = (int)((count + 31) & ~31ll);
         nl->cap_n = n;
         nl->cap_rows = count;
         nl->cap_cells = ncells;
-        const size_t n_ints = (size_t)2 * (ncells + 1) + (size_t)4 * n;
+        const size_t n_chunks = ((size_t)ncells + kScanChunk - 1) / kScanChunk;
+        const size_t n_ints = (size_t)2 * (ncells + 1) + n_chunks + (size_t)5 * n;
         TMD_CUDA(cudaMalloc(&nl->flags, 4 * sizeof(int)));
         TMD_CUDA(cudaMemsetAsync(nl->flags, 0, 4 * sizeof(int), s));
-        TMD_CUDA(cudaMalloc(&nl->entries, (size_t)nl->cap * nl->stride * sizeof(unsigned)));
-        TMD_CUDA(cudaMalloc(&nl->nneigh, (size_t)nl->stride * sizeof(int)));
+        TMD_CUDA(cudaMalloc(&nl->entries, (size_t)nl->cap * count * sizeof(unsigned)));
+        TMD_CUDA(cudaMalloc(&nl->nneigh, (size_t)count * sizeof(int)));
         TMD_CUDA(cudaMalloc(&nl->ints, n_ints * sizeof(int)));
         TMD_CUDA(cudaMemsetAsync(nl->ints, 0, n_ints * sizeof(int), s));  // counts[] must start at zero
         TMD_CUDA(cudaMalloc(&nl->wrapped, (size_t)n * sizeof(double4)));
-        TMD_CUDA(cudaMalloc(&nl->sorted, (size_t)n * sizeof(double4)));
-        TMD_CUDA(cudaMalloc(&nl->sortedf, (size_t)n * sizeof(float4)));
+        TMD_CUDA(cudaMalloc(&nl->xb, (size_t)n * sizeof(double4)));
+        TMD_CUDA(cudaMalloc(&nl->xbf, (size_t)n * sizeof(float4)));
         TMD_CUDA(cudaMalloc(&nl->xs, (size_t)n * sizeof(double4)));
         TMD_CUDA(cudaMalloc(&nl->image, (size_t)n * 3 * sizeof(double)));
         fresh = true;
@@ -519,41 +826,43 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
         nl->dim = dim;
         nl->ntypes = ntypes;
         nl->reach = reach;
-        nl->stride = (int)((count + 31) & ~31ll);
         for (int k = 0; k < 3; ++k) nl->len[k] = k < dim ? box->length[k] : 0.0;
-        // force a build; counts[] may hold a stale grid of another size: clear the cell integers
+        // force a build (counts[] is zero: the scan of every build re-zeroes it)
         static const int one = 1;
-        TMD_CUDA(cudaMemsetAsync(nl->ints, 0, (size_t)2 * (nl->cap_cells + 1) * sizeof(int), s));
         TMD_CUDA(cudaMemcpyAsync(nl->flags, &one, sizeof(int), cudaMemcpyHostToDevice, s));
     }
 
-    c.pos = pos;
-    c.tidx = tidx;
-    c.n = n;
-    c.first = first;
-    c.count = count;
-    c.ntypes = ntypes;
-    c.flags = flags;
-    c.force = force;
-    c.counts = nl->ints;
-    c.starts = nl->ints + (ncells + 1);
-    c.cell_of = nl->ints + 2 * ((size_t)nl->cap_cells + 1);
-    c.rank_of = c.cell_of + nl->cap_n;
-    c.order = c.cell_of + 2 * nl->cap_n;
-    c.slot_of = c.cell_of + 3 * nl->cap_n;
-    c.wrapped = nl->wrapped;
-    c.sorted = nl->sorted;
-    c.sortedf = nl->sortedf;
-    c.image = nl->image;
-    c.gate = nl->flags;
-    const int blocks = (int)((count + kNlThreads - 1) / kNlThreads);
-    TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)blocks * 10 * sizeof(double), (void **)&c.partial_vw));
-    a.gate = nl->flags;
-    a.flags = nl->flags;
+    a.pos = pos;
+    a.tidx = tidx;
+    a.n = n;
+    a.first = first;
+    a.count = count;
+    a.ntypes = ntypes;
+    a.flags = flags;
+    a.force = force;
+    a.nlflags = nl->flags;
+    {
+        const size_t cells1 = (size_t)nl->cap_cells + 1;
+        const size_t chunks = ((size_t)nl->cap_cells + kScanChunk - 1) / kScanChunk;
+        a.counts = nl->ints;
+        a.starts = nl->ints + cells1;
+        a.chunk_sums = nl->ints + 2 * cells1;
+        a.cell_of = nl->ints + 2 * cells1 + chunks;
+        a.rank_of = a.cell_of + nl->cap_n;
+        a.order = a.cell_of + 2 * nl->cap_n;
+        a.slot_of = a.cell_of + 3 * nl->cap_n;
+        a.order_tmp = a.cell_of + 4 * nl->cap_n;
+    }
+    a.wrapped = nl->wrapped;
+    a.xb = nl->xb;
+    a.xbf = nl->xbf;
+    a.xs = nl->xs;
+    a.image = nl->image;
     a.entries = nl->entries;
     a.nneigh = nl->nneigh;
     a.cap = nl->cap;
-    a.stride = nl->stride;
+    const int fblocks = nl_force_blocks(count, dim);
+    TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)fblocks * 10 * sizeof(double), (void **)&a.partial_vw));
     {
         // single-precision filter: coordinates in [0, L) (+- L after folding the shift) carry an
         // absolute error <= 5 * 2^-24 * L per component, i.e. < 2^-20 * Lmax on the distance
@@ -562,28 +871,25 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
         const double rf = reach + lmax * (1.0 / 1048576.0);
         a.reach2f = (float)(rf * rf * (1.0 + 1e-6));
     }
-    a.xs = nl->xs;
     a.half_skin2 = 0.25 * nl->skin * nl->skin;
     for (int k = 0; k < 3; ++k) a.centre[k] = k < dim ? 0.5 * box->length[k] : 0.0;
 
     const int nb = (int)((n + 255) / 256);
-    if (same) {  // otherwise the flag is already set and order / image / sorted are not valid yet
-        if (dim == 1) ::tmd::count_launch(), nl_gather_check_kernel<1><<<nb, 256, 0, s>>>(pos, nl->image, c.order, nl->sorted, n, a.half_skin2, nl->xs, nl->flags);
-        else if (dim == 2) ::tmd::count_launch(), nl_gather_check_kernel<2><<<nb, 256, 0, s>>>(pos, nl->image, c.order, nl->sorted, n, a.half_skin2, nl->xs, nl->flags);
-        else ::tmd::count_launch(), nl_gather_check_kernel<3><<<nb, 256, 0, s>>>(pos, nl->image, c.order, nl->sorted, n, a.half_skin2, nl->xs, nl->flags);
+    if (same) {  // otherwise the flag is already set and order / image / xb are not valid yet
+        if (dim == 1) ::tmd::count_launch(), nl_gather_check_kernel<1><<<nb, 256, 0, s>>>(pos, nl->image, a.order, nl->xb, n, a.half_skin2, nl->xs, nl->flags);
+        else if (dim == 2) ::tmd::count_launch(), nl_gather_check_kernel<2><<<nb, 256, 0, s>>>(pos, nl->image, a.order, nl->xb, n, a.half_skin2, nl->xs, nl->flags);
+        else ::tmd::count_launch(), nl_gather_check_kernel<3><<<nb, 256, 0, s>>>(pos, nl->image, a.order, nl->xb, n, a.half_skin2, nl->xs, nl->flags);
     }
     // ---- gated build ----
-    TMD_CHECK(launch_cell_build(c, dim, s, /*clear_first=*/false));
-    ::tmd::count_launch(), nl_copy_sorted_kernel<<<nb, 256, 0, s>>>(nl->sorted, nl->xs, n, nl->flags);
-    if (dim == 1) ::tmd::count_launch(), nl_build_kernel<1><<<blocks, kNlThreads, 0, s>>>(a);
-    else if (dim == 2) ::tmd::count_launch(), nl_build_kernel<2><<<blocks, kNlThreads, 0, s>>>(a);
-    else ::tmd::count_launch(), nl_build_kernel<3><<<blocks, kNlThreads, 0, s>>>(a);
-    // ---- every call ----
-    if (dim == 1) nl_launch_force<1>(a, blocks, s);
-    else if (dim == 2) nl_launch_force<2>(a, blocks, s);
-    else nl_launch_force<3>(a, blocks, s);
+    if (dim == 1) TMD_CHECK(nl_launch_build<1>(nl, a, s));
+    else if (dim == 2) TMD_CHECK(nl_launch_build<2>(nl, a, s));
+    else TMD_CHECK(nl_launch_build<3>(nl, a, s));
+    // ---- traversal ----
+    if (dim == 1) nl_launch_force<1>(a, fblocks, s);
+    else if (dim == 2) nl_launch_force<2>(a, fblocks, s);
+    else nl_launch_force<3>(a, fblocks, s);
     TMD_CUDA(cudaGetLastError());
-    return launch_reduce_vw(c.partial_vw, blocks, 0.5, flags, vw, s);
+    return launch_reduce_vw(a.partial_vw, fblocks, 0.5, flags, vw, s);
 }
 
 }  // extern "C"
