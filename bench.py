@@ -178,7 +178,6 @@ def bench_lj(args, cfg, rank, world):
         stepper = AtomDecomposition(system, integ)
         step = stepper.step
         stepper.prepare()
-        launches_per_step = stepper.launches_per_step
     else:
         system.evaluate(7)
         step = lambda: integ(system)  # noqa: E731

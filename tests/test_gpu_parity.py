@@ -787,3 +787,66 @@ def test_lj_1m_sampled_rows_and_properties(method):
     k["integrators"].VelocityVerlet(0.002).run(system, 10)
     e1 = system.particles.v_pot + 0.5 * np.sum(system.particles.vel**2)
     assert abs(e1 - e0) < 2e-5 * abs(e0)
+
+
+# ---- atom decomposition (multi-GPU path, ranks emulated on one device) -------------------------------------
+
+
+@pytest.mark.parametrize("kind", ["vv", "inertia"])
+@pytest.mark.parametrize("method", ["allpairs", "nlist"])
+def test_atom_decomposition_three_emulated_ranks_match_single_gpu(kind, method):
+    """Three 'ranks' in one process, each with its own copy of the system and its own row block; the
+    position all-gather is done by hand between the step halves.  Result = the single-GPU trajectory."""
+    from turtlemd_b200.parallel import AtomDecomposition, ShardPlan
+    from turtlemd_b200.philox import PhiloxNormal
+
+    k = _pkg()
+    pos, size = _fluid(10)  # N = 4000
+    vel = np.random.default_rng(6).standard_normal(pos.shape) * 0.9
+    mass = np.random.default_rng(7).uniform(0.8, 1.6, size=len(pos))
+    world, steps = 3, 12
+
+    def make():
+        pot = k["LennardJonesCut"](dim=3, shift=True, method=method, skin=0.3)
+        pot.set_parameters(SINGLE)
+        system = k["System"](k["Box"](low=size[:, 0], high=size[:, 1]),
+                             k["Particles"].from_arrays(pos, vel=vel, mass=mass), [pot])
+        if kind == "vv":
+            integ = k["integrators"].VelocityVerlet(0.004)
+        else:
+            integ = k["integrators"].LangevinInertia(timestep=0.004, gamma=0.3, beta=1.25, rgen=PhiloxNormal(key=21))
+        return system, integ
+
+    ref_system, ref_integ = make()
+    ref_system.potential_and_force()
+    for _ in range(steps):
+        ref_integ(ref_system)
+
+    ranks = []
+    for r in range(world):
+        system, integ = make()
+        dec = AtomDecomposition(system, integ, plan=ShardPlan(len(pos), world, r))
+        dec.prepare()
+        ranks.append(dec)
+    for _ in range(steps):
+        for dec in ranks:
+            dec.step_move()
+        for dst in ranks:  # the all-gather: everybody receives everybody's own rows
+            for src in ranks:
+                lo, cnt = src.plan.first * 3, src.plan.count * 3
+                dst._pos_pad[lo: lo + cnt].copy_(src._pos_pad[lo: lo + cnt])
+        for dec in ranks:
+            dec.step_force()
+    x = ranks[0].system.particles._pos.device().cpu().numpy().reshape(-1, 3)
+    assert rel_norm(x, ref_system.particles.pos) < 1e-11
+    v_total, w_total = 0.0, np.zeros((3, 3))
+    for dec in ranks:
+        lo, cnt = dec.plan.first, dec.plan.count
+        v_own = dec.system.particles._vel.device().cpu().numpy().reshape(-1, 3)[lo: lo + cnt]
+        assert rel_norm(v_own, ref_system.particles.vel[lo: lo + cnt]) < 1e-10
+        v_share, w_share = dec.reduce_observables()
+        v_total += v_share
+        w_total += w_share
+    assert abs(v_total - ref_system.particles.v_pot) <= 1e-11 * abs(ref_system.particles.v_pot)
+    if kind == "vv":
+        assert rel_norm(w_total, ref_system.particles.virial) < 1e-10
