@@ -365,8 +365,8 @@ __device__ __forceinline__ double group_sum(double v) {
 // energy / virial partials stay in registers for the whole kernel and are reduced once.  SINGLE: one
 // particle type (coefficients in registers, the shift `offset` applied once per lane from its hit
 // count).
-template <int DIM, bool SINGLE, int G, int MINB>
-__global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs a) {
+template <int DIM, bool SINGLE, int G, bool WV, bool WF>
+__global__ void __launch_bounds__(kNlThreads, 6) nl_force_kernel(const NlArgs a) {
     __shared__ double s_tab[SINGLE ? 1 : 6 * kMaxT2];
     __shared__ double s_red[10 * (kNlThreads / 32)];
     constexpr int kRowsPerBlock = kNlThreads / G;
@@ -462,12 +462,12 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
             if (rsq < r2c) {                                                     // strict '<' (lennardjones.py:291-294)
                 const double r2inv = rcp_fast(rsq);                              // :254
                 const double r6inv = (r2inv * r2inv) * r2inv;                    // :255
-                if (flags & TMD_WANT_V) {                                        // :276-282
+                if (WV) {                                                        // :276-282
                     vtot = fma(r6inv, fma(l3, r6inv, -l4), vtot);
                     if (SINGLE) hits += 1;
                     else vtot -= of;
                 }
-                if (flags & (TMD_WANT_F | TMD_WANT_W)) {
+                if (WF) {
                     const double flj = (r2inv * r6inv) * fma(l1, r6inv, -l2);    // :285-288
                     if (!crossing) {
 #pragma unroll
@@ -489,20 +489,24 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
 
         if (nn <= a.cap) {
             const unsigned *list = a.entries + (size_t)row * a.cap;
-            // software pipeline: entries two rounds ahead, records one round ahead
+            // software pipeline: entries two rounds ahead, records one round ahead; two record buffers
+            // used alternately so that nothing has to be moved between rounds
             int k = l;
             unsigned e0 = cur.e0, e1 = cur.e1;
-            double4 q0 = me;
-            if (k < nn) q0 = ld_record(a.xs + (e0 & kSlotMask));
+            double4 qa = me, qb = me;
+            if (k < nn) qa = ld_record(a.xs + (e0 & kSlotMask));
             while (k < nn) {
-                const unsigned e2 = k + 2 * G < nn ? __ldg(list + k + 2 * G) : 0u;
-                double4 q1 = me;
-                if (k + G < nn) q1 = ld_record(a.xs + (e1 & kSlotMask));
-                candidate(q0, (int)(e0 >> 27));
-                e0 = e1;
-                e1 = e2;
-                q0 = q1;
+                unsigned e2 = k + 2 * G < nn ? __ldg(list + k + 2 * G) : 0u;
+                if (k + G < nn) qb = ld_record(a.xs + (e1 & kSlotMask));
+                candidate(qa, (int)(e0 >> 27));
                 k += G;
+                if (k >= nn) break;
+                e0 = k + 2 * G < nn ? __ldg(list + k + 2 * G) : 0u;
+                if (k + G < nn) qa = ld_record(a.xs + (e2 & kSlotMask));
+                candidate(qb, (int)(e1 >> 27));
+                k += G;
+                e1 = e0;
+                e0 = e2;
             }
         } else {
             // list capacity exceeded at build time: walk the build-time cells (every pair now inside
@@ -583,24 +587,14 @@ static int nl_env_int(const char *name, int fallback) {
     return env ? atoi(env) : fallback;
 }
 
-// lanes per row atom in the traversal (TMD_NL_G = 1 | 2 | 4 | 8 | 16 | 32; default 4)
+// lanes per row atom in the traversal (TMD_NL_G = 2 | 4 | 8; default 4, the fastest measured)
 static int nl_group_lanes() {
     static int g = 0;
     if (g == 0) {
         const int v = nl_env_int("TMD_NL_G", 4);
-        g = (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 4;
+        g = (v == 2 || v == 4 || v == 8) ? v : 4;
     }
     return g;
-}
-
-// resident blocks per SM the traversal is compiled for (TMD_NL_MINB = 5 | 6 | 8; default 6)
-static int nl_min_blocks() {
-    static int b = 0;
-    if (b == 0) {
-        const int v = nl_env_int("TMD_NL_MINB", 6);
-        b = (v == 5 || v == 6 || v == 8) ? v : 6;
-    }
-    return b;
 }
 
 // stencil half width: cells of edge >= (rcut + skin) / H (TMD_NL_H = 1 | 2 | 3; default 1).  Finer
@@ -644,33 +638,29 @@ static bool nl_make_grid(const tmd_box *box, double reach, int64_t n, NlGrid &g)
     return true;
 }
 
-template <int DIM, int G, int MINB>
-static void nl_launch_force_gb(const NlArgs &a, int blocks, cudaStream_t s) {
-    if (a.ntypes == 1) ::tmd::count_launch(), nl_force_kernel<DIM, true, G, MINB><<<blocks, kNlThreads, 0, s>>>(a);
-    else ::tmd::count_launch(), nl_force_kernel<DIM, false, G, MINB><<<blocks, kNlThreads, 0, s>>>(a);
-}
-
 template <int DIM, int G>
 static void nl_launch_force_g(const NlArgs &a, int blocks, cudaStream_t s) {
-    if (DIM == 3) {  // tuning variants exist for the 3-D kernel only
-        switch (nl_min_blocks()) {
-            case 5: nl_launch_force_gb<DIM, G, 5>(a, blocks, s); return;
-            case 8: nl_launch_force_gb<DIM, G, 8>(a, blocks, s); return;
-            default: break;
-        }
+    const bool wv = a.flags & TMD_WANT_V, wf = a.flags & (TMD_WANT_F | TMD_WANT_W);
+#define TMD_NL_LAUNCH(SINGLE, WV, WF) \
+    ::tmd::count_launch(), nl_force_kernel<DIM, SINGLE, G, WV, WF><<<blocks, kNlThreads, 0, s>>>(a)
+    if (a.ntypes == 1) {
+        if (wv && wf) TMD_NL_LAUNCH(true, true, true);
+        else if (wf) TMD_NL_LAUNCH(true, false, true);
+        else TMD_NL_LAUNCH(true, true, false);
+    } else {
+        if (wv && wf) TMD_NL_LAUNCH(false, true, true);
+        else if (wf) TMD_NL_LAUNCH(false, false, true);
+        else TMD_NL_LAUNCH(false, true, false);
     }
-    nl_launch_force_gb<DIM, G, 6>(a, blocks, s);
+#undef TMD_NL_LAUNCH
 }
 
 template <int DIM>
 static void nl_launch_force(const NlArgs &a, int blocks, cudaStream_t s) {
-    if (DIM == 3) {
+    if (DIM == 3) {  // the lanes-per-atom tuning variants exist for the 3-D kernel only
         switch (nl_group_lanes()) {
-            case 1: nl_launch_force_g<DIM, 1>(a, blocks, s); return;
             case 2: nl_launch_force_g<DIM, 2>(a, blocks, s); return;
             case 8: nl_launch_force_g<DIM, 8>(a, blocks, s); return;
-            case 16: nl_launch_force_g<DIM, 16>(a, blocks, s); return;
-            case 32: nl_launch_force_g<DIM, 32>(a, blocks, s); return;
             default: break;
         }
     }
@@ -681,7 +671,7 @@ static void nl_launch_force(const NlArgs &a, int blocks, cudaStream_t s) {
 static int nl_force_blocks(int64_t count, int dim) {
     const int g = dim == 3 ? nl_group_lanes() : 4;
     const int64_t groups = (count + (kNlThreads / g) - 1) / (kNlThreads / g);
-    const int64_t want = (int64_t)num_sms() * (dim == 3 ? nl_min_blocks() : 6);
+    const int64_t want = (int64_t)num_sms() * 6;
     return (int)(groups < want ? groups : want);
 }
 
