@@ -12,13 +12,14 @@ __device__ __forceinline__ double4 ld256(const double4 *p) {
 }
 
 // idx table: [iters][32] record indices inside a window of `window` records (per block offset added)
-template <int MODE>  // 0 = LDG.256, 1 = 2x LDG.128, 2 = smem AoS 2x LDS.128, 3 = smem SoA 3x LDS.64
+template <int MODE>  // 0 = LDG.256, 1 = 2x LDG.128, 2 = smem AoS 2x LDS.128, 3 = smem SoA 3x LDS.64, 4 = 2x tex1Dfetch<int4>, 5 = LDG.256 and tex alternating
 __global__ void __launch_bounds__(256) gather_kernel(const double4 *__restrict__ recs, const int *__restrict__ idx,
-                                                     int iters, int window, double *out, long long *cycles) {
+                                                     int iters, int window, double *out, long long *cycles,
+                                                     cudaTextureObject_t tex) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double4 *base = recs + (size_t)(blockIdx.x % 64) * window;
-    if (MODE >= 2) {
+    if (MODE == 2 || MODE == 3) {
         for (int i = threadIdx.x; i < window; i += blockDim.x) {
             const double4 r = base[i];
             if (MODE == 2) { smem[4 * i] = r.x; smem[4 * i + 1] = r.y; smem[4 * i + 2] = r.z; smem[4 * i + 3] = r.w; }
@@ -33,6 +34,12 @@ __global__ void __launch_bounds__(256) gather_kernel(const double4 *__restrict__
         for (int k = 0; k < iters; ++k) {
             const int j = idx[((k + warp * 7) % iters) * 32 + lane];
             if (MODE == 0) { const double4 q = ld256(base + j); acc += q.x + q.y + q.z; }
+            else if (MODE == 4 || (MODE == 5 && (k & 1))) {
+                const int t = ((blockIdx.x % 64) * window + j) * 2;
+                const int4 a = tex1Dfetch<int4>(tex, t), b = tex1Dfetch<int4>(tex, t + 1);
+                acc += __hiloint2double(a.y, a.x) + __hiloint2double(a.w, a.z) + __hiloint2double(b.y, b.x);
+            }
+            else if (MODE == 5) { const double4 q = ld256(base + j); acc += q.x + q.y + q.z; }
             else if (MODE == 1) {
                 const double2 *p = reinterpret_cast<const double2 *>(base + j);
                 const double2 a = __ldg(p), b = __ldg(p + 1);
@@ -56,6 +63,17 @@ int main() {
     cudaMemset(recs, 0, sizeof(double4) * window * 64);
     cudaMalloc(&idx, sizeof(int) * iters * 32);
     cudaMalloc(&out, 8); cudaMalloc(&cyc, sizeof(long long) * blocks);
+    cudaTextureObject_t tex = 0;
+    {
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = recs;
+        rd.res.linear.desc = cudaCreateChannelDesc<int4>();
+        rd.res.linear.sizeInBytes = sizeof(double4) * window * 64;
+        cudaTextureDesc td = {};
+        td.readMode = cudaReadModeElementType;
+        if (cudaCreateTextureObject(&tex, &rd, &td, nullptr) != cudaSuccess) { printf("texture object failed\n"); return 1; }
+    }
     int *h = (int *)malloc(sizeof(int) * iters * 32);
     long long *hc = (long long *)malloc(sizeof(long long) * blocks);
     const char *names[] = {"consecutive (8 lines)", "stride2 (16 lines)", "stride4 (32 lines)", "random in 64-record window",
@@ -84,16 +102,18 @@ int main() {
         }
         cudaMemcpy(idx, h, sizeof(int) * iters * 32, cudaMemcpyHostToDevice);
         printf("%-48s", names[pat]);
-        for (int mode = 0; mode < 4; ++mode) {
-            const size_t smem = mode >= 2 ? sizeof(double) * 4 * window : 0;
+        for (int mode = 0; mode < 6; ++mode) {
+            const size_t smem = (mode == 2 || mode == 3) ? sizeof(double) * 4 * window : 0;
             for (int r = 0; r < 2; ++r) {
                 switch (mode) {
-                    case 0: gather_kernel<0><<<blocks, threads, smem>>>(recs, idx, iters, window, out, cyc); break;
-                    case 1: gather_kernel<1><<<blocks, threads, smem>>>(recs, idx, iters, window, out, cyc); break;
+                    case 0: gather_kernel<0><<<blocks, threads, smem>>>(recs, idx, iters, window, out, cyc, tex); break;
+                    case 1: gather_kernel<1><<<blocks, threads, smem>>>(recs, idx, iters, window, out, cyc, tex); break;
                     case 2: cudaFuncSetAttribute(gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                            gather_kernel<2><<<blocks, threads, smem>>>(recs, idx, iters, window, out, cyc); break;
-                    default: cudaFuncSetAttribute(gather_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                             gather_kernel<3><<<blocks, threads, smem>>>(recs, idx, iters, window, out, cyc); break;
+                            gather_kernel<2><<<blocks, threads, smem>>>(recs, idx, iters, window, out, cyc, tex); break;
+                    case 3: cudaFuncSetAttribute(gather_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                             gather_kernel<3><<<blocks, threads, smem>>>(recs, idx, iters, window, out, cyc, tex); break;
+                    case 4: gather_kernel<4><<<blocks, threads, 0>>>(recs, idx, iters, window, out, cyc, tex); break;
+                    default: gather_kernel<5><<<blocks, threads, 0>>>(recs, idx, iters, window, out, cyc, tex); break;
                 }
                 cudaDeviceSynchronize();
             }

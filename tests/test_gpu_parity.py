@@ -850,3 +850,32 @@ def test_atom_decomposition_three_emulated_ranks_match_single_gpu(kind, method):
     assert abs(v_total - ref_system.particles.v_pot) <= 1e-11 * abs(ref_system.particles.v_pot)
     if kind == "vv":
         assert rel_norm(w_total, ref_system.particles.virial) < 1e-10
+
+
+# ---- observables ------------------------------------------------------------------------
+
+
+def test_thermo_uses_the_device_reduction_and_matches_the_host_formula():
+    """System.thermo() after device-resident steps: kinetic tensor reduced on the GPU (velocities are
+    not downloaded), same numbers as the reference's NumPy expressions (system.py:101-130)."""
+    k = _pkg()
+    pos, size = _fluid(10)
+    rng = np.random.default_rng(14)
+    vel = rng.standard_normal(pos.shape)
+    mass = rng.uniform(0.5, 2.0, size=len(pos))
+    pot = _lj()
+    system = k["System"](k["Box"](low=size[:, 0], high=size[:, 1]),
+                         k["Particles"].from_arrays(pos, vel=vel, mass=mass), [pot])
+    system.potential_and_force()
+    k["integrators"].VelocityVerlet(0.002).run(system, 5)
+    part = system.particles
+    assert part._vel.dev_valid and not part._vel.host_valid
+    thermo = system.thermo()
+    assert not part._vel.host_valid  # thermo() did not pull the velocities
+    v, m = part.vel, part.mass
+    kin = 0.5 * np.einsum("ij,ik->jk", v * m, v)
+    volume = float(np.prod(size[:, 1] - size[:, 0]))
+    assert thermo["ekin"] == pytest.approx(kin.trace() / len(pos), rel=1e-13)
+    assert thermo["temperature"] == pytest.approx(np.mean(2.0 * np.diagonal(kin) / (len(pos) - 1)), rel=1e-13)
+    assert thermo["pressure"] == pytest.approx(((part.virial + 2.0 * kin) / volume).trace() / 3.0, rel=1e-12)
+    assert thermo["vpot"] == pytest.approx(part.v_pot / len(pos), rel=1e-15)

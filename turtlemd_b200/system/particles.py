@@ -207,8 +207,29 @@ def zero_momentum(particles: Particles, dim: list[bool] | None = None):
     particles.vel -= mom / particles.mass.sum()
 
 
+def _kinetic_energy_device(particles: Particles) -> np.ndarray:
+    """0.5 sum m v (x) v reduced on the device (``tmd_kinetic_tensor``); only 9 doubles come back."""
+    import ctypes as C  # noqa: F401
+
+    from .. import _device, _lib
+
+    npart, dim = particles._vel.shape
+    kin = _device.zeros(9)
+    _lib.call("tmd_kinetic_tensor", _device.dptr(particles._vel.device()), _device.dptr(particles._mass_device()),
+              npart, dim, _device.dptr(kin), _device.stream_ptr())
+    return kin.cpu().numpy().reshape(3, 3)[:dim, :dim].copy()
+
+
 def kinetic_energy(particles: Particles) -> tuple[np.ndarray, float]:
-    """Kinetic energy tensor and its trace (particles.py:156-168)."""
+    """Kinetic energy tensor and its trace (particles.py:156-168).
+
+    When the velocities live on the device (an integrator wrote them and nobody has read them on
+    the host since) the reduction runs there and the velocity array is not downloaded.
+    """
+    mirror = particles._vel
+    if mirror.dev_valid and not mirror.host_valid and len(particles.mass) > 1:
+        kin = _kinetic_energy_device(particles)
+        return kin, kin.trace()
     vel = particles._vel.peek()
     mom = vel * particles.mass
     if len(particles.mass) == 1:
@@ -220,7 +241,7 @@ def kinetic_energy(particles: Particles) -> tuple[np.ndarray, float]:
 
 def kinetic_temperature(particles: Particles, boltzmann: float, dof=None, kin_tensor=None):
     """(mean temperature, per-axis temperature, kinetic tensor) (particles.py:171-199)."""
-    ndof = particles.npart * np.ones(particles._vel.peek()[0].shape)
+    ndof = particles.npart * np.ones(particles._vel.shape[1:])
     if kin_tensor is None:
         kin_tensor, _ = kinetic_energy(particles)
     if dof is not None:
