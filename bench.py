@@ -172,12 +172,14 @@ def bench_lj(args, cfg, rank, world):
     pot.set_parameters(SINGLE)
     system = System(box, Particles.from_arrays(pos, vel=vel), [pot])
     integ = VelocityVerlet(cfg["dt"])
+    graphed = False
     if world > 1:
         from turtlemd_b200.parallel import AtomDecomposition
 
         stepper = AtomDecomposition(system, integ)
         step = stepper.step
         stepper.prepare()
+        graphed = stepper.capture() if os.environ.get("TMD_BENCH_GRAPH", "1") == "1" else False
     else:
         system.evaluate(7)
         step = lambda: integ(system)  # noqa: E731
@@ -196,7 +198,9 @@ def bench_lj(args, cfg, rank, world):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"LJ fluid N={n} jittered FCC rho=0.8, rc=2.5 sigma, shifted, "
                                f"VelocityVerlet dt={cfg['dt']}, {cfg['method']} kernel",
-                   "n_atoms": n, "parallelism": f"atom-decomposition x{world}" if world > 1 else "single GPU",
+                   "n_atoms": n, "parallelism": (f"atom-decomposition x{world}, NCCL all-gather of positions, step "
+                                                 f"{'replayed from a CUDA graph' if graphed else 'launched eagerly'}")
+                   if world > 1 else "single GPU",
                    "l2": "inputs (0.75 MB of positions) are L2-resident by nature of the workload; "
                          "the kernel is FP64-pipe bound, no L2 flush between steps"},
         "clocks": clocks.summary(), "gpu_launches": launches,

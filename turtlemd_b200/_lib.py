@@ -159,11 +159,19 @@ def call(name: str, *args) -> None:
     check(getattr(load(), name)(*args))
 
 
+_graph_launches = 0  # kernel launches replayed from CUDA graphs (the library only sees the recording)
+
+
 def launch_count() -> int:
-    """Kernels launched by the library so far in this process."""
+    """Kernels launched by the library so far in this process (graph replays included)."""
     n = C.c_int64(0)
     call("tmd_launch_count", C.byref(n))
-    return n.value
+    return n.value + _graph_launches
+
+
+def add_launches(count: int) -> None:
+    global _graph_launches
+    _graph_launches += int(count)
 
 
 def device_count() -> int:

@@ -110,6 +110,8 @@ class AtomDecomposition:
             self.plan = ShardPlan(self.n, self.world, self.rank)
             self._collectives = self.world > 1
         self._pos_pad = None
+        self._graph = None
+        self._graph_launches = 0
 
     # ---- set-up -----------------------------------------------------------------------------------
     def prepare(self) -> None:
@@ -154,9 +156,43 @@ class AtomDecomposition:
 
     def step(self) -> None:
         """One integration step: move the own atoms, exchange positions, forces for the own rows."""
+        if self._graph is not None:
+            self._graph.replay()
+            _lib.add_launches(self._graph_launches)
+            part = self.system.particles
+            part._pos.written_on_device()
+            part._vel.written_on_device()
+            part._force.written_on_device()
+            return
         self.step_move()
         self._gather_positions()
         self.step_force()
+
+    def capture(self, warm_steps: int = 3) -> bool:
+        """Record one step (kernels + the NCCL all-gather) in a CUDA graph and replay it from now on:
+        at 8 GPUs a step is ~100 us of device work and the Python / launch path would dominate.
+        Only for VelocityVerlet (the Langevin kernels take the stream offset as a launch parameter).
+        Returns False, leaving eager stepping in place, when capture is not possible."""
+        if not isinstance(self.integrator, VelocityVerlet) or self._graph is not None:
+            return self._graph is not None
+        torch = _device.torch()
+        for _ in range(warm_steps):  # allocations, occupancy queries and the first list build happen here
+            self.step()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        try:
+            with torch.cuda.graph(graph):
+                self.step_move()
+                self._gather_positions()
+                self.step_force()
+        except Exception:  # noqa: BLE001 - capture is an optimisation; eager stepping stays correct
+            torch.cuda.synchronize()
+            return False
+        self._graph_launches = _lib.launch_count() - before
+        _lib.add_launches(-self._graph_launches)  # recording is not launching
+        self._graph = graph
+        return True
 
     def _step_args(self):
         part, plan = self.system.particles, self.plan
