@@ -8,6 +8,8 @@ Prints ONE JSON line (rank 0).  Workloads (BASELINE.json configs):
             VelocityVerlet(0.005), Verlet neighbour list over a cell grid
   lj32k     configs[1]: LJ fluid N=32 000, all-pairs kernel
   lj1m_cells  same as lj1m with the stateless cell-list kernel
+  lj1m_langevin  configs[3]: the same fluid under LangevinInertia(gamma=0.3, T=0.8), in-kernel Philox noise
+  dimer256k   configs[4]: N=256 000 fluid, two bonded atoms of type 1 (DoubleWellPair) in LJ solvent
   replicas  configs[2]: 1M DoubleWell LangevinInertia replicas (replica-steps/s)
 For --gpus N > 1 (launched by torch.distributed.run) the LJ workloads are atom-decomposed with an
 all-gather of positions each step, the replicas are sharded with no communication.
@@ -44,6 +46,8 @@ WORKLOADS = {
     "lj256k": dict(rep=40, method="nlist", dt=0.005, unit="atom-steps/s"),
     "lj1m": dict(rep=63, method="nlist", dt=0.005, unit="atom-steps/s"),
     "lj1m_cells": dict(rep=63, method="cells", dt=0.005, unit="atom-steps/s"),
+    "lj1m_langevin": dict(rep=63, method="nlist", dt=0.005, unit="atom-steps/s", integrator="langevin"),
+    "dimer256k": dict(rep=40, method="nlist", dt=0.005, unit="atom-steps/s", dimer=True),
     "replicas": dict(n=1_000_000, dt=0.002, unit="replica-steps/s"),
 }
 
@@ -169,9 +173,33 @@ def bench_lj(args, cfg, rank, world):
     box = Box(low=size[:, 0], high=size[:, 1])
     extra = {} if args.skin is None else {"skin": args.skin}
     pot = LennardJonesCut(dim=3, shift=True, method=cfg["method"], **extra)
-    pot.set_parameters(SINGLE)
-    system = System(box, Particles.from_arrays(pos, vel=vel), [pot])
-    integ = VelocityVerlet(cfg["dt"])
+    ptype, pots, describe = None, [pot], ""
+    if cfg.get("dimer"):
+        # examples/movie-doublewell-pair.py at scale: two neighbouring atoms become type 1 and are bonded
+        # by a DoubleWellPair; LJ parameters identical for both types (rc = 2.5)
+        from turtlemd_b200.potentials import DoubleWellPair
+
+        ptype = np.zeros(n, dtype=int)
+        first = n // 2
+        near = int(np.argsort(np.sum((pos - pos[first]) ** 2, axis=1))[1])
+        ptype[[first, near]] = 1
+        pot.set_parameters({0: dict(SINGLE[0]), 1: dict(SINGLE[0])})
+        bond = DoubleWellPair(types=(1, 1), dim=3)
+        bond.set_parameters({"rzero": 2.0 ** (1.0 / 6.0), "height": 6.0, "width": 0.25})
+        pots.append(bond)
+        describe = " + DoubleWellPair dimer (types 0/1)"
+    else:
+        pot.set_parameters(SINGLE)
+    system = System(box, Particles.from_arrays(pos, vel=vel, ptype=ptype), pots)
+    if cfg.get("integrator") == "langevin":
+        from turtlemd_b200.integrators import LangevinInertia
+        from turtlemd_b200.philox import PhiloxNormal
+
+        integ = LangevinInertia(timestep=cfg["dt"], gamma=0.3, beta=1.0 / 0.8, rgen=PhiloxNormal(key=0))
+        describe += ", LangevinInertia gamma=0.3 T=0.8 (force() + potential() per step as in the reference)"
+    else:
+        integ = VelocityVerlet(cfg["dt"])
+        describe += f", VelocityVerlet dt={cfg['dt']}"
     graphed = False
     if world > 1:
         from turtlemd_b200.parallel import AtomDecomposition
@@ -196,13 +224,15 @@ def bench_lj(args, cfg, rank, world):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"LJ fluid N={n} jittered FCC rho=0.8, rc=2.5 sigma, shifted, "
-                               f"VelocityVerlet dt={cfg['dt']}, {cfg['method']} kernel",
+        "config": {"workload": f"LJ fluid N={n} jittered FCC rho=0.8, rc=2.5 sigma, shifted{describe}, "
+                               f"{cfg['method']} kernel",
                    "n_atoms": n, "parallelism": (f"atom-decomposition x{world}, NCCL all-gather of positions, step "
                                                  f"{'replayed from a CUDA graph' if graphed else 'launched eagerly'}")
                    if world > 1 else "single GPU",
-                   "l2": "inputs (0.75 MB of positions) are L2-resident by nature of the workload; "
-                         "the kernel is FP64-pipe bound, no L2 flush between steps"},
+                   "l2": (f"positions {pos.nbytes / 1e6:.2f} MB are L2-resident by nature of the workload and the kernel "
+                          "is FP64-pipe bound: no L2 flush between steps") if cfg["method"] == "allpairs" else
+                         (f"a step streams the state ({6 * pos.nbytes / 1e6:.0f} MB) and, for the list method, "
+                          "~300 MB of list entries: larger than L2, no flush needed")},
         "clocks": clocks.summary(), "gpu_launches": launches,
     }
     if rank != 0:
@@ -223,9 +253,18 @@ def bench_lj(args, cfg, rank, world):
         achieved = flops / ksec / 1e12
         kernel = {"allpairs": "lj_allpairs_kernel<3,7>", "cells": "lj_cells_kernel<3>",
                   "nlist": "nl_force_kernel<3,true>"}[cfg["method"]]
+        traffic = None
+        try:
+            table = json.loads((REPO / "profiles" / "traffic.json").read_text())
+            traffic = table.get(f"{kernel}@{n}", {}).get("bytes")
+        except (OSError, ValueError):
+            pass
+        step_bytes = 184.0 * n  # x, v, F read + written once, force-kernel reads, bookkeeping
         out["roofline"] = {
             "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": kernel,
+            "traffic": traffic, "kernel": kernel,
+            "hbm": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (sec / args.steps) / 1e9,
+                    "peak_gbs": peak_hbm(), "frac": step_bytes / (sec / args.steps) / 1e9 / peak_hbm()},
             "algorithmic_flops_per_launch": flops, "launch_ms": ksec * 1e3,
             "step_frac": flops / (sec / args.steps) / 1e12 / peak,
             "note": "algorithmic flops = SURVEY.md 8(d): 21 per pair check of a half-stencil cell list (all pairs "

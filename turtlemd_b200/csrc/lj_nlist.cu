@@ -300,51 +300,64 @@ __global__ void __launch_bounds__(kBinThreads) nl_bin_kernel(const NlArgs a) {
 }
 
 // Candidate lists (phase 5 of a rebuild): one thread per row atom walks the stencil runs with the
-// single-precision filter and appends to its own row-major list, eight entries (one 32-byte sector,
-// STG.256) at a time; ascending by (stencil row, slot).  Gated on the rebuild flag; persistent grid.
+// single-precision filter.  A hit costs one shared-memory store into the thread's 32-deep ring;
+// between runs the ring is drained to the row-major list in whole 32-byte sectors (STG.256);
+// ascending by (stencil row, slot).  Gated on the rebuild flag; persistent grid.
+constexpr int kRing = 32;
+
 template <int DIM>
 __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
     if (a.nlflags[0] == 0) return;
+    __shared__ unsigned s_ring[kRing][kNlThreads];
     const NlGrid &g = a.grid;
+    const int tid = threadIdx.x;
     const int64_t gthreads = (int64_t)gridDim.x * kNlThreads;
     const bool whole = a.first == 0 && a.count == a.n;
     const float lx = (float)g.len[0], ly = (float)g.len[1], lz = (float)g.len[2];
     const float reach2 = a.reach2f;
     const int cap = a.cap;
-    for (int64_t row = (int64_t)blockIdx.x * kNlThreads + threadIdx.x; row < a.count; row += gthreads) {
+    for (int64_t row = (int64_t)blockIdx.x * kNlThreads + tid; row < a.count; row += gthreads) {
         const int slot = whole ? (int)row : a.slot_of[a.first + row];
         const int atom = whole ? a.order[slot] : (int)(a.first + row);
         const float4 me = a.xbf[slot];
         const int cell = a.cell_of[atom];
         const int c0 = cell % g.nc[0], c1 = (cell / g.nc[0]) % g.nc[1], c2 = cell / (g.nc[0] * g.nc[1]);
         unsigned *list = a.entries + (size_t)row * cap;  // cap is a multiple of 8: rows are 32-byte aligned
-        unsigned e[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // the last eight entries, oldest first
-        int cnt = 0;
+        int cnt = 0, flushed = 0;                        // flushed is a multiple of 8
+        auto drain = [&](int keep) {                     // write whole sectors until fewer than `keep` entries wait
+            while (cnt - flushed >= keep) {
+                if (flushed + 8 <= cap) {
+                    unsigned e[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) e[k] = s_ring[(flushed + k) & (kRing - 1)][tid];
+                    st_entries8(list + flushed, e);
+                }
+                flushed += 8;
+            }
+        };
         for_each_run<DIM>(g, a.starts, c0, c1, c2, [&](int jbegin, int jend, int code) {
             const float xs = me.x - (code % 3 - 1) * lx;
             const float ys = me.y - ((code / 3) % 3 - 1) * ly;
             const float zs = me.z - (code / 9 - 1) * lz;
             const unsigned tag = (unsigned)code << 27;
-            for (int j = jbegin; j < jend; ++j) {
-                const float4 q = a.xbf[j];
-                float d = xs - q.x;
-                float r = d * d;
-                if (DIM > 1) { d = ys - q.y; r = fmaf(d, d, r); }
-                if (DIM > 2) { d = zs - q.z; r = fmaf(d, d, r); }
-                if (r < reach2 && j != slot) {
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) e[k] = e[k + 1];
-                    e[7] = tag | (unsigned)j;
-                    ++cnt;
-                    if ((cnt & 7) == 0 && cnt <= cap) st_entries8(list + cnt - 8, e);  // one full 32-byte sector
+            for (int j0 = jbegin; j0 < jend; j0 += kRing - 8) {  // at most 24 hits between drains: the ring cannot wrap
+                const int j1 = min(jend, j0 + kRing - 8);
+                for (int j = j0; j < j1; ++j) {
+                    const float4 q = a.xbf[j];
+                    float d = xs - q.x;
+                    float r = d * d;
+                    if (DIM > 1) { d = ys - q.y; r = fmaf(d, d, r); }
+                    if (DIM > 2) { d = zs - q.z; r = fmaf(d, d, r); }
+                    if (r < reach2 && j != slot) {
+                        s_ring[cnt & (kRing - 1)][tid] = tag | (unsigned)j;
+                        ++cnt;
+                    }
                 }
+                drain(8);
             }
         });
-        if (cnt <= cap) {  // the 0..7 entries after the last full batch
-            const int tail = cnt & 7;
-#pragma unroll
-            for (int k = 1; k < 8; ++k)
-                if (tail >= k) list[cnt - k] = e[8 - k];
+        if (cnt <= cap) {  // the 0..7 entries after the last full sector
+            for (int k = flushed; k < cnt; ++k) list[k] = s_ring[k & (kRing - 1)][tid];
         } else {
             atomicAdd(&a.nlflags[1], 1);  // statistics only: the traversal handles such a row exactly
         }
