@@ -17,6 +17,7 @@
 //     rsq < rcut2, division, force, virial) runs with many lanes active instead of 1-in-600
 //   * per-thread force / energy / virial accumulators; per-split partial forces are summed in a
 //     fixed order by the finishing pass -> no atomics, bit-reproducible runs.
+#include <stdlib.h>
 #include <string.h>
 
 #include "lj_common.cuh"
@@ -31,6 +32,9 @@ struct AllPairsArgs {
     const double *pos;
     const int32_t *tidx;
     const double4 *wrapped;
+    const float4 *wrapped_f;  // single-precision copy for the FP32 filter (fully periodic boxes)
+    float half_f[3];
+    float rc2_f;
     int64_t n, first, count;
     int n_itile, n_split;
     int64_t split_len;
@@ -45,7 +49,8 @@ struct AllPairsArgs {
 
 template <int DIM>
 __global__ void __launch_bounds__(256) lj_wrap_kernel(const double *__restrict__ pos, int64_t n, LjBox box,
-                                                      int pmask, double4 *__restrict__ wrapped) {
+                                                      int pmask, double4 *__restrict__ wrapped,
+                                                      float4 *__restrict__ wrapped_f) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double x[3] = {0.0, 0.0, 0.0};
@@ -56,6 +61,7 @@ __global__ void __launch_bounds__(256) lj_wrap_kernel(const double *__restrict__
         x[k] = v;
     }
     wrapped[i] = make_double4(x[0], x[1], x[2], 0.0);
+    if (wrapped_f) wrapped_f[i] = make_float4((float)x[0], (float)x[1], (float)x[2], 0.f);
 }
 
 template <int DIM, int PMASK>
@@ -76,9 +82,32 @@ __device__ __forceinline__ double filter_rsq(const double (&xw)[3], const double
     return r;
 }
 
-template <int DIM, int PMASK>
+// The same filter in single precision (fully periodic boxes, coordinates wrapped into [-L/2, L/2]):
+// twelve FP32 instructions per pair on the FMA pipe, which issues twice as many lanes per clock as
+// the FP64 pipe and leaves the latter to the exact path.  Conservative: the threshold is widened by
+// the single-precision rounding of the wrapped coordinates.
+template <int DIM>
+__device__ __forceinline__ float filter_rsq_f(const float (&xw)[3], const float4 q, const float (&h)[3]) {
+    float d = xw[0] - q.x;
+    d = h[0] - fabsf(fabsf(d) - h[0]);
+    float r = d * d;
+    if (DIM > 1) {
+        d = xw[1] - q.y;
+        d = h[1] - fabsf(fabsf(d) - h[1]);
+        r = fmaf(d, d, r);
+    }
+    if (DIM > 2) {
+        d = xw[2] - q.z;
+        d = h[2] - fabsf(fabsf(d) - h[2]);
+        r = fmaf(d, d, r);
+    }
+    return r;
+}
+
+template <int DIM, int PMASK, bool F32>
 __global__ void __launch_bounds__(kRows, 4) lj_allpairs_kernel(const AllPairsArgs a) {
-    __shared__ double4 s_w[kTile];
+    __shared__ double4 s_w[F32 ? 1 : kTile];
+    __shared__ float4 s_wf[F32 ? kTile : 1];
     __shared__ double s_o[kTile * DIM];
     __shared__ int s_t[kTile];
     __shared__ unsigned s_mask[kWords][kRows];
@@ -109,6 +138,15 @@ __global__ void __launch_bounds__(kRows, 4) lj_allpairs_kernel(const AllPairsArg
     const int ti = (ntypes > 1) ? a.tidx[i] : 0;
     const double h[3] = {a.box.half[0], a.box.half[1], a.box.half[2]};
     const long long rc2_bits = valid ? (long long)a.rc2_filter_bits : -1;  // invalid rows never hit
+    float xf[3] = {0.f, 0.f, 0.f};
+    const float hf[3] = {a.half_f[0], a.half_f[1], a.half_f[2]};
+    const float rc2_f = valid ? a.rc2_f : -1.f;
+    if (F32) {
+        const float4 w = a.wrapped_f[i];
+        xf[0] = w.x;
+        xf[1] = w.y;
+        xf[2] = w.z;
+    }
 
     PairAcc acc;
 #pragma unroll
@@ -127,25 +165,37 @@ __global__ void __launch_bounds__(kRows, 4) lj_allpairs_kernel(const AllPairsArg
         for (int s = tid; s < kTile; s += kRows) {
             const int64_t j = jt + s;
             if (j < j_end) {
-                s_w[s] = a.wrapped[j];
+                if (F32) s_wf[s] = a.wrapped_f[j];
+                else s_w[s] = a.wrapped[j];
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) s_o[s * DIM + k] = a.pos[j * DIM + k];
                 s_t[s] = (ntypes > 1) ? a.tidx[j] : 0;
+            } else if (F32) {
+                s_wf[s] = make_float4(1e18f, 1e18f, 1e18f, 0.f);  // rsq' ~ h^2 at most, but see the mask below
             } else {
                 s_w[s] = make_double4(1e300, 1e300, 1e300, 0.0);  // rsq' = inf: never passes
             }
         }
         __syncthreads();
 
-        // ---- filter: 12 FP64 instructions per pair in 3-D periodic ----
+        // ---- filter: 12 instructions per pair in 3-D periodic (FP64, or FP32 for fully periodic boxes) ----
+        const int64_t in_tile = j_end - jt;  // columns of this tile that exist
 #pragma unroll 1
         for (int word = 0; word < kWords; ++word) {
             unsigned m = 0;
 #pragma unroll
             for (int b = 0; b < 32; ++b) {
-                const double r = filter_rsq<DIM, PMASK>(xw, s_w[word * 32 + b], h);
-                if (__double_as_longlong(r) < rc2_bits) m |= 1u << b;
+                if (F32) {
+                    if (filter_rsq_f<DIM>(xf, s_wf[word * 32 + b], hf) < rc2_f) m |= 1u << b;
+                } else {
+                    const double r = filter_rsq<DIM, PMASK>(xw, s_w[word * 32 + b], h);
+                    if (__double_as_longlong(r) < rc2_bits) m |= 1u << b;
+                }
             }
+            // the folding h - ||d| - h| maps any far-away pad value back into the box: mask the columns
+            // of a partial last tile that do not exist
+            if (F32 && in_tile < (int64_t)(word + 1) * 32)
+                m &= in_tile <= (int64_t)word * 32 ? 0u : (0xffffffffu >> (32 - (int)(in_tile - (int64_t)word * 32)));
             s_mask[word][tid] = m;
         }
 
@@ -252,10 +302,15 @@ int load_lj_table(const double *table, int ntypes, LjTable &out, double &rc2max)
 }
 
 template <int DIM>
-static int run_allpairs(AllPairsArgs &a, int pmask, int blocks, cudaStream_t s) {
+static int run_allpairs(AllPairsArgs &a, int pmask, bool f32, int blocks, cudaStream_t s) {
+    if (f32) {
+        ::tmd::count_launch(), lj_allpairs_kernel<DIM, (1 << DIM) - 1, true><<<blocks, kRows, 0, s>>>(a);
+        TMD_CUDA(cudaGetLastError());
+        return TMD_OK;
+    }
 #define TMD_AP(P)                                                                        \
     case P:                                                                              \
-        if constexpr ((P) < (1 << DIM)) ::tmd::count_launch(), lj_allpairs_kernel<DIM, P><<<blocks, kRows, 0, s>>>(a); \
+        if constexpr ((P) < (1 << DIM)) ::tmd::count_launch(), lj_allpairs_kernel<DIM, P, false><<<blocks, kRows, 0, s>>>(a); \
         break;
     switch (pmask & ((1 << DIM) - 1)) {
         TMD_AP(0)
@@ -326,15 +381,38 @@ extern "C" int tmd_lj_allpairs(const double *pos, const int32_t *tidx, int64_t n
     TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)blocks * 10 * sizeof(double), (void **)&a.partial_vw));
     a.wrapped = wrapped;
 
+    // FP32 filter when every direction is periodic (TMD_AP_FILTER=fp64 keeps the FP64 filter): the
+    // wrapped coordinates are bounded by L/2, so their single-precision images are off by at most
+    // 2^-24 L/2 each; with the roundings of the twelve operations the distance is off by < 2^-20 Lmax.
+    bool f32 = false;
+    float4 *wrapped_f = nullptr;
+    a.wrapped_f = nullptr;
+    a.rc2_f = 0.f;
+    a.half_f[0] = a.half_f[1] = a.half_f[2] = 0.f;
+    static const bool fp64_only = [] {
+        const char *env = getenv("TMD_AP_FILTER");
+        return env && strcmp(env, "fp64") == 0;
+    }();
+    if (!fp64_only && pmask == (1 << dim) - 1 && rc2max > 0.0) {
+        double lmax = 0.0;
+        for (int k = 0; k < dim; ++k) lmax = fmax(lmax, box->length[k]);
+        const double reach = sqrt(rc2max) * (1.0 + 1e-6) + lmax * (1.0 / 1048576.0);
+        a.rc2_f = (float)(reach * reach * (1.0 + 1e-6));
+        for (int k = 0; k < dim; ++k) a.half_f[k] = (float)a.box.half[k];
+        TMD_CHECK(arena_get(SLOT_CELL_KEYS, (size_t)n * sizeof(float4), (void **)&wrapped_f));
+        a.wrapped_f = wrapped_f;
+        f32 = true;
+    }
+
     const int wblocks = (int)((n + 255) / 256);
-    if (dim == 1) ::tmd::count_launch(), lj_wrap_kernel<1><<<wblocks, 256, 0, s>>>(pos, n, a.box, pmask, wrapped);
-    else if (dim == 2) ::tmd::count_launch(), lj_wrap_kernel<2><<<wblocks, 256, 0, s>>>(pos, n, a.box, pmask, wrapped);
-    else ::tmd::count_launch(), lj_wrap_kernel<3><<<wblocks, 256, 0, s>>>(pos, n, a.box, pmask, wrapped);
+    if (dim == 1) ::tmd::count_launch(), lj_wrap_kernel<1><<<wblocks, 256, 0, s>>>(pos, n, a.box, pmask, wrapped, wrapped_f);
+    else if (dim == 2) ::tmd::count_launch(), lj_wrap_kernel<2><<<wblocks, 256, 0, s>>>(pos, n, a.box, pmask, wrapped, wrapped_f);
+    else ::tmd::count_launch(), lj_wrap_kernel<3><<<wblocks, 256, 0, s>>>(pos, n, a.box, pmask, wrapped, wrapped_f);
     TMD_CUDA(cudaGetLastError());
 
-    if (dim == 1) TMD_CHECK(run_allpairs<1>(a, pmask, blocks, s));
-    else if (dim == 2) TMD_CHECK(run_allpairs<2>(a, pmask, blocks, s));
-    else TMD_CHECK(run_allpairs<3>(a, pmask, blocks, s));
+    if (dim == 1) TMD_CHECK(run_allpairs<1>(a, pmask, f32, blocks, s));
+    else if (dim == 2) TMD_CHECK(run_allpairs<2>(a, pmask, f32, blocks, s));
+    else TMD_CHECK(run_allpairs<3>(a, pmask, f32, blocks, s));
 
     if (flags & TMD_WANT_F) TMD_CHECK(launch_lj_finish(a.partial_f, a.n_split, count, dim, first, flags, force, s));
     // every pair was visited from both of its rows
