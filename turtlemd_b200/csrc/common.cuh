@@ -41,6 +41,7 @@ int require_device();  // TMD_OK or TMD_ERR_NO_DEVICE
 enum ArenaSlot {
     SLOT_PARTIAL_F = 0,   // per-split force partials of the pair kernels
     SLOT_PARTIAL_VW,      // per-block (V, W) partials
+    SLOT_PARTIAL_C,       // symmetric all-pairs kernel: column (reaction) force partials
     SLOT_WRAPPED,         // wrapped / padded copy of the positions (double4 per atom)
     SLOT_TABLE,           // LJ type table on the device
     SLOT_CELL_KEYS,       // cell index per atom
