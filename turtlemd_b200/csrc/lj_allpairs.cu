@@ -624,7 +624,15 @@ extern "C" int tmd_lj_allpairs(const double *pos, const int32_t *tidx, int64_t n
     a.n_itile = (int)((count + kRows - 1) / kRows);
     // enough blocks for ~6 waves of 4 resident blocks per SM, column ranges in whole tiles
     const int64_t n_jtile = (n + kTile - 1) / kTile;
-    int64_t want_split = (int64_t)num_sms() * 4 * 6 / a.n_itile;
+    // (the symmetric kernel leaves the blocks below the diagonal idle: twice as many, so that the busy
+    // half still makes ~6 waves; TMD_AP_WAVES overrides)
+    static const int waves_env = [] {
+        const char *env = getenv("TMD_AP_WAVES");
+        return env ? atoi(env) : 0;
+    }();
+    const bool whole_system = first == 0 && count == n;
+    const int waves = waves_env > 0 ? waves_env : (whole_system ? 12 : 6);
+    int64_t want_split = (int64_t)num_sms() * 4 * waves / a.n_itile;
     if (want_split < 1) want_split = 1;
     if (want_split > n_jtile) want_split = n_jtile;
     const int64_t tiles_per_split = (n_jtile + want_split - 1) / want_split;
