@@ -88,31 +88,37 @@ int num_sms() {
 }
 
 // ---- (V, W) reduction ------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) reduce_vw_kernel(const double *__restrict__ partials, int nblocks,
-                                                        double scale, uint32_t flags, double *__restrict__ vw) {
-    __shared__ double smem[10 * 8];
-    double acc[10];
+// partials: [nblocks][10].  960 threads read the flat array coalesced; 960 is a multiple of 10, so a
+// thread always meets the same component.  Fixed order everywhere -> deterministic.
+constexpr int kReduceThreads = 960;
+
+__global__ void __launch_bounds__(kReduceThreads) reduce_vw_kernel(const double *__restrict__ partials, int nblocks,
+                                                                   double scale, uint32_t flags,
+                                                                   double *__restrict__ vw) {
+    __shared__ double smem[kReduceThreads];
+    const int total = nblocks * 10;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int e = threadIdx.x;
+    for (; e + 3 * kReduceThreads < total; e += 4 * kReduceThreads) {  // four loads in flight
 #pragma unroll
-    for (int k = 0; k < 10; ++k) acc[k] = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += 256) {
-#pragma unroll
-        for (int k = 0; k < 10; ++k) acc[k] += partials[(size_t)b * 10 + k];
+        for (int u = 0; u < 4; ++u) acc[u] += partials[e + u * kReduceThreads];
     }
-    block_sum<10, 256>(acc, smem);
-    if (threadIdx.x == 0) {
+    for (int u = 0; e < total; e += kReduceThreads, ++u) acc[u & 3] += partials[e];
+    smem[threadIdx.x] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        double s = 0.0;
+        for (int q = threadIdx.x; q < kReduceThreads; q += 10) s += smem[q];
         // quantities that were not asked for are left untouched (force() must not clobber v_pot)
         const bool accumulate = flags & TMD_ACCUMULATE;
-        if (flags & TMD_WANT_V) vw[0] = (accumulate ? vw[0] : 0.0) + scale * acc[0];
-        if (flags & TMD_WANT_W) {
-#pragma unroll
-            for (int k = 1; k < 10; ++k) vw[k] = (accumulate ? vw[k] : 0.0) + scale * acc[k];
-        }
+        const int k = threadIdx.x;
+        if (k == 0 ? (flags & TMD_WANT_V) : (flags & TMD_WANT_W)) vw[k] = (accumulate ? vw[k] : 0.0) + scale * s;
     }
 }
 
 int launch_reduce_vw(const double *partials, int nblocks, double scale, uint32_t flags, double *vw,
                      cudaStream_t stream) {
-    ::tmd::count_launch(), reduce_vw_kernel<<<1, 256, 0, stream>>>(partials, nblocks, scale, flags, vw);
+    ::tmd::count_launch(), reduce_vw_kernel<<<1, kReduceThreads, 0, stream>>>(partials, nblocks, scale, flags, vw);
     TMD_CUDA(cudaGetLastError());
     return TMD_OK;
 }
