@@ -200,14 +200,29 @@ def bench_lj(args, cfg, rank, world):
     else:
         integ = VelocityVerlet(cfg["dt"])
         describe += f", VelocityVerlet dt={cfg['dt']}"
-    graphed = False
-    if world > 1:
-        from turtlemd_b200.parallel import AtomDecomposition
+    graphed, parallelism, stepper = False, "single GPU", None
+    if world > 1 or os.environ.get("TMD_BENCH_DECOMP") == "slab1":
+        from turtlemd_b200.parallel import AtomDecomposition, SlabDecomposition
 
-        stepper = AtomDecomposition(system, integ)
+        if os.environ.get("TMD_BENCH_DECOMP", "slab") != "atoms" and cfg["method"] == "nlist" and not cfg.get("dimer"):
+            try:
+                stepper = SlabDecomposition(system, integ)
+                stepper.prepare()
+                parallelism = (f"slab decomposition x{world} (cell-order slot ranges), halo exchange of "
+                               f"{stepper.halo} boundary records with the two neighbours per step (NCCL send/recv), "
+                               "full exchange + re-binning at list rebuilds")
+            except NotImplementedError:
+                stepper = None  # slabs thinner than a halo: replicate positions instead
+                pot = LennardJonesCut(dim=3, shift=True, method=cfg["method"], **extra)
+                pot.set_parameters(SINGLE)
+                system = System(box, Particles.from_arrays(pos, vel=vel, ptype=ptype), [pot])
+        if stepper is None:
+            stepper = AtomDecomposition(system, integ)
+            stepper.prepare()
+            parallelism = f"atom-decomposition x{world}, NCCL all-gather of positions"
         step = stepper.step
-        stepper.prepare()
         graphed = stepper.capture() if os.environ.get("TMD_BENCH_GRAPH", "1") == "1" else False
+        parallelism += ", step replayed from CUDA graphs" if graphed else ", step launched eagerly"
     else:
         system.evaluate(7)
         step = lambda: integ(system)  # noqa: E731
@@ -226,9 +241,7 @@ def bench_lj(args, cfg, rank, world):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"LJ fluid N={n} jittered FCC rho=0.8, rc=2.5 sigma, shifted{describe}, "
                                f"{cfg['method']} kernel",
-                   "n_atoms": n, "parallelism": (f"atom-decomposition x{world}, NCCL all-gather of positions, step "
-                                                 f"{'replayed from a CUDA graph' if graphed else 'launched eagerly'}")
-                   if world > 1 else "single GPU",
+                   "n_atoms": n, "parallelism": parallelism,
                    "l2": (f"positions {pos.nbytes / 1e6:.2f} MB are L2-resident by nature of the workload and the kernel "
                           "is FP64-pipe bound: no L2 flush between steps") if cfg["method"] == "allpairs" else
                          (f"a step streams the state ({6 * pos.nbytes / 1e6:.0f} MB) and, for the list method, "
@@ -239,7 +252,7 @@ def bench_lj(args, cfg, rank, world):
         return None
 
     # ---- single-GPU extras: roofline of the dominant kernel, e2e, CPU baseline ---------------------
-    if world == 1:
+    if world == 1 and stepper is None:
         lib = _lib.load()
         tf, ms = C.c_double(0), C.c_double(0)
         _lib.check(lib.tmd_bench_dfma(5, C.byref(tf), C.byref(ms)))

@@ -150,6 +150,37 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
                  int64_t first, int64_t count,
                  double *force, double *vw, tmd_stream_t stream);
 
+/* Slab path (multi-GPU; also the sorted single-GPU run).  The rows of a rank are the
+ * cell-order SLOTS [slot_first, slot_first+slot_count) of the list's own ordering -- a spatially
+ * compact slab -- and the rank's state lives in slot order: `records` (n x 4 doubles: x, y, z with
+ * the lattice vector of the build removed, type bits) are what the pair kernel gathers from and
+ * what the tmd_slab_* integrator kernels advance, so on several GPUs the records of the boundary
+ * slots are the halo message.  There is no reference counterpart: the reference is one process
+ * (potentials/lennardjones.py:226-273 is still the arithmetic being evaluated).
+ *   tmd_nlist_bind_records  caller-owned record buffer (>= n*4 doubles, 32-byte aligned), before the first build
+ *   tmd_nlist_build_slots   bin ALL n atoms of pos (atom order), lists for the given slot rows;
+ *                           gated != 0: only if the handle's device flag [0] is raised
+ *   tmd_nlist_force_slots   traversal of the current records; force_s is indexed by SLOT (n x dim)
+ *   tmd_nlist_view          device pointers of the handle's tables (valid until the next reallocation) */
+typedef struct tmd_nlist_buffers {
+    double *records;        /* [n][4] current records, cell order                                      */
+    double *build_records;  /* [n][4] records at build time (displacement test)                        */
+    int32_t *order;         /* [n] slot -> atom                                                        */
+    int32_t *slot_of;       /* [n] atom -> slot                                                        */
+    double *image;          /* [n][3] by atom: lattice vector removed at build time                    */
+    int32_t *flags;         /* [8]: [0] rebuild request, [1] rows on the slow path, [2] builds, [3] calls,
+                               [4] / [5] slots below / above the row range that the lists reference    */
+    int32_t cells[3];       /* cell grid                                                               */
+    int32_t half_width;     /* stencil half width in cells                                             */
+    int32_t capacity;       /* list entries per row                                                    */
+} tmd_nlist_buffers;
+int tmd_nlist_bind_records(tmd_nlist *nl, double *records);
+int tmd_nlist_build_slots(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t n, const tmd_box *box,
+                          const double *table, int32_t ntypes, int64_t slot_first, int64_t slot_count,
+                          int32_t gated, tmd_stream_t stream);
+int tmd_nlist_force_slots(tmd_nlist *nl, uint32_t flags, double *force_s, double *vw, tmd_stream_t stream);
+int tmd_nlist_view(tmd_nlist *nl, tmd_nlist_buffers *out);
+
 /* K4. DoubleWell.potential / .force (potentials/well.py:65-81): V = sum a x^4 - b (x-c)^2 over
  * ALL n*dim coordinates, F = -4 a x^3 + 2 b (x - c), virial = 0.                                */
 int tmd_doublewell(const double *pos, int64_t n, int32_t dim, double a, double b, double c,
@@ -254,6 +285,30 @@ int tmd_philox_normal_fill(double *out, int64_t count, const tmd_rng *rng, tmd_s
 /* same numbers computed on the HOST by the same source (no device needed) */
 int tmd_host_philox_normal_fill(double *out, int64_t count, uint64_t key, uint64_t offset);
 int tmd_host_philox_raw_fill(uint64_t *out, int64_t count, uint64_t key, uint64_t offset);
+
+/* ---------------------------------------------------------------- slab (slot-ordered) integrators */
+/* The same updates on slot-ordered state (see the slab path above); rows = slots
+ * [slot_first, slot_first+slot_count), arrays indexed by global slot.  The drift kernels also raise
+ * *flag when a row has moved more than sqrt(half_skin2) from its build-time record.
+ * VelocityVerlet first half (integrators.py:88-90); the second half is tmd_vv_kick on offset pointers. */
+int tmd_slab_vv_kick_drift(double *records, double *vel_s, const double *force_s, const double *imass_s,
+                           const double *build_records, int64_t slot_first, int64_t slot_count, int32_t dim,
+                           double dt, double half_skin2, int32_t *flag, tmd_stream_t stream);
+/* LangevinInertia part 1 (integrators.py:265-279); noise addressed by atom index order[slot], i.e.
+ * the same draws as tmd_langevin_inertia_pre; part 2 is tmd_langevin_inertia_post on offset pointers. */
+int tmd_slab_langevin_inertia_pre(double *records, double *vel_s, const double *force_s, const double *imass_s,
+                                  const double *build_records, const int32_t *order, int64_t slot_first,
+                                  int64_t slot_count, int32_t dim, const tmd_langevin_consts *consts,
+                                  const tmd_rng *rng, double half_skin2, int32_t *flag, tmd_stream_t stream);
+/* slot order -> atom order (pos = record + image); any of pos / vel / force may be NULL.
+ * gate != NULL: do nothing unless *gate != 0 (device-side decision).                              */
+int tmd_slab_unsort(const double *records, const double *vel_s, const double *force_s, const int32_t *order,
+                    const double *image, int64_t n, int32_t dim, double *pos, double *vel, double *force,
+                    const int32_t *gate, tmd_stream_t stream);
+/* atom order -> slot order; any of vel_s / imass_s / force_s may be NULL                          */
+int tmd_slab_sort(const int32_t *order, int64_t n, int32_t dim, const double *vel, const double *imass,
+                  const double *force, double *vel_s, double *imass_s, double *force_s, const int32_t *gate,
+                  tmd_stream_t stream);
 
 /* ---------------------------------------------------------------- observables (next) */
 /* kinetic energy tensor 0.5 sum m v(x)v (system/particles.py:156-168) -> kin[9] (3x3 block)   */

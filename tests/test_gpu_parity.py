@@ -852,6 +852,105 @@ def test_atom_decomposition_three_emulated_ranks_match_single_gpu(kind, method):
         assert rel_norm(w_total, ref_system.particles.virial) < 1e-10
 
 
+# ---- slab decomposition (halo exchange instead of the position all-gather) ----------------------------------
+
+
+def _exchange_by_hand(ranks, full):
+    """What NCCL does between real ranks: copy own slot ranges (all of them, or the halo parts)."""
+    from turtlemd_b200.parallel import halo_ranges
+
+    for dst in ranks:
+        for src in ranks:
+            if src is dst:
+                continue
+            if full:
+                lo, cnt = src.plan.first, src.plan.count
+                dst.records[lo: lo + cnt].copy_(src.records[lo: lo + cnt])
+                dst.vel_s[lo * 3: (lo + cnt) * 3].copy_(src.vel_s[lo * 3: (lo + cnt) * 3])
+                dst.force_s[lo * 3: (lo + cnt) * 3].copy_(src.force_s[lo * 3: (lo + cnt) * 3])
+        if not full:
+            for name in ("recv_up", "recv_down"):
+                peer, a, b = halo_ranges(dst.plan, dst.halo)[name]
+                dst.records[a:b].copy_(ranks[peer].records[a:b])
+
+
+@pytest.mark.parametrize("kind", ["vv", "inertia"])
+@pytest.mark.parametrize("world", [1, 3])
+def test_slab_decomposition_emulated_ranks_match_single_gpu(kind, world):
+    """Ranks emulated in one process: slot-ordered state, halo exchange by hand, full exchange +
+    re-binning when any rank's displacement flag is up.  Result = the single-GPU trajectory."""
+    from turtlemd_b200.parallel import ShardPlan, SlabDecomposition
+    from turtlemd_b200.philox import PhiloxNormal
+
+    k = _pkg()
+    pos, size = _fluid(14)  # N = 10976: 8 cell layers of ~1372 atoms
+    pos = pos + 3.0 * (size[:, 1] - size[:, 0]) * np.random.default_rng(5).integers(-1, 2, size=pos.shape)  # unwrapped input
+    vel = np.random.default_rng(6).standard_normal(pos.shape) * 0.9
+    mass = np.random.default_rng(7).uniform(0.8, 1.6, size=len(pos))
+    steps = 40
+
+    def make():
+        pot = k["LennardJonesCut"](dim=3, shift=True, method="nlist", skin=0.3)
+        pot.set_parameters(SINGLE)
+        system = k["System"](k["Box"](low=size[:, 0], high=size[:, 1]),
+                             k["Particles"].from_arrays(pos, vel=vel, mass=mass), [pot])
+        if kind == "vv":
+            integ = k["integrators"].VelocityVerlet(0.004)
+        else:
+            integ = k["integrators"].LangevinInertia(timestep=0.004, gamma=0.3, beta=1.25, rgen=PhiloxNormal(key=21))
+        return system, integ
+
+    ref_system, ref_integ = make()
+    ref_system.potential_and_force()
+    for _ in range(steps):
+        ref_integ(ref_system)
+
+    ranks = []
+    for r in range(world):
+        system, integ = make()
+        dec = SlabDecomposition(system, integ, plan=ShardPlan(len(pos), world, r))
+        dec.prepare()
+        ranks.append(dec)
+    for _ in range(steps):
+        for dec in ranks:
+            dec.step_move()
+        if any([dec.moved_too_far() for dec in ranks]):
+            _exchange_by_hand(ranks, full=True)
+            for dec in ranks:
+                dec.rebuild()
+        else:
+            _exchange_by_hand(ranks, full=False)
+        for dec in ranks:
+            dec.step_force()
+    assert ranks[0].rebuilds >= 3  # the initial build and at least two on the way
+    _exchange_by_hand(ranks, full=True)
+    v_total, w_total = 0.0, np.zeros((3, 3))
+    for dec in ranks:
+        x, v, f = dec.gather_state()
+        assert rel_norm(x, ref_system.particles.pos) < 1e-11
+        assert rel_norm(v, ref_system.particles.vel) < 1e-9
+        assert rel_norm(f, ref_system.particles.force) < 1e-9
+        v_share, w_share = dec.reduce_observables()
+        v_total += v_share
+        w_total += w_share
+    assert abs(v_total - ref_system.particles.v_pot) <= 1e-10 * abs(ref_system.particles.v_pot)
+    if kind == "vv":
+        assert rel_norm(w_total, ref_system.particles.virial) < 1e-9
+
+
+def test_slab_decomposition_refuses_thin_slabs():
+    from turtlemd_b200.parallel import ShardPlan, SlabDecomposition
+
+    k = _pkg()
+    pos, size = _fluid(10)  # N = 4000: six cell layers, eight ranks would own less than a halo each
+    pot = k["LennardJonesCut"](dim=3, shift=True, method="nlist", skin=0.3)
+    pot.set_parameters(SINGLE)
+    system = k["System"](k["Box"](low=size[:, 0], high=size[:, 1]), k["Particles"].from_arrays(pos), [pot])
+    dec = SlabDecomposition(system, k["integrators"].VelocityVerlet(0.004), plan=ShardPlan(len(pos), 8, 3))
+    with pytest.raises(NotImplementedError):
+        dec.prepare()
+
+
 # ---- observables (SURVEY.md 8f rank 1) ------------------------------------------------------------------------
 
 

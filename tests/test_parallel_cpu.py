@@ -9,7 +9,7 @@ import socket
 import numpy as np
 import pytest
 
-from turtlemd_b200.parallel import ShardPlan, replica_shard
+from turtlemd_b200.parallel import ShardPlan, halo_ranges, replica_shard
 
 
 def test_shard_plan_covers_everything_once():
@@ -83,3 +83,78 @@ def test_two_rank_gather_noise_and_reduce(n, dim):
         assert p.exitcode == 0
     assert sorted(r[0] for r in results) == [0, 1]
     assert all(r[1] and r[2] and r[3] for r in results), results
+
+
+# ---- slab decomposition: halo plan and exchange -----------------------------------------------------------
+
+
+def test_halo_ranges_form_a_ring():
+    """What a rank sends up is what its upper neighbour receives from below, at the same slots;
+    received ranges lie outside the own slab; the ring closes across the periodic boundary."""
+    for n, world, halo in ((1000188, 8, 58000), (10976, 3, 3000), (4000, 2, 1500), (64, 4, 16)):
+        plans = [ShardPlan(n, world, r) for r in range(world)]
+        ranges = [halo_ranges(p, halo) for p in plans]
+        for r, (p, mine) in enumerate(zip(plans, ranges)):
+            up, down = (r + 1) % world, (r - 1) % world
+            assert mine["send_up"] == (up, p.first + p.count - halo, p.first + p.count)
+            assert mine["send_down"] == (down, p.first, p.first + halo)
+            assert ranges[up]["recv_down"] == (r,) + mine["send_up"][1:]
+            assert ranges[down]["recv_up"] == (r,) + mine["send_down"][1:]
+            for name in ("recv_up", "recv_down"):
+                _, a, b = mine[name]
+                assert b - a == halo and 0 <= a and b <= n
+                assert b <= p.first or a >= p.first + p.count
+    with pytest.raises(NotImplementedError):
+        halo_ranges(ShardPlan(100, 4, 0), 26)  # slabs of 25 slots
+
+
+def _halo_worker(rank, world, port, n, halo, queue):
+    import torch
+    import torch.distributed as dist
+
+    from turtlemd_b200.parallel import ShardPlan, halo_exchange, halo_ranges
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = ShardPlan(n, world, rank)
+        truth = torch.arange(plan.padded * 4, dtype=torch.float64).reshape(plan.padded, 4) * 0.25 + 1.0
+        records = torch.full((plan.padded, 4), -7.0, dtype=torch.float64)
+        records[plan.first: plan.first + plan.count] = truth[plan.first: plan.first + plan.count]
+        halo_exchange(records, plan, halo)
+        ok = True
+        for name in ("recv_up", "recv_down"):
+            _, a, b = halo_ranges(plan, halo)[name]
+            ok = ok and bool(torch.equal(records[a:b], truth[a:b]))
+        ok = ok and bool(torch.equal(records[plan.first: plan.first + plan.count],
+                                     truth[plan.first: plan.first + plan.count]))
+        # nothing else was touched
+        mask = torch.ones(plan.padded, dtype=torch.bool)
+        mask[plan.first: plan.first + plan.count] = False
+        for name in ("recv_up", "recv_down"):
+            _, a, b = halo_ranges(plan, halo)[name]
+            mask[a:b] = False
+        ok = ok and bool(torch.all(records[mask] == -7.0))
+        # the rebuild decision: OR of the per-rank displacement flags
+        flag = torch.tensor([1 if rank == world - 1 else 0], dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        queue.put((rank, ok, int(flag.item())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,halo", [(1001, 200), (64, 32)])
+def test_two_rank_halo_exchange(n, halo):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_halo_worker, args=(r, 2, port, n, halo, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [queue.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] and r[2] == 1 for r in results), results

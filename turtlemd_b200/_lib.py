@@ -53,9 +53,20 @@ class LangevinConsts(C.Structure):
         "one_minus_e2", "one_minus_e_sq")]
 
 
+class NlistBuffers(C.Structure):
+    """``tmd_nlist_buffers``: device pointers of a neighbour-list handle (slab path)."""
+
+    _fields_ = [
+        ("records", C.c_void_p), ("build_records", C.c_void_p), ("order", C.c_void_p),
+        ("slot_of", C.c_void_p), ("image", C.c_void_p), ("flags", C.c_void_p),
+        ("cells", C.c_int32 * 3), ("half_width", C.c_int32), ("capacity", C.c_int32),
+    ]
+
+
 _P = C.c_void_p
 _I64, _I32, _U32, _U64, _D = C.c_int64, C.c_int32, C.c_uint32, C.c_uint64, C.c_double
 _BOX, _RNG, _LC = C.POINTER(Box), C.POINTER(Rng), C.POINTER(LangevinConsts)
+_NLB = C.POINTER(NlistBuffers)
 
 # name -> argtypes; every function returns int (tmd_status) unless listed in _NON_STATUS
 PROTOTYPES = {
@@ -86,6 +97,14 @@ PROTOTYPES = {
     "tmd_lj_nlist_usable": [_I64, _BOX, _P, _I32, _D, C.POINTER(C.c_int)],
     "tmd_nlist_stats": [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I32)],
     "tmd_lj_nlist": [_P, _P, _P, _I64, _BOX, _P, _I32, _U32, _I64, _I64, _P, _P, _P],
+    "tmd_nlist_bind_records": [_P, _P],
+    "tmd_nlist_build_slots": [_P, _P, _P, _I64, _BOX, _P, _I32, _I64, _I64, _I32, _P],
+    "tmd_nlist_force_slots": [_P, _U32, _P, _P, _P],
+    "tmd_nlist_view": [_P, _NLB],
+    "tmd_slab_vv_kick_drift": [_P, _P, _P, _P, _P, _I64, _I64, _I32, _D, _D, _P, _P],
+    "tmd_slab_langevin_inertia_pre": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _LC, _RNG, _D, _P, _P],
+    "tmd_slab_unsort": [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P],
+    "tmd_slab_sort": [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P],
     "tmd_doublewell": [_P, _I64, _I32, _D, _D, _D, _U32, _P, _P, _P],
     "tmd_dwpair": [_P, _I64, _BOX, _P, _I32, _P, _I32, _I32, _D, _D, _D, _U32, _P, _P, _P],
     "tmd_vv_kick_drift": [_P, _P, _P, _P, _I64, _I32, _D, _P],

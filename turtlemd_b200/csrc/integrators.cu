@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "philox_normal.h"
 #include "doublewell.cuh"
+#include "integrator_math.cuh"
 
 namespace tmd {
 
@@ -69,11 +70,6 @@ static inline Launch ew_launch(int64_t total) {
     const int64_t e = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); \
     if (e >= total) return;                                               \
     const bool two = (e + 1) < total;
-
-// v += (half*F)*imass   (integrators.py:88 and :94)
-__device__ __forceinline__ double kick(double v, double f, double im, double half) {
-    return __dadd_rn(v, __dmul_rn(__dmul_rn(half, f), im));
-}
 
 // ---- Velocity Verlet -----------------------------------------------------------------------------
 template <int DIM, bool VEC, int KICKS, bool DRIFT>
@@ -149,16 +145,6 @@ __global__ void __launch_bounds__(256) verlet_kernel(double *__restrict__ pos, d
 }
 
 // ---- noise ------------------------------------------------------------------------------------------
-// normals q0 and q0+1 of the stream
-__device__ __forceinline__ void two_normals(uint64_t key, uint64_t q0, bool two, double &z0, double &z1) {
-    if ((q0 & 1ull) == 0) {
-        normal_pair(key, q0 >> 1, z0, z1);
-    } else {
-        z0 = normal_at(key, q0);
-        z1 = two ? normal_at(key, q0 + 1) : 0.0;
-    }
-}
-
 // ---- Langevin, overdamped ------------------------------------------------------------------------
 template <int DIM, bool VEC, bool HOSTNOISE>
 __global__ void __launch_bounds__(256) overdamped_kernel(double *__restrict__ pos, double *__restrict__ vel,
@@ -189,34 +175,6 @@ __global__ void __launch_bounds__(256) overdamped_kernel(double *__restrict__ po
 }
 
 // ---- Langevin with inertia ----------------------------------------------------------------------
-struct InertiaPerParticle {
-    double a2, b1, b2, l00, l10, l11;
-};
-
-__device__ __forceinline__ InertiaPerParticle inertia_constants(const tmd_langevin_consts &c, double im) {
-    InertiaPerParticle p;
-    p.a2 = __dmul_rn(c.a2f, im);  // integrators.py:239-241
-    p.b1 = __dmul_rn(c.b1f, im);
-    p.b2 = __dmul_rn(c.b2f, im);
-    // integrators.py:249-256 and the 2x2 Cholesky of :261
-    const double sr2 = __dmul_rn(__ddiv_rn(__dmul_rn(c.dt, im), c.beta_gamma), c.kfac);
-    const double sv2 = __ddiv_rn(__dmul_rn(c.one_minus_e2, im), c.beta);
-    const double crv = __dmul_rn(__ddiv_rn(im, c.beta_gamma), c.one_minus_e_sq);
-    p.l00 = __dsqrt_rn(sr2);
-    p.l10 = __ddiv_rn(crv, p.l00);
-    p.l11 = __dsqrt_rn(__dsub_rn(sv2, __dmul_rn(p.l10, p.l10)));
-    return p;
-}
-
-__device__ __forceinline__ void inertia_pre_update(double &x, double &v, double f, double xr, double vr,
-                                                   const tmd_langevin_consts &c, const InertiaPerParticle &p) {
-    // pos += a1*vel + a2*force + pos_rand ; vel2 = c0*vel + b1*force + vel_rand (integrators.py:270-279)
-    const double dx = __dadd_rn(__dadd_rn(__dmul_rn(c.a1, v), __dmul_rn(p.a2, f)), xr);
-    const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(c.c0, v), __dmul_rn(p.b1, f)), vr);
-    x = __dadd_rn(x, dx);
-    v = v2;
-}
-
 template <int DIM, bool VEC, bool HOSTNOISE>
 __global__ void __launch_bounds__(256) inertia_pre_kernel(double *__restrict__ pos, double *__restrict__ vel,
                                                           const double *__restrict__ force,

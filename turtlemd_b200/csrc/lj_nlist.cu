@@ -57,10 +57,13 @@ struct NlArgs {
     const double *pos;
     const int32_t *tidx;
     int64_t n, first, count;
+    int row_mode;        // 0: rows are atoms first .. first+count-1, forces indexed by atom;
+                         // 1: rows are cell-order SLOTS first .. first+count-1, forces indexed by slot (slab path)
     int ntypes;
     uint32_t flags;
     NlGrid grid;
-    int *nlflags;        // [0] rebuild, [1] rows on the slow path, [2] builds, [3] calls
+    int *nlflags;        // [0] rebuild, [1] rows on the slow path, [2] builds, [3] calls,
+                         // [4], [5] slots below / above the row range that the lists reference (slab path)
     int *counts;         // [ncells]     zero between builds
     int *starts;         // [ncells + 1]
     int *chunk_sums;     // [ceil(ncells / kScanChunk)]
@@ -107,6 +110,10 @@ struct tmd_nlist {
     int cap;
     int build_blocks[3];  // list-kernel grid per dim (0 = not yet queried)
     int bin_blocks[3];    // cooperative binning grid per dim
+    // slab path (tmd_nlist_build_slots / tmd_nlist_force_slots)
+    int row_mode;         // signature: 0 = atom rows, 1 = slot rows
+    double4 *xs_ext;      // caller-owned current-position records used instead of xs (exchange buffer)
+    tmd::NlArgs *saved;   // launch arguments of the last slot build, reused by the traversal
 };
 
 namespace tmd {
@@ -317,8 +324,8 @@ __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
     const float reach2 = a.reach2f;
     const int cap = a.cap;
     for (int64_t row = (int64_t)blockIdx.x * kNlThreads + tid; row < a.count; row += gthreads) {
-        const int slot = whole ? (int)row : a.slot_of[a.first + row];
-        const int atom = whole ? a.order[slot] : (int)(a.first + row);
+        const int slot = whole ? (int)row : (a.row_mode ? (int)(a.first + row) : a.slot_of[a.first + row]);
+        const int atom = (whole || a.row_mode) ? a.order[slot] : (int)(a.first + row);
         const float4 me = a.xbf[slot];
         const int cell = a.cell_of[atom];
         const int c0 = cell % g.nc[0], c1 = (cell / g.nc[0]) % g.nc[1], c2 = cell / (g.nc[0] * g.nc[1]);
@@ -363,6 +370,31 @@ __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
         }
         a.nneigh[row] = cnt;
     }
+}
+
+// Slab path: how far outside the row range [first, first+count) the lists of those rows reach, in
+// slots.  A row in layer z (slowest direction) references slots of layers z-h .. z+h only, and a
+// layer is a contiguous slot range, so the extents follow from the cell table; they tell the halo
+// exchange how many records of the neighbouring ranks must be current.  nlflags[4] = below, [5] = above.
+__global__ void nl_reach_kernel(const NlArgs a, int dim) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const NlGrid &g = a.grid;
+    const int nz = g.nc[dim - 1];
+    const int layer = g.ncells / nz;
+    const int64_t n = a.n, lo = a.first, hi = a.first + a.count;
+    const int z_lo = a.cell_of[a.order[lo]] / layer, z_hi = a.cell_of[a.order[hi - 1]] / layer;
+    int below, above;
+    if (z_hi - z_lo + 1 + 2 * g.h >= nz) {
+        below = (int)lo;  // the rows and their stencil span every layer: everything is needed
+        above = (int)(n - hi);
+    } else {
+        const int zb = ((z_lo - g.h) % nz + nz) % nz, za = (z_hi + g.h) % nz;
+        const int64_t need_lo = a.starts[zb * layer], need_hi = a.starts[(za + 1) * layer];
+        below = (int)(need_lo <= lo ? lo - need_lo : lo + n - need_lo);
+        above = (int)(need_hi >= hi ? need_hi - hi : need_hi + n - hi);
+    }
+    a.nlflags[4] = below;
+    a.nlflags[5] = above;
 }
 
 template <int G>
@@ -419,8 +451,8 @@ __global__ void __launch_bounds__(kNlThreads, 6) nl_force_kernel(const NlArgs a)
         Row r;
         const int64_t row = base + grp;
         r.valid = row < a.count;
-        r.slot = !r.valid ? 0 : (whole ? (int)row : a.slot_of[a.first + row]);
-        r.atom = !r.valid ? 0 : (whole ? a.order[r.slot] : (int)(a.first + row));
+        r.slot = !r.valid ? 0 : (whole ? (int)row : (a.row_mode ? (int)(a.first + row) : a.slot_of[a.first + row]));
+        r.atom = !r.valid ? 0 : ((whole || a.row_mode) ? a.order[r.slot] : (int)(a.first + row));
         r.me = a.xs[r.slot];
         r.nn = r.valid ? a.nneigh[row] : 0;
         r.e0 = r.e1 = 0u;
@@ -539,7 +571,7 @@ __global__ void __launch_bounds__(kNlThreads, 6) nl_force_kernel(const NlArgs a)
         for (int k = 0; k < DIM; ++k) f[k] = group_sum<G>(facc[k]);
         if (l == 0 && valid) {
             if (flags & TMD_WANT_F) {
-                double *dst = a.force + (int64_t)atom * DIM;
+                double *dst = a.force + (int64_t)(a.row_mode ? slot : atom) * DIM;
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) dst[k] = (flags & TMD_ACCUMULATE) ? dst[k] + f[k] : f[k];
             }
@@ -575,6 +607,8 @@ __global__ void __launch_bounds__(kNlThreads, 6) nl_force_kernel(const NlArgs a)
 // ---- host side -----------------------------------------------------------------------------------
 
 static void nl_release(tmd_nlist *nl) {
+    delete nl->saved;
+    nl->saved = nullptr;
     cudaFree(nl->flags);
     cudaFree(nl->entries);
     cudaFree(nl->nneigh);
@@ -584,6 +618,7 @@ static void nl_release(tmd_nlist *nl) {
     cudaFree(nl->xbf);
     cudaFree(nl->xs);
     cudaFree(nl->image);
+    nl->xs = nullptr;
     nl->flags = nullptr;
     nl->entries = nullptr;
     nl->nneigh = nullptr;
@@ -761,21 +796,12 @@ int tmd_lj_nlist_usable(int64_t n, const tmd_box *box, const double *table, int3
     return TMD_OK;
 }
 
-int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t n, const tmd_box *box,
-                 const double *table, int32_t ntypes, uint32_t flags, int64_t first, int64_t count,
-                 double *force, double *vw, tmd_stream_t stream) {
-    TMD_REQUIRE(nl != nullptr, "nl is NULL");
-    TMD_REQUIRE(box && box->dim >= 1 && box->dim <= 3, "box->dim must be 1..3");
-    TMD_REQUIRE(n >= 0 && first >= 0 && count >= 0 && first + count <= n, "rows [first, first+count) must lie in [0, n)");
-    TMD_REQUIRE(pos || n == 0, "pos is NULL");
-    TMD_REQUIRE(ntypes == 1 || tidx, "tidx is required when ntypes > 1");
-    TMD_REQUIRE(!(flags & TMD_WANT_F) || force, "force is NULL but TMD_WANT_F is set");
-    TMD_REQUIRE(vw != nullptr, "vw is NULL");
-    TMD_CHECK(require_device());
-    cudaStream_t s = as_stream(stream);
+// Everything a call needs apart from pos / tidx / flags / force: coefficient table, grid, (re)allocation,
+// signature check (a change forces a rebuild), pointers.  `same` = the lists of the previous call
+// are still for this system and row range.
+static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double *table, int32_t ntypes,
+                      int64_t first, int64_t count, int row_mode, cudaStream_t s, NlArgs &a, bool &same) {
     const int dim = box->dim;
-
-    NlArgs a;
     double rc2max = 0.0;
     TMD_CHECK(load_lj_table(table, ntypes, a.tab, rc2max));
     const double reach = sqrt(rc2max) + nl->skin;
@@ -784,7 +810,6 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
                   "and 2 <= n < 2^27; use tmd_lj_allpairs", 2 * nl_half_width() + 1, nl_half_width());
         return TMD_ERR_UNSUPPORTED;
     }
-    if (count == 0) return launch_reduce_vw(nullptr, 0, 0.5, flags, vw, s);
 
     // ---- (re)allocate and decide whether the signature changed ----
     bool fresh = false;
@@ -806,8 +831,8 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
         nl->cap_cells = ncells;
         const size_t n_chunks = ((size_t)ncells + kScanChunk - 1) / kScanChunk;
         const size_t n_ints = (size_t)2 * (ncells + 1) + n_chunks + (size_t)5 * n;
-        TMD_CUDA(cudaMalloc(&nl->flags, 4 * sizeof(int)));
-        TMD_CUDA(cudaMemsetAsync(nl->flags, 0, 4 * sizeof(int), s));
+        TMD_CUDA(cudaMalloc(&nl->flags, 8 * sizeof(int)));
+        TMD_CUDA(cudaMemsetAsync(nl->flags, 0, 8 * sizeof(int), s));
         TMD_CUDA(cudaMalloc(&nl->entries, (size_t)nl->cap * count * sizeof(unsigned)));
         TMD_CUDA(cudaMalloc(&nl->nneigh, (size_t)count * sizeof(int)));
         TMD_CUDA(cudaMalloc(&nl->ints, n_ints * sizeof(int)));
@@ -815,12 +840,12 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
         TMD_CUDA(cudaMalloc(&nl->wrapped, (size_t)n * sizeof(double4)));
         TMD_CUDA(cudaMalloc(&nl->xb, (size_t)n * sizeof(double4)));
         TMD_CUDA(cudaMalloc(&nl->xbf, (size_t)n * sizeof(float4)));
-        TMD_CUDA(cudaMalloc(&nl->xs, (size_t)n * sizeof(double4)));
+        if (!nl->xs_ext) TMD_CUDA(cudaMalloc(&nl->xs, (size_t)n * sizeof(double4)));
         TMD_CUDA(cudaMalloc(&nl->image, (size_t)n * 3 * sizeof(double)));
         fresh = true;
     }
-    bool same = !fresh && nl->n == n && nl->first == first && nl->count == count && nl->dim == dim &&
-                nl->ntypes == ntypes && nl->reach == reach;
+    same = !fresh && nl->n == n && nl->first == first && nl->count == count && nl->dim == dim &&
+           nl->ntypes == ntypes && nl->reach == reach && nl->row_mode == row_mode;
     for (int k = 0; k < dim && same; ++k) same = nl->len[k] == box->length[k];
     if (!same) {
         nl->n = n;
@@ -829,20 +854,22 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
         nl->dim = dim;
         nl->ntypes = ntypes;
         nl->reach = reach;
+        nl->row_mode = row_mode;
         for (int k = 0; k < 3; ++k) nl->len[k] = k < dim ? box->length[k] : 0.0;
         // force a build (counts[] is zero: the scan of every build re-zeroes it)
-        static const int one = 1;
-        TMD_CUDA(cudaMemcpyAsync(nl->flags, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+        TMD_CUDA(cudaMemsetAsync(nl->flags, 1, sizeof(int), s));
     }
 
-    a.pos = pos;
-    a.tidx = tidx;
+    a.pos = nullptr;
+    a.tidx = nullptr;
     a.n = n;
     a.first = first;
     a.count = count;
+    a.row_mode = row_mode;
     a.ntypes = ntypes;
-    a.flags = flags;
-    a.force = force;
+    a.flags = 0;
+    a.force = nullptr;
+    a.partial_vw = nullptr;
     a.nlflags = nl->flags;
     {
         const size_t cells1 = (size_t)nl->cap_cells + 1;
@@ -859,13 +886,11 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
     a.wrapped = nl->wrapped;
     a.xb = nl->xb;
     a.xbf = nl->xbf;
-    a.xs = nl->xs;
+    a.xs = nl->xs_ext ? nl->xs_ext : nl->xs;
     a.image = nl->image;
     a.entries = nl->entries;
     a.nneigh = nl->nneigh;
     a.cap = nl->cap;
-    const int fblocks = nl_force_blocks(count, dim);
-    TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)fblocks * 10 * sizeof(double), (void **)&a.partial_vw));
     {
         // single-precision filter: coordinates in [0, L) (+- L after folding the shift) carry an
         // absolute error <= 5 * 2^-24 * L per component, i.e. < 2^-20 * Lmax on the distance
@@ -876,6 +901,42 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
     }
     a.half_skin2 = 0.25 * nl->skin * nl->skin;
     for (int k = 0; k < 3; ++k) a.centre[k] = k < dim ? 0.5 * box->length[k] : 0.0;
+    return TMD_OK;
+}
+
+static int nl_traverse(NlArgs &a, int dim, uint32_t flags, double *force, double *vw, cudaStream_t s) {
+    a.flags = flags;
+    a.force = force;
+    const int fblocks = nl_force_blocks(a.count, dim);
+    TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)fblocks * 10 * sizeof(double), (void **)&a.partial_vw));
+    if (dim == 1) nl_launch_force<1>(a, fblocks, s);
+    else if (dim == 2) nl_launch_force<2>(a, fblocks, s);
+    else nl_launch_force<3>(a, fblocks, s);
+    TMD_CUDA(cudaGetLastError());
+    return launch_reduce_vw(a.partial_vw, fblocks, 0.5, flags, vw, s);
+}
+
+int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t n, const tmd_box *box,
+                 const double *table, int32_t ntypes, uint32_t flags, int64_t first, int64_t count,
+                 double *force, double *vw, tmd_stream_t stream) {
+    TMD_REQUIRE(nl != nullptr, "nl is NULL");
+    TMD_REQUIRE(box && box->dim >= 1 && box->dim <= 3, "box->dim must be 1..3");
+    TMD_REQUIRE(n >= 0 && first >= 0 && count >= 0 && first + count <= n, "rows [first, first+count) must lie in [0, n)");
+    TMD_REQUIRE(pos || n == 0, "pos is NULL");
+    TMD_REQUIRE(ntypes == 1 || tidx, "tidx is required when ntypes > 1");
+    TMD_REQUIRE(!(flags & TMD_WANT_F) || force, "force is NULL but TMD_WANT_F is set");
+    TMD_REQUIRE(vw != nullptr, "vw is NULL");
+    TMD_REQUIRE(nl->xs_ext == nullptr, "this handle is bound to a slab (tmd_nlist_bind_records)");
+    TMD_CHECK(require_device());
+    cudaStream_t s = as_stream(stream);
+    const int dim = box->dim;
+    if (count == 0) return launch_reduce_vw(nullptr, 0, 0.5, flags, vw, s);
+
+    NlArgs a;
+    bool same = false;
+    TMD_CHECK(nl_prepare(nl, n, box, table, ntypes, first, count, 0, s, a, same));
+    a.pos = pos;
+    a.tidx = tidx;
 
     const int nb = (int)((n + 255) / 256);
     if (same) {  // otherwise the flag is already set and order / image / xb are not valid yet
@@ -888,11 +949,71 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
     else if (dim == 2) TMD_CHECK(nl_launch_build<2>(nl, a, s));
     else TMD_CHECK(nl_launch_build<3>(nl, a, s));
     // ---- traversal ----
-    if (dim == 1) nl_launch_force<1>(a, fblocks, s);
-    else if (dim == 2) nl_launch_force<2>(a, fblocks, s);
-    else nl_launch_force<3>(a, fblocks, s);
+    return nl_traverse(a, dim, flags, force, vw, s);
+}
+
+// ---- slab path: rows are cell-order slots, state lives in slot order ------------------------------
+
+int tmd_nlist_bind_records(tmd_nlist *nl, double *records) {
+    TMD_REQUIRE(nl != nullptr, "nl is NULL");
+    TMD_REQUIRE(nl->cap_n == 0, "bind the record buffer before the first build");
+    TMD_REQUIRE((reinterpret_cast<uintptr_t>(records) & 31u) == 0, "records must be 32-byte aligned");
+    nl->xs_ext = reinterpret_cast<double4 *>(records);
+    return TMD_OK;
+}
+
+int tmd_nlist_build_slots(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t n, const tmd_box *box,
+                          const double *table, int32_t ntypes, int64_t slot_first, int64_t slot_count,
+                          int32_t gated, tmd_stream_t stream) {
+    TMD_REQUIRE(nl != nullptr, "nl is NULL");
+    TMD_REQUIRE(box && box->dim >= 1 && box->dim <= 3, "box->dim must be 1..3");
+    TMD_REQUIRE(n >= 2 && slot_first >= 0 && slot_count > 0 && slot_first + slot_count <= n,
+                "slots [slot_first, slot_first+slot_count) must lie in [0, n)");
+    TMD_REQUIRE(pos != nullptr, "pos is NULL");
+    TMD_REQUIRE(ntypes == 1 || tidx, "tidx is required when ntypes > 1");
+    TMD_CHECK(require_device());
+    cudaStream_t s = as_stream(stream);
+    const int dim = box->dim;
+    NlArgs a;
+    bool same = false;
+    TMD_CHECK(nl_prepare(nl, n, box, table, ntypes, slot_first, slot_count, 1, s, a, same));
+    a.pos = pos;
+    a.tidx = tidx;
+    if (!gated) TMD_CUDA(cudaMemsetAsync(nl->flags, 1, sizeof(int), s));  // any non-zero value raises the flag
+    if (dim == 1) TMD_CHECK(nl_launch_build<1>(nl, a, s));
+    else if (dim == 2) TMD_CHECK(nl_launch_build<2>(nl, a, s));
+    else TMD_CHECK(nl_launch_build<3>(nl, a, s));
+    ::tmd::count_launch(), nl_reach_kernel<<<1, 32, 0, s>>>(a, dim);
     TMD_CUDA(cudaGetLastError());
-    return launch_reduce_vw(a.partial_vw, fblocks, 0.5, flags, vw, s);
+    if (!nl->saved) {
+        nl->saved = new (std::nothrow) NlArgs();
+        if (!nl->saved) return TMD_ERR_NOMEM;
+    }
+    *nl->saved = a;
+    return TMD_OK;
+}
+
+int tmd_nlist_force_slots(tmd_nlist *nl, uint32_t flags, double *force_s, double *vw, tmd_stream_t stream) {
+    TMD_REQUIRE(nl != nullptr && nl->saved != nullptr, "no slot build on this handle");
+    TMD_REQUIRE(!(flags & TMD_WANT_F) || force_s, "force_s is NULL but TMD_WANT_F is set");
+    TMD_REQUIRE(vw != nullptr, "vw is NULL");
+    NlArgs a = *nl->saved;
+    return nl_traverse(a, nl->dim, flags, force_s, vw, as_stream(stream));
+}
+
+int tmd_nlist_view(tmd_nlist *nl, tmd_nlist_buffers *out) {
+    TMD_REQUIRE(nl != nullptr && nl->saved != nullptr && out != nullptr, "no slot build on this handle");
+    const NlArgs &a = *nl->saved;
+    out->records = reinterpret_cast<double *>(a.xs);
+    out->build_records = reinterpret_cast<double *>(a.xb);
+    out->order = a.order;
+    out->slot_of = a.slot_of;
+    out->image = a.image;
+    out->flags = a.nlflags;
+    for (int k = 0; k < 3; ++k) out->cells[k] = a.grid.nc[k];
+    out->half_width = a.grid.h;
+    out->capacity = a.cap;
+    return TMD_OK;
 }
 
 }  // extern "C"

@@ -10,6 +10,12 @@ The reference is single-process; this module is what the B
   all-gathers the new positions over NVLink (NCCL, in place, equal padded shards).  Energy and
   virial are per-rank shares that are all-reduced only when somebody looks.  A single-GPU run is
   the yardstick: forces agree to summation order (<= 1e-12).
+* :class:`SlabDecomposition` -- the same system, but every rank owns a spatial SLAB: a contiguous
+  range of the neighbour list's cell-order slots, with its state (records, velocities, forces) kept
+  in that order.  The integrator kernels advance the records the pair kernel gathers from, so per
+  step a rank only exchanges the records of its boundary slots with its two neighbours (a few
+  hundred kB instead of the whole position array) and nothing else scales with N; the whole state
+  is exchanged only when the lists are rebuilt (every ~10 steps), which also re-assigns the slabs.
 * :func:`replica_shard` -- independent replica ensembles (the infretis use case): rank r holds
   replicas ``[r*n, (r+1)*n)`` of a global ensemble, no communication at all; the noise of replica
   i depends only on its global index (counter-based stream), so any sharding gives the same
@@ -20,6 +26,7 @@ The reference is single-process; this module is what the B
 from __future__ import annotations
 
 import ctypes as C
+import math
 from dataclasses import dataclass
 
 import numpy as np
@@ -266,3 +273,337 @@ class AtomDecomposition:
             out.append(dev.cpu().numpy().reshape(self.n, dim))
         del dist
         return tuple(out)
+
+
+def halo_ranges(plan: ShardPlan, halo: int) -> dict[str, tuple[int, int, int]]:
+    """Slot ranges of one halo exchange for ``plan.rank``: name -> (peer, begin, end).
+
+    A rank sends the first ``halo`` slots it owns to the rank below and the last ``halo`` to the rank
+    above, and receives the corresponding ranges of its neighbours at the SAME slot indices (records
+    are stored by global slot on every rank).  Ranks form a ring: the slot order is periodic because
+    the box is.  Pure host logic (tested on CPU)."""
+    world, rank = plan.world, plan.rank
+    prev, nxt = (rank - 1) % world, (rank + 1) % world
+    lo, hi = plan.first, plan.first + plan.count
+    nlo, ncnt = plan.bounds(nxt)
+    plo, pcnt = plan.bounds(prev)
+    if halo > min(plan.count, ncnt, pcnt):
+        raise NotImplementedError(
+            f"halo of {halo} slots exceeds a slab of {min(plan.count, ncnt, pcnt)}: too many ranks for this "
+            "system, use AtomDecomposition")
+    return {
+        "send_down": (prev, lo, lo + halo),
+        "send_up": (nxt, hi - halo, hi),
+        "recv_up": (nxt, nlo, nlo + halo),
+        "recv_down": (prev, plo + pcnt - halo, plo + pcnt),
+    }
+
+
+def halo_exchange(records, plan: ShardPlan, halo: int, group=None) -> None:
+    """Exchange the boundary records with the two neighbouring ranks (NCCL send/recv on CUDA
+    tensors, gloo on CPU tensors).  ``records`` is (padded, width); rows = global slots."""
+    import torch.distributed as dist
+
+    if plan.world == 1 or halo == 0:
+        return
+    r = halo_ranges(plan, halo)
+    ops = []
+    for name in ("send_down", "send_up"):
+        peer, a, b = r[name]
+        ops.append(dist.P2POp(dist.isend, records[a:b], peer, group))
+    for name in ("recv_up", "recv_down"):  # the peer's send_down is my recv_up: same order on both sides
+        peer, a, b = r[name]
+        ops.append(dist.P2POp(dist.irecv, records[a:b], peer, group))
+    for work in dist.batch_isend_irecv(ops):
+        work.wait()
+
+
+class SlabDecomposition:
+    """One LJ system stepped by ``world`` GPUs, each owning a slab of cell-order slots.
+
+    Per step and rank: one fused kick+drift(+displacement test) kernel over the own slots, a halo
+    exchange of boundary records with the two neighbours, the list traversal for the own rows, the
+    closing kick.  The displacement flags are OR-ed over the ranks (a 4-byte all-reduce) and read by
+    the host; when set, every rank all-gathers records and velocities, re-bins the whole system
+    (identical result everywhere), takes its new slot range and rebuilds its lists.
+    ``world == 1`` is the sorted single-GPU run (no exchange).
+
+    The trajectory equals the single-GPU one up to rounding: positions advance as records
+    (``x - lattice vector``), forces sum in list order."""
+
+    def __init__(self, system, integrator, group=None, plan: ShardPlan | None = None):
+        import torch.distributed as dist
+
+        if not isinstance(integrator, (VelocityVerlet, LangevinInertia)):
+            raise NotImplementedError("SlabDecomposition supports VelocityVerlet and LangevinInertia")
+        if isinstance(integrator, LangevinInertia) and not _is_device_stream(integrator.rgen):
+            raise NotImplementedError("sharded Langevin dynamics needs the counter-based PhiloxNormal stream")
+        pots = system.potentials
+        if len(pots) != 1 or not isinstance(pots[0], LennardJonesCut):
+            raise NotImplementedError("SlabDecomposition steps systems with a single LennardJonesCut potential")
+        self.system, self.integrator, self.group, self.pot = system, integrator, group, pots[0]
+        self.n, self.dim = system.particles._pos.shape
+        if plan is not None:  # tests emulate several ranks in one process and exchange by hand
+            self.world, self.rank, self.plan = plan.world, plan.rank, plan
+            self._collectives = False
+        else:
+            self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+            self.plan = ShardPlan(self.n, self.world, self.rank)
+            self._collectives = self.world > 1
+        self.halo = 0
+        self.rebuilds = 0
+        self._graphs = None
+        self._graph_launches = {}
+
+    # ---- set-up -----------------------------------------------------------------------------------
+    def prepare(self) -> None:
+        """Upload the state, build the lists for this rank's slab, evaluate the initial forces."""
+        _device.require_cuda()
+        torch = _device.torch()
+        part, plan, dim, n = self.system.particles, self.plan, self.dim, self.n
+        if plan.count == 0:
+            raise NotImplementedError("more ranks than atoms")
+        self.records = _device.zeros((plan.padded, 4))
+        self.vel_s = _device.zeros(plan.padded * dim)
+        self.force_s = _device.zeros(plan.padded * dim)
+        self.imass_s = _device.zeros(plan.padded)
+        self._flag = _device.zeros(1, dtype="int32")
+        self._flag_host = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+        self._reach_host = torch.zeros(8, dtype=torch.int32, pin_memory=True)
+        types, table, tidx = self.pot._tables(part)
+        self._table, self._ntypes = table, len(types)
+        self._tidx = part._static_device(f"lj_tidx_{id(self.pot)}", tidx, np.int32) if len(types) > 1 else None
+        self._box = self.system.box.to_abi()
+        self._half_skin2 = 0.25 * float(self.pot.skin) ** 2
+        self._nl = self.pot._nlist_handle()
+        _lib.call("tmd_nlist_bind_records", self._nl, _device.dptr(self.records))
+        part._pos.device()
+        part._vel.device()
+        part._force.device_uninitialised(n * dim).zero_()
+        part._force.written_on_device(shape=part._pos.shape)
+        if isinstance(self.integrator, LangevinInertia):
+            self.integrator.initiate_parameters(self.system)
+        self._build()
+        if self.world > 1:
+            self._agree_on_halo()
+        self._force(_ALL)
+
+    def _view(self):
+        view = _lib.NlistBuffers()
+        _lib.call("tmd_nlist_view", self._nl, C.byref(view))
+        return view
+
+    def _build(self) -> None:
+        """Bin all atoms of the atom-ordered position array, lists for the own slots, sort the state."""
+        part, plan, dim = self.system.particles, self.plan, self.dim
+        stream = _device.stream_ptr()
+        pos, vel = part._pos.device(), part._vel.device()
+        _lib.call("tmd_nlist_build_slots", self._nl, _device.dptr(pos),
+                  _device.dptr(self._tidx) if self._tidx is not None else None, self.n, C.byref(self._box),
+                  _lib.hptr(self._table), self._ntypes, plan.first, plan.count, 0, stream)
+        self._v = self._view()
+        if self._v.records != self.records.data_ptr():
+            raise RuntimeError("neighbour list does not use the bound record buffer")
+        _lib.call("tmd_slab_sort", self._v.order, self.n, dim, _device.dptr(vel), _device.dptr(part._imass_device()),
+                  None, _device.dptr(self.vel_s), _device.dptr(self.imass_s), None, None, stream)
+        self.rebuilds += 1
+
+    def needed_halo(self) -> int:
+        """Slots beyond the own range that the current lists reference (synchronises)."""
+        torch = _device.torch()
+        _lib.call("tmd_memcpy_d2h_async", C.c_void_p(self._reach_host.data_ptr()), self._v.flags, 32,
+                  _device.stream_ptr())
+        torch.cuda.current_stream().synchronize()
+        return int(max(self._reach_host[4], self._reach_host[5]))
+
+    def _agree_on_halo(self) -> None:
+        """Halo width in slots, the same on every rank without talking: the lists of a row in layer z
+        (slowest direction) reference layers z-h .. z+h, and the slab boundary may sit anywhere inside
+        a layer, so up to h+1 layers of the neighbour are needed; +10 % for uneven layers.  Each rank
+        then checks its own lists against it."""
+        v = self._v
+        layers = int(v.cells[self.dim - 1])
+        halo = int(math.ceil((v.half_width + 1) * self.n / layers * 1.10)) + 64
+        self.halo = min(halo, min(self.plan.all_counts()))
+        halo_ranges(self.plan, self.halo)  # raises when a slab is thinner than the halo
+        need = self.needed_halo()
+        if self._collectives:  # the same verdict on every rank
+            import torch.distributed as dist
+
+            torch = _device.torch()
+            worst = torch.tensor([need], device="cuda", dtype=torch.int64)
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.group)
+            need = int(worst.item())
+        if need > self.halo:
+            raise NotImplementedError(
+                f"the lists of rank {self.rank} reach {need} slots beyond its slab, more than the halo of "
+                f"{self.halo}: too many ranks for this system, use AtomDecomposition")
+
+    # ---- pieces of a step ---------------------------------------------------------------------------
+    def _own(self, tensor, width):
+        lo = self.plan.first * width
+        return tensor[lo: lo + self.plan.count * width]
+
+    def _force(self, flags: int) -> None:
+        vw = self.system.particles._vw_buffer()
+        _lib.call("tmd_nlist_force_slots", self._nl, flags,
+                  _device.dptr(self.force_s) if flags & _lib.WANT_F else None, _device.dptr(vw), _device.stream_ptr())
+
+    def step_move(self) -> None:
+        """Kick + drift of the own slots (records advance in place) and the displacement test."""
+        plan, dim, integ, v = self.plan, self.dim, self.integrator, self._v
+        stream = _device.stream_ptr()
+        self._flag.zero_()
+        args = (_device.dptr(self.records), _device.dptr(self.vel_s), _device.dptr(self.force_s),
+                _device.dptr(self.imass_s), v.build_records)
+        if isinstance(integ, VelocityVerlet):
+            _lib.call("tmd_slab_vv_kick_drift", *args, plan.first, plan.count, dim, float(integ.timestep),
+                      self._half_skin2, _device.dptr(self._flag), stream)
+        else:
+            rng = _lib.Rng(integ.rgen.key, integ.rgen.position)
+            integ.rgen.advance(2 * self.n * dim)  # the stream moves on by the GLOBAL draw count on every rank
+            _lib.call("tmd_slab_langevin_inertia_pre", *args, v.order, plan.first, plan.count, dim,
+                      C.byref(integ._consts), C.byref(rng), self._half_skin2, _device.dptr(self._flag), stream)
+
+    def step_force(self) -> None:
+        """Forces for the own rows from the current records and the closing velocity update."""
+        plan, dim, integ = self.plan, self.dim, self.integrator
+        vel, force = self._own(self.vel_s, dim), self._own(self.force_s, dim)
+        imass = self._own(self.imass_s, 1)
+        stream = _device.stream_ptr()
+        if isinstance(integ, VelocityVerlet):
+            self._force(_ALL)
+            _lib.call("tmd_vv_kick", _device.dptr(vel), _device.dptr(force), _device.dptr(imass), plan.count, dim,
+                      float(integ.timestep), stream)
+        else:
+            self._force(_lib.WANT_F | _lib.WANT_W)
+            _lib.call("tmd_langevin_inertia_post", _device.dptr(vel), _device.dptr(force), _device.dptr(imass),
+                      plan.count, dim, C.byref(integ._consts), stream)
+            self._force(_lib.WANT_V | _lib.V_STANDALONE)
+
+    def moved_too_far(self) -> bool:
+        """This rank's displacement flag of the last :meth:`step_move` (synchronises)."""
+        torch = _device.torch()
+        self._flag_host.copy_(self._flag)
+        torch.cuda.current_stream().synchronize()
+        return bool(self._flag_host[0])
+
+    def unsort(self, with_force: bool = False) -> None:
+        """Slot-ordered state of ALL slots -> the atom-ordered device arrays of ``system.particles``."""
+        part, dim, v = self.system.particles, self.dim, self._v
+        pos, vel = part._pos.device_uninitialised(self.n * dim), part._vel.device_uninitialised(self.n * dim)
+        force = part._force.device_uninitialised(self.n * dim) if with_force else None
+        _lib.call("tmd_slab_unsort", _device.dptr(self.records), _device.dptr(self.vel_s),
+                  _device.dptr(self.force_s) if with_force else None, v.order, v.image, self.n, dim,
+                  _device.dptr(pos), _device.dptr(vel), _device.dptr(force) if with_force else None, None,
+                  _device.stream_ptr())
+        part._pos.written_on_device()
+        part._vel.written_on_device()
+        if with_force:
+            part._force.written_on_device()
+
+    def rebuild(self) -> None:
+        """After the FULL exchange of records and velocities: new cell order, new slabs, new lists."""
+        self.unsort()
+        self._build()
+        if self.world > 1:
+            self._agree_on_halo()
+
+    def _exchange_full(self, with_force: bool = False) -> None:
+        if not self._collectives:
+            return
+        plan, dim = self.plan, self.dim
+        all_gather_padded(self.records.view(-1), plan, 4, self.group)
+        all_gather_padded(self.vel_s, plan, dim, self.group)
+        if with_force:
+            all_gather_padded(self.force_s, plan, dim, self.group)
+
+    def step(self) -> None:
+        """One integration step (all ranks call this together)."""
+        import torch.distributed as dist
+
+        torch = _device.torch()
+        g = self._graphs
+        if g is not None:
+            g["move"].replay()
+            _lib.add_launches(self._graph_launches["move"])
+            torch.cuda.current_stream().synchronize()
+            if self._flag_host[0]:
+                self._exchange_full()
+                self.rebuild()
+                g["force"].replay()
+                _lib.add_launches(self._graph_launches["force"])
+            else:
+                g["halo_force"].replay()
+                _lib.add_launches(self._graph_launches["halo_force"])
+            return
+        self.step_move()
+        if self._collectives:
+            dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self.group)
+        if self.moved_too_far():
+            self._exchange_full()
+            self.rebuild()
+        elif self._collectives:
+            halo_exchange(self.records, self.plan, self.halo, self.group)
+        self.step_force()
+
+    def capture(self, warm_steps: int = 3) -> bool:
+        """Record the three pieces of a step in CUDA graphs (move + flag all-reduce + flag download;
+        halo exchange + forces + kick; forces + kick after a rebuild).  VelocityVerlet only (the
+        Langevin kernels take the stream offset as a launch parameter)."""
+        import torch.distributed as dist
+
+        if not isinstance(self.integrator, VelocityVerlet) or self._graphs is not None:
+            return self._graphs is not None
+        torch = _device.torch()
+        for _ in range(warm_steps):
+            self.step()
+        torch.cuda.synchronize()
+        graphs, launches = {}, {}
+
+        def move():
+            self.step_move()
+            if self._collectives:
+                dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self.group)
+            self._flag_host.copy_(self._flag, non_blocking=True)
+
+        def halo_force():
+            if self._collectives:
+                halo_exchange(self.records, self.plan, self.halo, self.group)
+            self.step_force()
+
+        try:
+            for name, fn in (("move", move), ("halo_force", halo_force), ("force", self.step_force)):
+                graph = torch.cuda.CUDAGraph()
+                before = _lib.launch_count()
+                with torch.cuda.graph(graph):
+                    fn()
+                launches[name] = _lib.launch_count() - before
+                _lib.add_launches(-launches[name])  # recording is not launching
+                graphs[name] = graph
+        except Exception:  # noqa: BLE001 - capture is an optimisation; eager stepping stays correct
+            torch.cuda.synchronize()
+            return False
+        # the recording did not execute anything: the state is that of the last eager step
+        self._graphs, self._graph_launches = graphs, launches
+        return True
+
+    # ---- looking at the result ------------------------------------------------------------------------
+    def reduce_observables(self) -> tuple[float, np.ndarray]:
+        """All-reduce the (V, W) shares; returns (v_pot, virial) of the whole system on every rank."""
+        import torch.distributed as dist
+
+        vw = self.system.particles._vw_buffer().clone()
+        if self._collectives:
+            dist.all_reduce(vw, group=self.group)
+        host = vw.cpu().numpy()
+        return float(host[0]), host[1:].reshape(3, 3)[: self.dim, : self.dim].copy()
+
+    def gather_state(self):
+        """(pos, vel, force) of the whole system in atom order as host arrays on every rank."""
+        self._exchange_full(with_force=True)
+        self.unsort(with_force=True)
+        part = self.system.particles
+        return tuple(m.device().cpu().numpy().reshape(self.n, self.dim) for m in (part._pos, part._vel, part._force))
+
