@@ -233,6 +233,8 @@ def bench_lj(args, cfg, rank, world):
         sec = timed(step, args.steps, world)
     launches = _lib.launch_count() - launches0
     value = n * args.steps / sec
+    if stepper is not None:
+        stepper.release()
 
     out = {
         "metric": "atom-steps/sec (FP64 LJ force+integrate)", "value": value, "unit": cfg["unit"],
@@ -444,11 +446,19 @@ def main():
     else:
         rank, world, _ = dist_setup(args.gpus)
         out = (bench_replicas if args.workload == "replicas" else bench_lj)(args, cfg, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+            out = None
         if world > 1:
             import torch.distributed as dist
 
+            # the result is out; a communicator that will not shut down must not hang the box
+            watchdog = threading.Timer(60.0, lambda: os._exit(0))
+            watchdog.daemon = True
+            watchdog.start()
             dist.barrier()
             dist.destroy_process_group()
+            watchdog.cancel()
     if out is not None:
         print(json.dumps(out))
 

@@ -169,7 +169,8 @@ typedef struct tmd_nlist_buffers {
     int32_t *slot_of;       /* [n] atom -> slot                                                        */
     double *image;          /* [n][3] by atom: lattice vector removed at build time                    */
     int32_t *flags;         /* [8]: [0] rebuild request, [1] rows on the slow path, [2] builds, [3] calls,
-                               [4] / [5] slots below / above the row range that the lists reference    */
+                               [4] / [5] slots below / above the row range that the lists reference,
+                               [6] atoms in the fullest cell layer of the slowest direction              */
     int32_t cells[3];       /* cell grid                                                               */
     int32_t half_width;     /* stencil half width in cells                                             */
     int32_t capacity;       /* list entries per row                                                    */

@@ -1,0 +1,84 @@
+"""Multi-GPU parity check, launched by torch.distributed.run (one rank per GPU, NCCL):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tests/multi_gpu_check.py [slab|atoms] [rep] [steps] [graph]
+
+Every rank steps its share of one LJ fluid with the chosen decomposition; rank 0 also runs the
+plain single-GPU integrator on the same input and compares positions, velocities, forces, energy
+and virial.  Prints one line `MULTI_GPU_CHECK ok ...` (or `FAILED ...`) on rank 0; exit code 1 on
+failure.  tests/test_gpu_parity.py runs it when the box has two or more GPUs."""
+import os
+import pathlib
+import sys
+
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import bench
+from turtlemd_b200.integrators import VelocityVerlet
+from turtlemd_b200.parallel import AtomDecomposition, SlabDecomposition
+from turtlemd_b200.potentials import LennardJonesCut
+from turtlemd_b200.system import Box, Particles, System
+
+
+def main():
+    import faulthandler
+
+    faulthandler.dump_traceback_later(int(os.environ.get("TMD_CHECK_WATCHDOG", "240")), exit=True)  # never hang a GPU box
+    kind = sys.argv[1] if len(sys.argv) > 1 else "slab"
+    rep = int(sys.argv[2]) if len(sys.argv) > 2 else 24
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    graph = len(sys.argv) > 4 and sys.argv[4] == "graph"
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    pos, vel, size = bench.lj_inputs(rep)
+
+    def make():
+        pot = LennardJonesCut(dim=3, shift=True, method="nlist")
+        pot.set_parameters(bench.SINGLE)
+        return System(Box(low=size[:, 0], high=size[:, 1]), Particles.from_arrays(pos, vel=vel), [pot])
+
+    system = make()
+    dec = (SlabDecomposition if kind == "slab" else AtomDecomposition)(system, VelocityVerlet(0.005))
+    dec.prepare()
+    done = 0
+    if graph:
+        if not dec.capture(warm_steps=3):
+            raise RuntimeError("CUDA graph capture failed")
+        done = 3
+    for _ in range(steps - done):
+        dec.step()
+    x, v, f = dec.gather_state()
+    v_pot, virial = dec.reduce_observables()
+    ok, text = True, ""
+    if rank == 0:
+        ref = make()
+        integ = VelocityVerlet(0.005)
+        ref.potential_and_force()
+        for _ in range(steps):
+            integ(ref)
+        scale = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))  # noqa: E731
+        errs = {"pos": scale(x, ref.particles.pos), "vel": scale(v, ref.particles.vel),
+                "force": scale(f, ref.particles.force),
+                "v_pot": abs(v_pot - ref.particles.v_pot) / abs(ref.particles.v_pot),
+                "virial": scale(virial, ref.particles.virial)}
+        ok = errs["pos"] < 1e-11 and errs["vel"] < 1e-9 and errs["force"] < 1e-9 and errs["v_pot"] < 1e-10 \
+            and errs["virial"] < 1e-9
+        extra = f" rebuilds={dec.rebuilds} halo={dec.halo}" if kind == "slab" else ""
+        text = (f"MULTI_GPU_CHECK {'ok' if ok else 'FAILED'} kind={kind} world={world} n={len(pos)} steps={steps} "
+                f"graph={graph}{extra} " + " ".join(f"{k}={e:.2e}" for k, e in errs.items()))
+        print(text, flush=True)
+    if graph:
+        dec.release()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -951,6 +951,28 @@ def test_slab_decomposition_refuses_thin_slabs():
         dec.prepare()
 
 
+@pytest.mark.parametrize("kind,graph", [("slab", ""), ("slab", "graph"), ("atoms", "")])
+def test_two_real_ranks_match_single_gpu(kind, graph):
+    """Two processes, two GPUs, NCCL: tests/multi_gpu_check.py compares the decomposed trajectory with
+    the single-GPU one.  Skipped on a one-GPU box (the emulated-rank tests above cover the logic)."""
+    import socket
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    script = str(GOLDEN.parent / "multi_gpu_check.py")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), script, kind, "24", "40"] + ([graph] if graph else [])
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
+    assert proc.returncode == 0 and "MULTI_GPU_CHECK ok" in proc.stdout, proc.stdout[-3000:] + proc.stderr[-3000:]
+
+
 # ---- observables (SURVEY.md 8f rank 1) ------------------------------------------------------------------------
 
 

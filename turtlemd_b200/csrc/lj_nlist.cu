@@ -375,7 +375,8 @@ __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
 // Slab path: how far outside the row range [first, first+count) the lists of those rows reach, in
 // slots.  A row in layer z (slowest direction) references slots of layers z-h .. z+h only, and a
 // layer is a contiguous slot range, so the extents follow from the cell table; they tell the halo
-// exchange how many records of the neighbouring ranks must be current.  nlflags[4] = below, [5] = above.
+// exchange how many records of the neighbouring ranks must be current.  nlflags[4] = below, [5] = above,
+// [6] = atoms in the fullest layer.
 __global__ void nl_reach_kernel(const NlArgs a, int dim) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const NlGrid &g = a.grid;
@@ -395,6 +396,9 @@ __global__ void nl_reach_kernel(const NlArgs a, int dim) {
     }
     a.nlflags[4] = below;
     a.nlflags[5] = above;
+    int most = 0;  // fullest layer: with the stencil width it bounds what any slab can ever need
+    for (int z = 0; z < nz; ++z) most = max(most, a.starts[(z + 1) * layer] - a.starts[z * layer]);
+    a.nlflags[6] = most;
 }
 
 template <int G>

@@ -201,6 +201,13 @@ class AtomDecomposition:
         self._graph = graph
         return True
 
+    def release(self) -> None:
+        """Drop the captured graph (do this before destroying the process group: a CUDA graph that
+        holds NCCL kernels keeps the communicator busy)."""
+        if self._graph is not None:
+            _device.torch().cuda.synchronize()
+            self._graph = None
+
     def _step_args(self):
         part, plan = self.system.particles, self.plan
         pos, vel = self._own(part._pos.device()), self._own(part._vel.device())
@@ -384,9 +391,10 @@ class SlabDecomposition:
         part._force.written_on_device(shape=part._pos.shape)
         if isinstance(self.integrator, LangevinInertia):
             self.integrator.initiate_parameters(self.system)
+        self._reach_event = None
         self._build()
         if self.world > 1:
-            self._agree_on_halo()
+            self._agree_on_halo(first=True)
         self._force(_ALL)
 
     def _view(self):
@@ -409,36 +417,59 @@ class SlabDecomposition:
                   None, _device.dptr(self.vel_s), _device.dptr(self.imass_s), None, None, stream)
         self.rebuilds += 1
 
-    def needed_halo(self) -> int:
-        """Slots beyond the own range that the current lists reference (synchronises)."""
-        torch = _device.torch()
+    def _request_reach(self) -> None:
+        """Asynchronous download of the flag words the build just enqueued will write."""
         _lib.call("tmd_memcpy_d2h_async", C.c_void_p(self._reach_host.data_ptr()), self._v.flags, 32,
                   _device.stream_ptr())
-        torch.cuda.current_stream().synchronize()
-        return int(max(self._reach_host[4], self._reach_host[5]))
+        self._reach_event = _device.torch().cuda.Event()
+        self._reach_event.record()
 
-    def _agree_on_halo(self) -> None:
-        """Halo width in slots, the same on every rank without talking: the lists of a row in layer z
-        (slowest direction) reference layers z-h .. z+h, and the slab boundary may sit anywhere inside
-        a layer, so up to h+1 layers of the neighbour are needed; +10 % for uneven layers.  Each rank
-        then checks its own lists against it."""
-        v = self._v
-        layers = int(v.cells[self.dim - 1])
-        halo = int(math.ceil((v.half_width + 1) * self.n / layers * 1.10)) + 64
-        self.halo = min(halo, min(self.plan.all_counts()))
-        halo_ranges(self.plan, self.halo)  # raises when a slab is thinner than the halo
-        need = self.needed_halo()
-        if self._collectives:  # the same verdict on every rank
-            import torch.distributed as dist
+    def _collect_reach(self) -> tuple[int, int] | None:
+        """(slots beyond the own range that the lists reference, atoms in the fullest cell layer) of the
+        build whose download was requested last; waits for it (a no-op when that was steps ago)."""
+        if self._reach_event is None:
+            return None
+        self._reach_event.synchronize()
+        self._reach_event = None
+        return int(max(self._reach_host[4], self._reach_host[5])), int(self._reach_host[6])
 
-            torch = _device.torch()
-            worst = torch.tensor([need], device="cuda", dtype=torch.int64)
-            dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.group)
-            need = int(worst.item())
+    def needed_halo(self) -> int:
+        """Slots beyond the own range that the current lists reference (synchronises)."""
+        self._request_reach()
+        return self._collect_reach()[0]
+
+    def _agree_on_halo(self, first: bool) -> None:
+        """Halo width in slots, the same on every rank.  The lists of a row in layer z (slowest
+        direction) reference layers z-h .. z+h, and the slab boundary may sit anywhere inside a layer,
+        so up to h+1 layers of the neighbour are needed: sized by the fullest layer (+25 %) at the
+        first build (all ranks bin the whole system identically, so they agree without talking).
+        Layer populations drift (a lattice start melts): every later build's reach is downloaded
+        asynchronously and checked when it has arrived -- an overrun means forces were computed from
+        stale halo records, which is an error, not something to paper over."""
+        thinnest = min(self.plan.all_counts())
+        if first:
+            self._request_reach()
+            need, fullest = self._collect_reach()
+            if self._collectives:  # the same verdict on every rank: prepare() may fall back to another scheme
+                import torch.distributed as dist
+
+                torch = _device.torch()
+                worst = torch.tensor([need], device="cuda", dtype=torch.int64)
+                dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.group)
+                need = int(worst.item())
+            self.halo = min(int(math.ceil((self._v.half_width + 1) * fullest * 1.25)) + 64, thinnest)
+            halo_ranges(self.plan, self.halo)  # raises when a slab is thinner than the halo
+            if need > self.halo:
+                raise NotImplementedError(
+                    f"the lists reach {need} slots beyond a slab, more than the {self.halo} a neighbour can "
+                    "supply: too many ranks for this system, use AtomDecomposition")
+            return
+        previous = self._collect_reach()  # the numbers of the build before this one
+        self._request_reach()             # this build's: looked at next time
+        need = previous[0] if previous else 0
         if need > self.halo:
-            raise NotImplementedError(
-                f"the lists of rank {self.rank} reach {need} slots beyond its slab, more than the halo of "
-                f"{self.halo}: too many ranks for this system, use AtomDecomposition")
+            raise RuntimeError(f"rank {self.rank}: the lists reached {need} slots beyond the slab but the halo "
+                               f"exchange carries {self.halo}; forces since the previous rebuild are invalid")
 
     # ---- pieces of a step ---------------------------------------------------------------------------
     def _own(self, tensor, width):
@@ -508,7 +539,7 @@ class SlabDecomposition:
         self.unsort()
         self._build()
         if self.world > 1:
-            self._agree_on_halo()
+            self._agree_on_halo(first=False)
 
     def _exchange_full(self, with_force: bool = False) -> None:
         if not self._collectives:
@@ -552,42 +583,52 @@ class SlabDecomposition:
         """Record the three pieces of a step in CUDA graphs (move + flag all-reduce + flag download;
         halo exchange + forces + kick; forces + kick after a rebuild).  VelocityVerlet only (the
         Langevin kernels take the stream offset as a launch parameter)."""
-        import torch.distributed as dist
-
         if not isinstance(self.integrator, VelocityVerlet) or self._graphs is not None:
             return self._graphs is not None
         torch = _device.torch()
         for _ in range(warm_steps):
             self.step()
         torch.cuda.synchronize()
-        graphs, launches = {}, {}
+        self._graphs, self._graph_launches = {}, {}
+        try:
+            for name in ("move", "halo_force", "force"):
+                self._record(name)
+        except Exception:  # noqa: BLE001 - capture is an optimisation; eager stepping stays correct
+            torch.cuda.synchronize()
+            self._graphs = None
+            return False
+        return True  # recording executes nothing: the state is that of the last eager step
 
-        def move():
+    def release(self) -> None:
+        """Drop the captured graphs (do this before destroying the process group: a CUDA graph that
+        holds NCCL kernels keeps the communicator busy)."""
+        if self._graphs is not None:
+            _device.torch().cuda.synchronize()
+            self._graphs = None
+
+    def _piece(self, name: str) -> None:
+        import torch.distributed as dist
+
+        if name == "move":
             self.step_move()
             if self._collectives:
                 dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self.group)
             self._flag_host.copy_(self._flag, non_blocking=True)
+            return
+        if name == "halo_force" and self._collectives:
+            halo_exchange(self.records, self.plan, self.halo, self.group)
+        self.step_force()
 
-        def halo_force():
-            if self._collectives:
-                halo_exchange(self.records, self.plan, self.halo, self.group)
-            self.step_force()
-
-        try:
-            for name, fn in (("move", move), ("halo_force", halo_force), ("force", self.step_force)):
-                graph = torch.cuda.CUDAGraph()
-                before = _lib.launch_count()
-                with torch.cuda.graph(graph):
-                    fn()
-                launches[name] = _lib.launch_count() - before
-                _lib.add_launches(-launches[name])  # recording is not launching
-                graphs[name] = graph
-        except Exception:  # noqa: BLE001 - capture is an optimisation; eager stepping stays correct
-            torch.cuda.synchronize()
-            return False
-        # the recording did not execute anything: the state is that of the last eager step
-        self._graphs, self._graph_launches = graphs, launches
-        return True
+    def _record(self, name: str) -> None:
+        torch = _device.torch()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            self._piece(name)
+        self._graph_launches[name] = _lib.launch_count() - before
+        _lib.add_launches(-self._graph_launches[name])  # recording is not launching
+        self._graphs[name] = graph
 
     # ---- looking at the result ------------------------------------------------------------------------
     def reduce_observables(self) -> tuple[float, np.ndarray]:
