@@ -12,7 +12,9 @@ Prints ONE JSON line (rank 0).  Workloads (BASELINE.json configs):
   dimer256k   configs[4]: N=256 000 fluid, two bonded atoms of type 1 (DoubleWellPair) in LJ solvent
   replicas  configs[2]: 1M DoubleWell LangevinInertia replicas (replica-steps/s)
 For --gpus N > 1 (launched by torch.distributed.run) the LJ workloads are atom-decomposed with an
-all-gather of positions each step, the replicas are sharded with no communication.
+all-gather of positions each step (TMD_BENCH_DECOMP=slab: slab decomposition with a halo exchange
+instead -- measured slower at 2 and 8 GPUs in round 1), the replicas are
+sharded with no communication.
 
 value     device-resident throughput (state in HBM when the timed region starts)
 e2e       the same step through the public Python API with HOST arrays: every step re-binds
@@ -204,7 +206,7 @@ def bench_lj(args, cfg, rank, world):
     if world > 1 or os.environ.get("TMD_BENCH_DECOMP") == "slab1":
         from turtlemd_b200.parallel import AtomDecomposition, SlabDecomposition
 
-        if os.environ.get("TMD_BENCH_DECOMP", "slab") != "atoms" and cfg["method"] == "nlist" and not cfg.get("dimer"):
+        if os.environ.get("TMD_BENCH_DECOMP", "atoms") in ("slab", "slab1") and cfg["method"] == "nlist" and not cfg.get("dimer"):
             try:
                 stepper = SlabDecomposition(system, integ)
                 stepper.prepare()

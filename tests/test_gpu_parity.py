@@ -789,6 +789,41 @@ def test_lj_1m_sampled_rows_and_properties(method):
     assert abs(e1 - e0) < 2e-5 * abs(e0)
 
 
+def test_langevin_inertia_on_the_list_path_folds_potential_into_the_force_pass():
+    """LangevinInertia calls force() and then potential() at the same positions (integrators.py:280-282).
+    On the neighbour-list path the energy is taken from the force traversal; it must be the number a
+    separate potential() pass gives, bit for bit, and half the traversals must be launched."""
+    from turtlemd_b200 import _lib
+    from turtlemd_b200.philox import PhiloxNormal
+
+    k = _pkg()
+    pos, size = _fluid(10)
+
+    def make(method):
+        pot = k["LennardJonesCut"](dim=3, shift=True, method=method, skin=0.3)
+        pot.set_parameters(SINGLE)
+        system = k["System"](k["Box"](low=size[:, 0], high=size[:, 1]), k["Particles"].from_arrays(pos), [pot])
+        integ = k["integrators"].LangevinInertia(timestep=0.004, gamma=0.3, beta=1.25, rgen=PhiloxNormal(key=5))
+        system.potential_and_force()
+        return system, integ
+
+    system, integ = make("nlist")
+    assert system.energy_rides_with_forces()
+    integ(system)
+    before = _lib.launch_count()
+    for _ in range(5):
+        integ(system)
+    per_step = (_lib.launch_count() - before) / 5
+    v_step = system.particles.v_pot
+    assert v_step == system.potential()  # a fresh energy-only pass over the same positions
+    other, integ2 = make("allpairs")
+    assert not other.energy_rides_with_forces()  # two formulas there (lennardjones.py:172 vs :254-255): two passes
+    for _ in range(6):
+        integ2(other)
+    assert abs(other.particles.v_pot - v_step) <= 1e-10 * abs(v_step)
+    assert per_step <= 8  # pre, gather/check, 2 gated build kernels, traversal, reduce, post (was 12 with two passes)
+
+
 # ---- atom decomposition (multi-GPU path, ranks emulated on one device) -------------------------------------
 
 

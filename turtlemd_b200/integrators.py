@@ -320,11 +320,15 @@ class LangevinInertia(MDIntegrator):
                   _device.dptr(nvel) if nvel is not None else None, stream)
         part._pos.written_on_device()
         part._vel.written_on_device()
-        system.evaluate(_lib.WANT_F | _lib.WANT_W)
+        # force() and, after the velocity update, potential() -- at the same positions
+        # (integrators.py:280-282): one traversal when that gives the same numbers
+        one_pass = system.energy_rides_with_forces()
+        system.evaluate(_lib.WANT_F | _lib.WANT_W | (_lib.WANT_V if one_pass else 0))
         _lib.call("tmd_langevin_inertia_post", _device.dptr(vel), _device.dptr(part._force.device()),
                   _device.dptr(imass), n, dim, C.byref(self._consts), stream)
         part._vel.written_on_device()
-        system.evaluate(_lib.WANT_V | _lib.V_STANDALONE)
+        if not one_pass:
+            system.evaluate(_lib.WANT_V | _lib.V_STANDALONE)
 
     def run(self, system, steps: int, first: int = 0, n_global: int | None = None):
         """``steps`` steps in ONE kernel for a DoubleWell-only system with the in-kernel stream.

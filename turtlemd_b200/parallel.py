@@ -244,11 +244,13 @@ class AtomDecomposition:
                 _lib.call("tmd_vv_kick", _device.dptr(vel), _device.dptr(force), _device.dptr(imass),
                           plan.count, dim, float(integ.timestep), stream)
         else:
-            self._evaluate(_lib.WANT_F | _lib.WANT_W)
+            one_pass = self.system.energy_rides_with_forces()
+            self._evaluate(_lib.WANT_F | _lib.WANT_W | (_lib.WANT_V if one_pass else 0))
             if plan.count:
                 _lib.call("tmd_langevin_inertia_post", _device.dptr(vel), _device.dptr(force), _device.dptr(imass),
                           plan.count, dim, C.byref(integ._consts), stream)
-            self._evaluate(_lib.WANT_V | _lib.V_STANDALONE)
+            if not one_pass:
+                self._evaluate(_lib.WANT_V | _lib.V_STANDALONE)
         self.system.particles._vel.written_on_device()
 
     # ---- looking at the result ------------------------------------------------------------------------
@@ -508,10 +510,9 @@ class SlabDecomposition:
             _lib.call("tmd_vv_kick", _device.dptr(vel), _device.dptr(force), _device.dptr(imass), plan.count, dim,
                       float(integ.timestep), stream)
         else:
-            self._force(_lib.WANT_F | _lib.WANT_W)
+            self._force(_ALL)  # force() and potential() at the same positions (integrators.py:280-282): one traversal
             _lib.call("tmd_langevin_inertia_post", _device.dptr(vel), _device.dptr(force), _device.dptr(imass),
                       plan.count, dim, C.byref(integ._consts), stream)
-            self._force(_lib.WANT_V | _lib.V_STANDALONE)
 
     def moved_too_far(self) -> bool:
         """This rank's displacement flag of the last :meth:`step_move` (synchronises)."""

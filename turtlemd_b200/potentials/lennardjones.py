@@ -167,6 +167,22 @@ class LennardJonesCut(Potential):
             return "tmd_lj_nlist"
         return "tmd_lj_cells" if self._use_cells(npart, box_abi, table, ntyp) else "tmd_lj_allpairs"
 
+    def _energy_is_pass_independent(self, system) -> bool:
+        """The neighbour-list traversal forms r6inv the same way whether or not forces are asked for
+        (it ignores TMD_V_STANDALONE), so V of a combined pass equals V of an energy-only pass bit for
+        bit.  The all-pairs and cell kernels follow the reference's two formulas (lennardjones.py:172
+        vs :254-255), which differ in the last place: there the two passes are kept."""
+        particles = system.particles
+        if particles.npart < 2:
+            return True
+        key = (particles.npart, tuple(np.asarray(system.box.length, dtype=float).tolist()), id(particles.ptype), self.method)
+        cached = getattr(self, "_pass_cache", None)
+        if cached is None or cached[0] != key:
+            types, table, _ = self._tables(particles)
+            name = self._kernel_for(particles.npart, system.box.to_abi(), table, len(types))
+            cached = self._pass_cache = (key, name == "tmd_lj_nlist")
+        return cached[1]
+
     def _use_cells(self, npart, box_abi, table, ntyp) -> bool:
         if self.method == "allpairs":
             return False

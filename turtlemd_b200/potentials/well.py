@@ -42,6 +42,9 @@ class DoubleWell(Potential):
     def _abc(self):
         return float(self.params["a"]), float(self.params["b"]), float(self.params["c"])
 
+    def _energy_is_pass_independent(self, system) -> bool:
+        return True  # one formula for V whatever else is computed (well.py)
+
     def _launch(self, system, pos, force, vw, flags):
         particles = system.particles
         shape = particles._pos.shape
@@ -140,6 +143,9 @@ class DoubleWellPair(Potential):
             dev1 = _device.to_device(idx1) if len(idx1) else None
             cache = self._cache = (ptype, len(ptype), idx0, idx1, dev0, dev1)
         return cache[2:]
+
+    def _energy_is_pass_independent(self, system) -> bool:
+        return True  # one formula for V whatever else is computed (well.py)
 
     def _launch(self, system, pos, force, vw, flags):
         particles = system.particles

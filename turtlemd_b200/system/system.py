@@ -66,6 +66,19 @@ class System:
             particles._vw_fresh.add("virial")
         return True
 
+    def energy_rides_with_forces(self) -> bool:
+        """True when evaluating V in the same pass as F and W gives the very numbers a separate
+        ``potential()`` pass would (every potential says so through ``_energy_is_pass_independent``).
+        LangevinInertia evaluates ``force()`` and then ``potential()`` at the SAME positions
+        (integrators.py:280-282); when this holds the second traversal is folded into the first."""
+        if not self.potentials:
+            return False
+        for pot in self.potentials:
+            check = getattr(pot, "_energy_is_pass_independent", None)
+            if check is None or not check(self):
+                return False
+        return True
+
     def _foreign_potential(self, pot, flags, first, force, vw):
         """A user-defined host ``Potential`` in the list: call it and add its result on the device."""
         want_f = bool(flags & (_lib.WANT_F | _lib.WANT_W))
