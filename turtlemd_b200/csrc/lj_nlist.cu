@@ -42,6 +42,7 @@ namespace tmd {
 constexpr int kNlThreads = 128;
 constexpr unsigned kSlotMask = 0x07FFFFFFu;
 constexpr int kHomeCode = 13;  // (0,0,0) shift
+constexpr int kNeverHi = 0x7FF80BAD;  // high word of a NaN payload no arithmetic produces (see nl_force_kernel)
 constexpr int kBinThreads = 256;           // cooperative binning kernel
 constexpr int kScanChunk = kBinThreads * 8;
 
@@ -308,9 +309,21 @@ __global__ void __launch_bounds__(kBinThreads) nl_bin_kernel(const NlArgs a) {
 
 // Candidate lists (phase 5 of a rebuild): one thread per row atom walks the stencil runs with the
 // single-precision filter.  A hit costs one shared-memory store into the thread's 32-deep ring;
-// between runs the ring is drained to the row-major list in whole 32-byte sectors (STG.256);
-// ascending by (stencil row, slot).  Gated on the rebuild flag; persistent grid.
+// between filter rounds the ring is drained to the row-major list one 16-entry block (two STG.256)
+// at a time.  Gated on the rebuild flag; persistent grid.
+//
+// List layout.  Logically a row is ascending by (stencil row, slot).  In memory every block of
+// kBlockEntries = 16 logical entries is stored TRANSPOSED as a 4 x 4 matrix: logical entry q of a
+// block sits at position (q % 4) * 4 + q / 4, so that lane l of the traversal's four-lane group
+// finds the entries of its next four rounds (q = l, l + 4, l + 8, l + 12) in ONE aligned 16-byte
+// load, while the four lanes of a round still work on four consecutive logical entries (nearly
+// consecutive slots, whose 32-byte records share cache lines).
 constexpr int kRing = 32;
+constexpr int kBlockEntries = 16;
+constexpr int kChunk = 16;  // candidates per filter round
+static_assert(kBlockEntries - 1 + kChunk <= kRing, "the ring must hold a waiting partial block plus one filter round");
+
+__device__ __forceinline__ int block_position(int q) { return (q & 3) * 4 + (q >> 2); }  // its own inverse
 
 template <int DIM>
 __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
@@ -329,17 +342,21 @@ __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
         const float4 me = a.xbf[slot];
         const int cell = a.cell_of[atom];
         const int c0 = cell % g.nc[0], c1 = (cell / g.nc[0]) % g.nc[1], c2 = cell / (g.nc[0] * g.nc[1]);
-        unsigned *list = a.entries + (size_t)row * cap;  // cap is a multiple of 8: rows are 32-byte aligned
-        int cnt = 0, flushed = 0;                        // flushed is a multiple of 8
-        auto drain = [&](int keep) {                     // write whole sectors until fewer than `keep` entries wait
-            while (cnt - flushed >= keep) {
-                if (flushed + 8 <= cap) {
-                    unsigned e[8];
+        unsigned *list = a.entries + (size_t)row * cap;  // cap is a multiple of 16: rows are 64-byte aligned
+        int cnt = 0, flushed = 0;                        // flushed is a multiple of 16
+        auto drain = [&]() {                             // write whole blocks while at least one is waiting
+            while (cnt - flushed >= kBlockEntries) {
+                if (flushed + kBlockEntries <= cap) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) e[k] = s_ring[(flushed + k) & (kRing - 1)][tid];
-                    st_entries8(list + flushed, e);
+                    for (int half = 0; half < 2; ++half) {
+                        unsigned e[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            e[k] = s_ring[(flushed + block_position(8 * half + k)) & (kRing - 1)][tid];
+                        st_entries8(list + flushed + 8 * half, e);
+                    }
                 }
-                flushed += 8;
+                flushed += kBlockEntries;
             }
         };
         for_each_run<DIM>(g, a.starts, c0, c1, c2, [&](int jbegin, int jend, int code) {
@@ -347,24 +364,36 @@ __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
             const float ys = me.y - ((code / 3) % 3 - 1) * ly;
             const float zs = me.z - (code / 9 - 1) * lz;
             const unsigned tag = (unsigned)code << 27;
-            for (int j0 = jbegin; j0 < jend; j0 += kRing - 8) {  // at most 24 hits between drains: the ring cannot wrap
-                const int j1 = min(jend, j0 + kRing - 8);
-                for (int j = j0; j < j1; ++j) {
-                    const float4 q = a.xbf[j];
+            // kChunk candidates at a time: distances first (loads not predicated: the index is clamped and
+            // the bits of candidates beyond the run are masked afterwards), hits recorded as bits, then
+            // the few set bits are turned into entries.  At most 15 + kChunk entries wait: the ring cannot wrap.
+            for (int j0 = jbegin; j0 < jend; j0 += kChunk) {
+                unsigned m = 0;
+                const int last = jend - 1;
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u) {
+                    const float4 q = a.xbf[min(j0 + u, last)];
                     float d = xs - q.x;
                     float r = d * d;
                     if (DIM > 1) { d = ys - q.y; r = fmaf(d, d, r); }
                     if (DIM > 2) { d = zs - q.z; r = fmaf(d, d, r); }
-                    if (r < reach2 && j != slot) {
-                        s_ring[cnt & (kRing - 1)][tid] = tag | (unsigned)j;
-                        ++cnt;
-                    }
+                    if (r < reach2) m |= 1u << u;
                 }
-                drain(8);
+                const int left = jend - j0;
+                if (left < kChunk) m &= (1u << left) - 1u;
+                const unsigned self = (unsigned)(slot - j0);
+                if (self < (unsigned)kChunk) m &= ~(1u << self);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    s_ring[cnt & (kRing - 1)][tid] = tag | (unsigned)(j0 + b);
+                    ++cnt;
+                }
+                drain();
             }
         });
-        if (cnt <= cap) {  // the 0..7 entries after the last full sector
-            for (int k = flushed; k < cnt; ++k) list[k] = s_ring[k & (kRing - 1)][tid];
+        if (cnt <= cap) {  // the 0..15 entries of the last, partial block (same transposed positions)
+            for (int k = flushed; k < cnt; ++k) list[flushed + block_position(k - flushed)] = s_ring[k & (kRing - 1)][tid];
         } else {
             atomicAdd(&a.nlflags[1], 1);  // statistics only: the traversal handles such a row exactly
         }
@@ -408,18 +437,25 @@ __device__ __forceinline__ double group_sum(double v) {
     return v;
 }
 
-// Traversal.  G lanes share one row atom: lane l takes candidates l, l+G, l+2G, ... of its list, so
-// the lanes of a group read consecutive entries (one 32-byte sector) and gather records of
-// nearly consecutive slots.  Blocks are persistent (grid-stride over groups of kNlThreads/G rows): the
-// energy / virial partials stay in registers for the whole kernel and are reduced once.  SINGLE: one
-// particle type (coefficients in registers, the shift `offset` applied once per lane from its hit
-// count).
-template <int DIM, bool SINGLE, int G, bool WV, bool WF>
-__global__ void __launch_bounds__(kNlThreads, 6) nl_force_kernel(const NlArgs a) {
+// Traversal.  G = 4 lanes share one row atom: in round r of a 16-entry block lane l takes logical entry
+// 4 r + l, so the lanes of a group gather records of nearly consecutive slots; the transposed block
+// layout (see nl_list_kernel) hands a lane the entries of four rounds in one 16-byte load.  Blocks are
+// persistent (grid-stride over groups of kNlThreads/G rows): the energy / virial partials stay in
+// registers for the whole kernel and are reduced once.  SINGLE: one particle type (coefficients in
+// registers, the shift `offset` applied once per lane from its hit count).
+template <int DIM, bool SINGLE, int G, bool WV, bool WF, int MINB>
+__global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs a) {
+    static_assert(G * 4 == kBlockEntries, "the block layout of the lists is for four lanes per row atom");
     __shared__ double s_tab[SINGLE ? 1 : 6 * kMaxT2];
     __shared__ double s_red[10 * (kNlThreads / 32)];
+    // per-thread virial partials (xx xy xz yy yz zz).  They are touched once per row (lane 0) and once
+    // per pair that crosses a box face, so they live in shared memory: the twelve registers they would
+    // hold go to a third record buffer (deeper gather pipeline) instead.
+    __shared__ double s_w[6][kNlThreads];
     constexpr int kRowsPerBlock = kNlThreads / G;
     const int tid = threadIdx.x;
+#pragma unroll
+    for (int w = 0; w < 6; ++w) s_w[w][tid] = 0.0;
     const int l = tid % G, grp = tid / G;
     const bool whole = a.first == 0 && a.count == a.n;
     const int ntypes = a.ntypes;
@@ -440,31 +476,27 @@ __global__ void __launch_bounds__(kNlThreads, 6) nl_force_kernel(const NlArgs a)
                  off = a.tab.c[4][0], rc2 = a.tab.c[5][0];
     // per-lane totals over all rows of this block: energy, hit count (the shift is applied at the end),
     // virial (xx xy xz yy yz zz) = 2 F (x) x of the rows this lane leads - sum f (x) S of crossing pairs
-    double vtot = 0.0, wtot[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double vtot = 0.0;
     int hits = 0;
 
     // Everything a row needs before its first pair can be evaluated; fetched one row ahead so that
     // the dependent chain (row -> list head -> record) of the NEXT row overlaps this row's arithmetic.
     struct Row {
         bool valid;
-        int slot, atom, nn;
+        int slot, nn;
         double4 me;
-        unsigned e0, e1;
+        uint4 e;  // this lane's entries of the first block
     };
     auto fetch = [&](int64_t base) {
         Row r;
         const int64_t row = base + grp;
         r.valid = row < a.count;
         r.slot = !r.valid ? 0 : (whole ? (int)row : (a.row_mode ? (int)(a.first + row) : a.slot_of[a.first + row]));
-        r.atom = !r.valid ? 0 : ((whole || a.row_mode) ? a.order[r.slot] : (int)(a.first + row));
         r.me = a.xs[r.slot];
         r.nn = r.valid ? a.nneigh[row] : 0;
-        r.e0 = r.e1 = 0u;
-        if (r.nn <= a.cap) {
-            const unsigned *list = a.entries + (size_t)row * a.cap;
-            if (l < r.nn) r.e0 = __ldg(list + l);
-            if (l + G < r.nn) r.e1 = __ldg(list + l + G);
-        }
+        // first entries of the row, whatever its length (cap >= 16: in bounds; unused words are never dereferenced)
+        r.e = make_uint4(0u, 0u, 0u, 0u);
+        if (r.valid) r.e = __ldg(reinterpret_cast<const uint4 *>(a.entries + (size_t)row * a.cap) + l);
         return r;
     };
 
@@ -476,19 +508,30 @@ __global__ void __launch_bounds__(kNlThreads, 6) nl_force_kernel(const NlArgs a)
         if (base + stride < a.count) next = fetch(base + stride);
         const int64_t row = base + grp;
         const bool valid = cur.valid;
-        const int slot = cur.slot, atom = cur.atom, nn = cur.nn;
+        const int slot = cur.slot, nn = cur.nn;
         const double4 me = cur.me;
         const int ti = SINGLE ? 0 : (int)__double_as_longlong(me.w);
         double facc[3] = {0.0, 0.0, 0.0};
 
-        auto candidate = [&](const double4 q, int code) {
-            double d[3] = {0.0, 0.0, 0.0};
-            d[0] = me.x - q.x;
-            if (DIM > 1) d[1] = me.y - q.y;
-            if (DIM > 2) d[2] = me.z - q.z;
+        // A candidate is handled in two halves.  consume(): the three subtractions that read the gathered
+        // record (the scoreboard wait of its load happens here).  compute(): everything else.
+        struct Delta {
+            double d[3];
+            int t;  // type of the neighbour (multi-type systems)
+        };
+        auto consume = [&](const double4 q) {
+            Delta r;
+            r.d[0] = me.x - q.x;
+            r.d[1] = DIM > 1 ? me.y - q.y : 0.0;
+            r.d[2] = DIM > 2 ? me.z - q.z : 0.0;
+            r.t = SINGLE ? 0 : (int)__double_as_longlong(q.w);
+            return r;
+        };
+        auto compute = [&](const Delta &dl, int code) {
+            double d[3] = {dl.d[0], dl.d[1], dl.d[2]};
             double l1 = lj1, l2 = lj2, l3 = lj3, l4 = lj4, of = off, r2c = rc2;
             if (!SINGLE) {
-                const int p = ti * ntypes + (int)__double_as_longlong(q.w);
+                const int p = ti * ntypes + dl.t;
                 l1 = s_tab[0 * kMaxT2 + p];
                 l2 = s_tab[1 * kMaxT2 + p];
                 l3 = s_tab[2 * kMaxT2 + p];
@@ -529,7 +572,7 @@ __global__ void __launch_bounds__(kNlThreads, 6) nl_force_kernel(const NlArgs a)
                             if (k < DIM) facc[k] += fk;
 #pragma unroll
                             for (int b = k; b < 3; ++b, ++w)
-                                if (b < DIM) wtot[w] = fma(-fk, S[b], wtot[w]);
+                                if (b < DIM) s_w[w][tid] = fma(-fk, S[b], s_w[w][tid]);
                         }
                     }
                 }
@@ -537,35 +580,50 @@ __global__ void __launch_bounds__(kNlThreads, 6) nl_force_kernel(const NlArgs a)
         };
 
         if (nn <= a.cap) {
-            const unsigned *list = a.entries + (size_t)row * a.cap;
-            // software pipeline: entries two rounds ahead, records one round ahead; two record buffers
-            // used alternately so that nothing has to be moved between rounds
+            // Software pipeline over half blocks (two rounds).  ptxas tracks every gather of this loop with
+            // ONE scoreboard, so the wait in front of a record's first use waits for every load in flight: a
+            // gather issued just before that wait would be waited for at once (ncu, r01p: 40 % of the stall
+            // samples sat there).  Hence the order: consume the two records that are due (one wait), THEN
+            // issue the two gathers of the next half block (and, once per block, the next entries), then
+            // do the arithmetic of the two candidates while those loads fly.  `go` makes the gathers depend
+            // on a consumed value so that the assembler cannot hoist them above the wait; it is false only
+            // for one particular NaN payload.  k = logical index of this lane's candidate in round 0.
+            const uint4 *blk = reinterpret_cast<const uint4 *>(a.entries + (size_t)row * a.cap) + l;
             int k = l;
-            unsigned e0 = cur.e0, e1 = cur.e1;
+            uint4 e = cur.e;
             double4 qa = me, qb = me;
-            if (k < nn) qa = ld_record(a.xs + (e0 & kSlotMask));
+            if (k < nn) qa = ld_record(a.xs + (e.x & kSlotMask));
+            if (k + G < nn) qb = ld_record(a.xs + (e.y & kSlotMask));
             while (k < nn) {
-                unsigned e2 = k + 2 * G < nn ? __ldg(list + k + 2 * G) : 0u;
-                if (k + G < nn) qb = ld_record(a.xs + (e1 & kSlotMask));
-                candidate(qa, (int)(e0 >> 27));
-                k += G;
-                if (k >= nn) break;
-                e0 = k + 2 * G < nn ? __ldg(list + k + 2 * G) : 0u;
-                if (k + G < nn) qa = ld_record(a.xs + (e2 & kSlotMask));
-                candidate(qb, (int)(e1 >> 27));
-                k += G;
-                e1 = e0;
-                e0 = e2;
+                Delta da = consume(qa), db = consume(qb);
+                bool go = __double2hiint(da.d[0]) != kNeverHi;
+                blk += kBlockEntries / 4;
+                uint4 en = e;
+                if (go && k + 4 * G < nn) en = __ldg(blk);
+                if (go && k + 2 * G < nn) qa = ld_record(a.xs + (e.z & kSlotMask));
+                if (go && k + 3 * G < nn) qb = ld_record(a.xs + (e.w & kSlotMask));
+                compute(da, (int)(e.x >> 27));
+                if (k + G < nn) compute(db, (int)(e.y >> 27));
+                if (k + 2 * G >= nn) break;
+                da = consume(qa);
+                db = consume(qb);
+                go = __double2hiint(da.d[0]) != kNeverHi;
+                if (go && k + 4 * G < nn) qa = ld_record(a.xs + (en.x & kSlotMask));
+                if (go && k + 5 * G < nn) qb = ld_record(a.xs + (en.y & kSlotMask));
+                compute(da, (int)(e.z >> 27));
+                if (k + 3 * G < nn) compute(db, (int)(e.w >> 27));
+                k += 4 * G;
+                e = en;
             }
         } else {
             // list capacity exceeded at build time: walk the build-time cells (every pair now inside
             // rcut was inside rcut + skin then, hence in this stencil)
-            const int cell = a.cell_of[atom];
+            const int cell = a.cell_of[(whole || a.row_mode) ? a.order[slot] : (int)(a.first + row)];
             const int c0 = cell % a.grid.nc[0], c1 = (cell / a.grid.nc[0]) % a.grid.nc[1],
                       c2 = cell / (a.grid.nc[0] * a.grid.nc[1]);
             for_each_run<DIM>(a.grid, a.starts, c0, c1, c2, [&](int jbegin, int jend, int code) {
                 for (int j = jbegin + l; j < jend; j += G)
-                    if (j != slot) candidate(a.xs[j], code);
+                    if (j != slot) compute(consume(a.xs[j]), code);
             });
         }
 
@@ -575,7 +633,8 @@ __global__ void __launch_bounds__(kNlThreads, 6) nl_force_kernel(const NlArgs a)
         for (int k = 0; k < DIM; ++k) f[k] = group_sum<G>(facc[k]);
         if (l == 0 && valid) {
             if (flags & TMD_WANT_F) {
-                double *dst = a.force + (int64_t)(a.row_mode ? slot : atom) * DIM;
+                const int atom = a.row_mode ? slot : (whole ? a.order[slot] : (int)(a.first + row));
+                double *dst = a.force + (int64_t)atom * DIM;
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) dst[k] = (flags & TMD_ACCUMULATE) ? dst[k] + f[k] : f[k];
             }
@@ -586,7 +645,7 @@ __global__ void __launch_bounds__(kNlThreads, 6) nl_force_kernel(const NlArgs a)
                 for (int p = 0; p < 3; ++p)
 #pragma unroll
                     for (int q = p; q < 3; ++q, ++w)
-                        if (q < DIM) wtot[w] = fma(2.0 * f[p], x[q], wtot[w]);
+                        if (q < DIM) s_w[w][tid] = fma(2.0 * f[p], x[q], s_w[w][tid]);
             }
         }
     }
@@ -594,6 +653,9 @@ __global__ void __launch_bounds__(kNlThreads, 6) nl_force_kernel(const NlArgs a)
     // per-block share of (V, W) in the "every pair seen from both atoms, halve at the end" convention
     double red[10];
     red[0] = SINGLE ? vtot - hits * off : vtot;
+    double wtot[6];
+#pragma unroll
+    for (int w = 0; w < 6; ++w) wtot[w] = s_w[w][tid];
     red[1] = wtot[0]; red[2] = wtot[1]; red[3] = wtot[2];
     red[4] = wtot[1]; red[5] = wtot[3]; red[6] = wtot[4];
     red[7] = wtot[2]; red[8] = wtot[4]; red[9] = wtot[5];
@@ -639,16 +701,6 @@ static int nl_env_int(const char *name, int fallback) {
     return env ? atoi(env) : fallback;
 }
 
-// lanes per row atom in the traversal (TMD_NL_G = 2 | 4 | 8; default 4, the fastest measured)
-static int nl_group_lanes() {
-    static int g = 0;
-    if (g == 0) {
-        const int v = nl_env_int("TMD_NL_G", 4);
-        g = (v == 2 || v == 4 || v == 8) ? v : 4;
-    }
-    return g;
-}
-
 // stencil half width: cells of edge >= (rcut + skin) / H (TMD_NL_H = 1 | 2 | 3; default 1).  Finer
 // cells halve the candidates a rebuild tests but cut them into many short runs; measured on B200
 // (N = 1M, rho = 0.8) H = 1 rebuilds fastest and the traversal does not care.
@@ -690,11 +742,22 @@ static bool nl_make_grid(const tmd_box *box, double reach, int64_t n, NlGrid &g)
     return true;
 }
 
-template <int DIM, int G>
-static void nl_launch_force_g(const NlArgs &a, int blocks, cudaStream_t s) {
+// resident traversal blocks per SM (TMD_NL_MINB = 5 .. 8): the register budget of a thread is 65536 /
+// (128 MINB); see profiles/r01q_sweep_minb.txt
+static int nl_min_blocks() {
+    static int m = 0;
+    if (m == 0) {
+        const int v = nl_env_int("TMD_NL_MINB", 5);
+        m = (v >= 5 && v <= 8) ? v : 5;
+    }
+    return m;
+}
+
+template <int DIM, int MINB>
+static void nl_launch_force_m(const NlArgs &a, int blocks, cudaStream_t s) {
     const bool wv = a.flags & TMD_WANT_V, wf = a.flags & (TMD_WANT_F | TMD_WANT_W);
 #define TMD_NL_LAUNCH(SINGLE, WV, WF) \
-    ::tmd::count_launch(), nl_force_kernel<DIM, SINGLE, G, WV, WF><<<blocks, kNlThreads, 0, s>>>(a)
+    ::tmd::count_launch(), nl_force_kernel<DIM, SINGLE, 4, WV, WF, MINB><<<blocks, kNlThreads, 0, s>>>(a)
     if (a.ntypes == 1) {
         if (wv && wf) TMD_NL_LAUNCH(true, true, true);
         else if (wf) TMD_NL_LAUNCH(true, false, true);
@@ -709,21 +772,22 @@ static void nl_launch_force_g(const NlArgs &a, int blocks, cudaStream_t s) {
 
 template <int DIM>
 static void nl_launch_force(const NlArgs &a, int blocks, cudaStream_t s) {
-    if (DIM == 3) {  // the lanes-per-atom tuning variants exist for the 3-D kernel only
-        switch (nl_group_lanes()) {
-            case 2: nl_launch_force_g<DIM, 2>(a, blocks, s); return;
-            case 8: nl_launch_force_g<DIM, 8>(a, blocks, s); return;
+    if (DIM == 3) {  // the occupancy variants exist for the 3-D kernel only
+        switch (nl_min_blocks()) {
+            case 6: nl_launch_force_m<DIM, 6>(a, blocks, s); return;
+            case 7: nl_launch_force_m<DIM, 7>(a, blocks, s); return;
+            case 8: nl_launch_force_m<DIM, 8>(a, blocks, s); return;
             default: break;
         }
     }
-    nl_launch_force_g<DIM, 4>(a, blocks, s);
+    nl_launch_force_m<DIM, 5>(a, blocks, s);
 }
 
 // persistent traversal grid: resident blocks per SM x SMs, never more blocks than row groups
 static int nl_force_blocks(int64_t count, int dim) {
-    const int g = dim == 3 ? nl_group_lanes() : 4;
+    const int g = 4;
     const int64_t groups = (count + (kNlThreads / g) - 1) / (kNlThreads / g);
-    const int64_t want = (int64_t)num_sms() * 6;
+    const int64_t want = (int64_t)num_sms() * (dim == 3 ? nl_min_blocks() : 5);
     return (int)(groups < want ? groups : want);
 }
 
@@ -821,13 +885,13 @@ static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double
     if (n > nl->cap_n || count > nl->cap_rows || ncells > nl->cap_cells) {
         TMD_CUDA(cudaStreamSynchronize(s));
         nl_release(nl);
-        // expected neighbours within reach at this density, +35 % and a floor, rounded to 8
+        // expected neighbours within reach at this density, +35 % and a floor, rounded to whole blocks
         double volume = 1.0;
         for (int k = 0; k < dim; ++k) volume *= box->length[k];
         const double sphere = dim == 3 ? 4.18879020478639 * reach * reach * reach
                                        : (dim == 2 ? 3.14159265358979 * reach * reach : 2.0 * reach);
         int cap = (int)(1.35 * (double)n / volume * sphere) + 24;
-        cap = (cap + 7) & ~7;
+        cap = (cap + kBlockEntries - 1) & ~(kBlockEntries - 1);
         if (cap > 1024) cap = 1024;
         nl->cap = cap;
         nl->cap_n = n;
