@@ -310,7 +310,9 @@ def test_langevin_fused_multi_step_equals_single_steps():
     _assert_frame(system, g, 10)
     # sharded: two halves with global offsets reproduce the same replicas bit for bit
     full_pos = system.particles.pos.copy()
-    for first, count in ((0, 40), (40, 24)):
+    # (0, 40) / (40, 24): two coordinates per thread sharing one Philox block; (0, 41): the same kernel with a
+    # lone last coordinate; (41, 23): stream position not a multiple of four -> one coordinate per thread
+    for first, count in ((0, 40), (40, 24), (0, 41), (41, 23)):
         sl = slice(first, first + count)
         sub = dict(pos0=g["pos0"][sl], vel0=g["vel0"][sl], mass=g["mass"][sl], ptype=g["ptype"][sl])
         shard = _traj_system(sub, [k["DoubleWell"](a=a, b=b, c=c)])

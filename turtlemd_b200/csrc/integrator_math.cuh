@@ -23,6 +23,13 @@ __device__ __forceinline__ void two_normals(uint64_t key, uint64_t q0, bool two,
     }
 }
 
+// normals q0 .. q0 + 3 of the stream, q0 a multiple of four: the four words of ONE Philox block
+__device__ __forceinline__ void four_normals(uint64_t key, uint64_t q0, double (&z)[4]) {
+    const Philox4 b = philox4x64_10(q0 >> 2, key);
+    normal_pair_from_raw(b.w[0], b.w[1], z[0], z[1]);
+    normal_pair_from_raw(b.w[2], b.w[3], z[2], z[3]);
+}
+
 struct InertiaPerParticle {
     double a2, b1, b2, l00, l10, l11;
 };

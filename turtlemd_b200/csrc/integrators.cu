@@ -197,7 +197,16 @@ __global__ void __launch_bounds__(256) inertia_pre_kernel(double *__restrict__ p
         // element e consumes normals q_base + 2e (position) and + 2e + 1 (velocity):
         // multivariate_normal reshapes its 2*dim draws to (dim, 2)  (integrators.py:312-313)
         double n0, n1;
-        two_normals(key, q_base + 2ull * (uint64_t)e, true, n0, n1);
+        const uint64_t q = q_base + 2ull * (uint64_t)e;
+        if (two && (q & 3ull) == 0) {  // both pairs of this thread are the halves of one Philox block
+            double z[4];
+            four_normals(key, q, z);
+            xr.a = __dmul_rn(pa.l00, z[0]);
+            vr.a = __dadd_rn(__dmul_rn(pa.l10, z[0]), __dmul_rn(pa.l11, z[1]));
+            xr.b = __dmul_rn(pb.l00, z[2]);
+            vr.b = __dadd_rn(__dmul_rn(pb.l10, z[2]), __dmul_rn(pb.l11, z[3]));
+        } else {
+        two_normals(key, q, true, n0, n1);
         xr.a = __dmul_rn(pa.l00, n0);  // norm @ cho.T  (integrators.py:315)
         vr.a = __dadd_rn(__dmul_rn(pa.l10, n0), __dmul_rn(pa.l11, n1));
         if (two) {
@@ -206,6 +215,7 @@ __global__ void __launch_bounds__(256) inertia_pre_kernel(double *__restrict__ p
             vr.b = __dadd_rn(__dmul_rn(pb.l10, n0), __dmul_rn(pb.l11, n1));
         } else {
             xr.b = vr.b = 0.0;
+        }
         }
     }
     inertia_pre_update(x.a, v.a, f.a, xr.a, vr.a, c, pa);
@@ -257,6 +267,54 @@ __global__ void __launch_bounds__(256) inertia_doublewell_kernel(
         vel[e] = v;
         force[e] = f;
         vsum[0] = dw_energy(x, a, b, cpar);              // system.potential()  (integrators.py:282)
+    }
+    block_sum<1, 256>(vsum, smem);
+    if (threadIdx.x == 0) {
+        double *row = partial_v + (size_t)blockIdx.x * 10;
+        row[0] = vsum[0];
+#pragma unroll
+        for (int k = 1; k < 10; ++k) row[k] = 0.0;
+    }
+}
+
+// Two coordinates per thread: when the stream position of every even coordinate is a multiple of four,
+// the two Box-Muller pairs a thread needs per step are the two halves of ONE Philox block (the kernel is
+// bound by the 64-bit multiplies of Philox: this halves them).  Same numbers as inertia_doublewell_kernel.
+template <int DIM, bool VEC>
+__global__ void __launch_bounds__(256) inertia_doublewell_pair_kernel(
+    double *__restrict__ pos, double *__restrict__ vel, double *__restrict__ force,
+    const double *__restrict__ imass, int64_t total, double a, double b, double cpar,
+    tmd_langevin_consts c, uint64_t key, uint64_t q_base, uint64_t q_step, int nsteps,
+    double *__restrict__ partial_v) {
+    __shared__ double smem[8];
+    const int64_t e = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    double vsum[1] = {0.0};
+    if (e < total) {
+        const bool two = (e + 1) < total;
+        const D2 im = ld_imass<DIM>(imass, e, two);
+        const InertiaPerParticle pa = inertia_constants(c, im.a);
+        const InertiaPerParticle pb = (im.b == im.a) ? pa : inertia_constants(c, im.b);
+        D2 x = ld2<VEC>(pos, e, two), v = ld2<VEC>(vel, e, two), f = ld2<VEC>(force, e, two);
+        uint64_t q = q_base + 2ull * (uint64_t)e;  // a multiple of four (checked by the launcher)
+        for (int s = 0; s < nsteps; ++s, q += q_step) {
+            double z[4];
+            four_normals(key, q, z);
+            const double xra = __dmul_rn(pa.l00, z[0]);
+            const double vra = __dadd_rn(__dmul_rn(pa.l10, z[0]), __dmul_rn(pa.l11, z[1]));
+            const double xrb = __dmul_rn(pb.l00, z[2]);
+            const double vrb = __dadd_rn(__dmul_rn(pb.l10, z[2]), __dmul_rn(pb.l11, z[3]));
+            inertia_pre_update(x.a, v.a, f.a, xra, vra, c, pa);
+            inertia_pre_update(x.b, v.b, f.b, xrb, vrb, c, pb);
+            f.a = dw_force(x.a, a, b, cpar);                   // system.force()      (integrators.py:280)
+            f.b = dw_force(x.b, a, b, cpar);
+            v.a = __dadd_rn(v.a, __dmul_rn(pa.b2, f.a));       // vel = vel2 + b2*F   (integrators.py:281)
+            v.b = __dadd_rn(v.b, __dmul_rn(pb.b2, f.b));
+        }
+        st2<VEC>(pos, e, two, x);
+        st2<VEC>(vel, e, two, v);
+        st2<VEC>(force, e, two, f);
+        vsum[0] = dw_energy(x.a, a, b, cpar);                  // system.potential()  (integrators.py:282)
+        if (two) vsum[0] += dw_energy(x.b, a, b, cpar);
     }
     block_sum<1, 256>(vsum, smem);
     if (threadIdx.x == 0) {
@@ -433,7 +491,7 @@ int tmd_langevin_inertia_doublewell(double *pos, double *vel, double *force, con
     TMD_CHECK(require_device());
     const int64_t total = n * dim;
     cudaStream_t s = as_stream(stream);
-    const int blocks = (int)((total + 255) / 256);
+    int blocks = (int)((total + 255) / 256);
     if (blocks == 0) {
         TMD_CUDA(cudaMemsetAsync(vw, 0, 10 * sizeof(double), s));
         return TMD_OK;
@@ -442,6 +500,19 @@ int tmd_langevin_inertia_doublewell(double *pos, double *vel, double *force, con
     TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)blocks * 10 * sizeof(double), (void **)&partials));
     const uint64_t q_base = rng->offset + 2ull * (uint64_t)first * (uint64_t)dim;
     const uint64_t q_step = 2ull * (uint64_t)n_global * (uint64_t)dim;
+    if ((q_base & 3ull) == 0 && (q_step & 3ull) == 0) {
+        // coordinate pairs share a Philox block on every step: two coordinates per thread
+        const bool vec = aligned16(pos) && aligned16(vel) && aligned16(force);
+        blocks = ew_launch(total).blocks;
+#define TMD_IDW2(D, V) \
+    ::tmd::count_launch(), inertia_doublewell_pair_kernel<D, V><<<blocks, 256, 0, s>>>(pos, vel, force, imass, total, a, b, c, *consts, rng->key, q_base, q_step, nsteps, partials)
+        if (dim == 1) { if (vec) TMD_IDW2(1, true); else TMD_IDW2(1, false); }
+        else if (dim == 2) { if (vec) TMD_IDW2(2, true); else TMD_IDW2(2, false); }
+        else { if (vec) TMD_IDW2(3, true); else TMD_IDW2(3, false); }
+#undef TMD_IDW2
+        TMD_CUDA(cudaGetLastError());
+        return launch_reduce_vw(partials, blocks, 1.0, TMD_WANT_V, vw, s);
+    }
 #define TMD_IDW(D) \
     ::tmd::count_launch(), inertia_doublewell_kernel<D><<<blocks, 256, 0, s>>>(pos, vel, force, imass, total, a, b, c, *consts, rng->key, q_base, q_step, nsteps, partials)
     if (dim == 1) TMD_IDW(1); else if (dim == 2) TMD_IDW(2); else TMD_IDW(3);
