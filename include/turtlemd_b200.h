@@ -316,6 +316,21 @@ int tmd_slab_sort(const int32_t *order, int64_t n, int32_t dim, const double *ve
 int tmd_kinetic_tensor(const double *vel, const double *mass, int64_t n, int32_t dim,
                        double *kin, tmd_stream_t stream);
 
+/* ---------------------------------------------------------------- velocity set-up */
+/* generate_maxwell_velocities step 1 (system/particles.py:260-262):
+ *   vel[i,k] = sqrt(imass[i]) * z,  z = normal number  rng->offset + (first + i)*dim + k  of the stream
+ * (the order in which rgen.normal(size=(n,dim)) hands them out).                                    */
+int tmd_maxwell_draw(double *vel, const double *imass, int64_t n, int32_t dim, const tmd_rng *rng,
+                     int64_t first, tmd_stream_t stream);
+/* linear_momentum + mass.sum() (system/particles.py:135-137, :153):
+ *   out[0] = sum_i mass[i],  out[1+k] = sum_i vel[i,k]*mass[i]   (device double[4], fixed summation order) */
+int tmd_momentum(const double *vel, const double *mass, int64_t n, int32_t dim, double *out,
+                 tmd_stream_t stream);
+/* vel[i,k] -= shift[k] (zero_momentum, :153) when shift != NULL, then vel[i,k] *= scale (:269) when
+ * do_scale != 0; shift is a HOST double[dim].  Two roundings, in the reference's order.             */
+int tmd_vel_shift_scale(double *vel, int64_t n, int32_t dim, const double *shift, int32_t do_scale,
+                        double scale, tmd_stream_t stream);
+
 /* ---------------------------------------------------------------- host-buffer plug-in API ---- */
 /* LennardJonesCut.{potential_and_force,force,potential}(system) with the reference's own
  * arrays: pos (n,dim) f64, ptype (n,) int64 already mapped to 0..ntypes-1, outputs force

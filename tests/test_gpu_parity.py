@@ -296,6 +296,39 @@ def test_langevin_doublewell_replicas(kind, dim, draws):
     assert rgen.position == 11 * 64 * dim * (2 if kind == "inertia" else 1)  # 11 steps were taken
 
 
+@pytest.mark.parametrize("tag", ["3d_500", "1d_64", "2d_301"])
+def test_maxwell_velocities_on_the_device(tag):
+    """Velocity set-up with the in-kernel stream (draw, momentum removal, rescaling on the device) against
+    the reference fed the Philox twin (system/particles.py:140-153, :227-269)."""
+    from turtlemd_b200.philox import PhiloxNormal
+    from turtlemd_b200.system import Particles
+    from turtlemd_b200.system.particles import (generate_maxwell_velocities, kinetic_temperature,
+                                                linear_momentum, zero_momentum)
+
+    g = load_golden(f"maxwell_{tag}.npz")
+    n, dim = g["vel"].shape
+    dof = None if g["dof"].size == 0 else list(g["dof"])
+    part = Particles.from_arrays(np.zeros((n, dim)), mass=g["mass"])
+    rgen = PhiloxNormal(key=int(g["key"]))
+    generate_maxwell_velocities(part, rgen, temperature=float(g["temperature"]), boltzmann=float(g["boltzmann"]),
+                                dof=dof, momentum=bool(g["momentum"]))
+    assert rgen.position == int(g["draws"])
+    assert part._vel.dev_valid and not part._vel.host_valid  # nothing was drawn or reduced on the host
+    temp, _, _ = kinetic_temperature(part, float(g["boltzmann"]), dof=dof)  # device reduction
+    assert temp == pytest.approx(float(g["temperature"]), rel=1e-12)
+    if bool(g["momentum"]):
+        scale = np.abs(g["vel"] * g["mass"][:, None]).sum()
+        assert np.all(np.abs(linear_momentum(part)) < 1e-13 * scale)
+    assert rel_norm(part.vel, g["vel"]) < 1e-13
+    # zero_momentum with an axis mask on velocities that live on the device only
+    part.vel = g["vel"] + g["drift"]
+    part._vel.device()
+    part._vel.written_on_device()
+    zero_momentum(part, dim=[bool(m) for m in g["mask"]])
+    assert part._vel.dev_valid and not part._vel.host_valid
+    assert rel_norm(part.vel, g["vel_masked"]) < 1e-13
+
+
 def test_langevin_fused_multi_step_equals_single_steps():
     k = _pkg()
     from turtlemd_b200.philox import PhiloxNormal

@@ -187,6 +187,27 @@ def test_maxwell_velocities_and_thermo():
     assert System(box, Particles(dim=3)).thermo()["ekin"] is None
 
 
+@pytest.mark.parametrize("tag", ["3d_500", "1d_64", "2d_301"])
+def test_maxwell_velocities_match_reference_fixture(tag):
+    """generate_maxwell_velocities / zero_momentum against the reference fed the same stream
+    (tests/golden/make_golden_maxwell.py; system/particles.py:140-153, :227-269)."""
+    from oracle.philox_ref import OraclePhiloxNormal
+
+    g = load_golden(f"maxwell_{tag}.npz")
+    n, dim = g["vel"].shape
+    dof = None if g["dof"].size == 0 else list(g["dof"])
+    for make in (OraclePhiloxNormal, PhiloxNormal):  # unknown generator: host draws; the twin: device when there is one
+        part = Particles.from_arrays(np.zeros((n, dim)), mass=g["mass"])
+        rgen = make(key=int(g["key"]))
+        generate_maxwell_velocities(part, rgen, temperature=float(g["temperature"]),
+                                    boltzmann=float(g["boltzmann"]), dof=dof, momentum=bool(g["momentum"]))
+        assert rgen.position == int(g["draws"])
+        assert np.allclose(part.vel, g["vel"], rtol=1e-12, atol=1e-14)
+    part.vel = g["vel"] + g["drift"]
+    zero_momentum(part, dim=[bool(m) for m in g["mask"]])
+    assert np.allclose(part.vel, g["vel_masked"], rtol=1e-13, atol=1e-15)
+
+
 # ---- potentials: host-side parameter logic ----------------------------------------------------------
 
 

@@ -120,6 +120,9 @@ PROTOTYPES = {
     "tmd_host_philox_normal_fill": [_P, _I64, _U64, _U64],
     "tmd_host_philox_raw_fill": [_P, _I64, _U64, _U64],
     "tmd_kinetic_tensor": [_P, _P, _I64, _I32, _P, _P],
+    "tmd_maxwell_draw": [_P, _P, _I64, _I32, _RNG, _I64, _P],
+    "tmd_momentum": [_P, _P, _I64, _I32, _P, _P],
+    "tmd_vel_shift_scale": [_P, _I64, _I32, _P, _I32, _D, _P],
     "tmd_host_lj": [_P, _P, _I64, _BOX, _P, _I32, _U32, _I32, _P, _P],
     "tmd_host_doublewell": [_P, _I64, _I32, _D, _D, _D, _U32, _P, _P],
     "tmd_host_dwpair": [_P, _P, _I64, _BOX, _I64, _I64, _D, _D, _D, _U32, _P, _P],

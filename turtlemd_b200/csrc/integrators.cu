@@ -358,6 +358,54 @@ __global__ void __launch_bounds__(256) kinetic_kernel(const double *__restrict__
     }
 }
 
+// ---- velocity set-up (system/particles.py:140-153, 227-269) ---------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(256) maxwell_draw_kernel(double *__restrict__ vel, const double *__restrict__ imass,
+                                                           int64_t total, uint64_t key, uint64_t q_base) {
+    TMD_EW_PROLOGUE
+    const D2 im = ld_imass<DIM>(imass, e, two);
+    double z0, z1;
+    two_normals(key, q_base + (uint64_t)e, two, z0, z1);
+    vel[e] = __dmul_rn(__dsqrt_rn(im.a), z0);  // np.sqrt(imass) * rgen.normal(...)
+    if (two) vel[e + 1] = __dmul_rn(__dsqrt_rn(im.b), z1);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) momentum_kernel(const double *__restrict__ vel, const double *__restrict__ mass,
+                                                       int64_t n, double *__restrict__ partials) {
+    __shared__ double smem[10 * 8];
+    double acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double m = mass[i];
+        acc[0] += m;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) acc[1 + k] += __dmul_rn(vel[i * DIM + k], m);  // particles.vel * particles.mass
+    }
+    block_sum<10, 256>(acc, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) partials[(size_t)blockIdx.x * 10 + k] = acc[k];
+    }
+}
+
+struct Shift3 {
+    double s[3];
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(256) vel_shift_scale_kernel(double *__restrict__ vel, int64_t total, Shift3 shift,
+                                                              int do_shift, int do_scale, double scale) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    double v = vel[e];
+    if (do_shift) v = __dsub_rn(v, shift.s[e % DIM]);
+    if (do_scale) v = __dmul_rn(v, scale);
+    vel[e] = v;
+}
+
 }  // namespace tmd
 
 using namespace tmd;
@@ -565,6 +613,62 @@ int tmd_host_philox_raw_fill(uint64_t *out, int64_t count, uint64_t key, uint64_
         const Philox4 b = philox4x64_10(m >> 2, key);
         out[t] = b.w[m & 3ull];
     }
+    return TMD_OK;
+}
+
+int tmd_maxwell_draw(double *vel, const double *imass, int64_t n, int32_t dim, const tmd_rng *rng, int64_t first,
+                     tmd_stream_t stream) {
+    TMD_REQUIRE(dim >= 1 && dim <= 3 && n >= 0 && first >= 0, "bad sizes");
+    TMD_REQUIRE(rng != nullptr && (n == 0 || (vel && imass)), "vel, imass and rng are required");
+    TMD_CHECK(require_device());
+    const int64_t total = n * dim;
+    if (total == 0) return TMD_OK;
+    const Launch l = ew_launch(total);
+    cudaStream_t s = as_stream(stream);
+    const uint64_t q_base = rng->offset + (uint64_t)first * (uint64_t)dim;
+#define TMD_MXW(D) ::tmd::count_launch(), maxwell_draw_kernel<D><<<l.blocks, l.threads, 0, s>>>(vel, imass, total, rng->key, q_base)
+    if (dim == 1) TMD_MXW(1); else if (dim == 2) TMD_MXW(2); else TMD_MXW(3);
+#undef TMD_MXW
+    TMD_CUDA(cudaGetLastError());
+    return TMD_OK;
+}
+
+int tmd_momentum(const double *vel, const double *mass, int64_t n, int32_t dim, double *out, tmd_stream_t stream) {
+    TMD_REQUIRE(dim >= 1 && dim <= 3 && n >= 0 && out, "bad arguments");
+    TMD_REQUIRE(n == 0 || (vel && mass), "vel and mass are required");
+    TMD_CHECK(require_device());
+    cudaStream_t s = as_stream(stream);
+    int blocks = (int)((n + 255) / 256);
+    const int cap = num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    double *partials = nullptr, *vw = nullptr;
+    TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)blocks * 10 * sizeof(double), (void **)&partials));
+    TMD_CHECK(arena_get(SLOT_MISC, 10 * sizeof(double), (void **)&vw));
+    if (dim == 1) ::tmd::count_launch(), momentum_kernel<1><<<blocks, 256, 0, s>>>(vel, mass, n, partials);
+    else if (dim == 2) ::tmd::count_launch(), momentum_kernel<2><<<blocks, 256, 0, s>>>(vel, mass, n, partials);
+    else ::tmd::count_launch(), momentum_kernel<3><<<blocks, 256, 0, s>>>(vel, mass, n, partials);
+    TMD_CUDA(cudaGetLastError());
+    TMD_CHECK(launch_reduce_vw(partials, blocks, 1.0, TMD_WANT_V | TMD_WANT_W, vw, s));
+    TMD_CUDA(cudaMemcpyAsync(out, vw, 4 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return TMD_OK;
+}
+
+int tmd_vel_shift_scale(double *vel, int64_t n, int32_t dim, const double *shift, int32_t do_scale, double scale,
+                        tmd_stream_t stream) {
+    TMD_REQUIRE(dim >= 1 && dim <= 3 && n >= 0, "bad sizes");
+    TMD_REQUIRE(n == 0 || vel, "vel is NULL");
+    TMD_CHECK(require_device());
+    const int64_t total = n * dim;
+    if (total == 0 || (!shift && !do_scale)) return TMD_OK;
+    Shift3 sh = {{0.0, 0.0, 0.0}};
+    for (int k = 0; k < dim && shift; ++k) sh.s[k] = shift[k];
+    const int blocks = (int)((total + 255) / 256);
+    cudaStream_t s = as_stream(stream);
+#define TMD_VSS(D) ::tmd::count_launch(), vel_shift_scale_kernel<D><<<blocks, 256, 0, s>>>(vel, total, sh, shift != nullptr, do_scale, scale)
+    if (dim == 1) TMD_VSS(1); else if (dim == 2) TMD_VSS(2); else TMD_VSS(3);
+#undef TMD_VSS
+    TMD_CUDA(cudaGetLastError());
     return TMD_OK;
 }
 

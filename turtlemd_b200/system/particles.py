@@ -9,6 +9,7 @@ the reference's host helpers (SURVEY.md section 8f ranks a device version next).
 """
 from __future__ import annotations
 
+import ctypes as C
 from collections.abc import Iterator
 
 import numpy as np
@@ -193,18 +194,49 @@ class Particles:
         self._static.clear()
 
 
+def _on_device_only(particles: Particles) -> bool:
+    """The velocities were last written by a kernel and nobody has looked at them on the host since."""
+    mirror = particles._vel
+    return mirror.dev_valid and not mirror.host_valid and len(particles.mass) > 1
+
+
+def _momentum_device(particles: Particles) -> np.ndarray:
+    """sum_i m_i v_i reduced on the device (``tmd_momentum``); four doubles come back."""
+    from .. import _device, _lib
+
+    npart, dim = particles._vel.shape
+    out = _device.zeros(4)
+    _lib.call("tmd_momentum", _device.dptr(particles._vel.device()), _device.dptr(particles._mass_device()),
+              npart, dim, _device.dptr(out), _device.stream_ptr())
+    return out.cpu().numpy()[1: 1 + dim].copy()
+
+
 def linear_momentum(particles: Particles) -> np.ndarray:
+    """Total linear momentum (particles.py:135-137); reduced on the device when the velocities live there."""
+    if _on_device_only(particles):
+        return _momentum_device(particles)
     return np.sum(particles.vel * particles.mass, axis=0)
 
 
 def zero_momentum(particles: Particles, dim: list[bool] | None = None):
     """Remove the centre-of-mass motion, optionally only along chosen axes (particles.py:140-153)."""
+    on_device = _on_device_only(particles)
     mom = linear_momentum(particles)
     if dim is not None:
         for k, reset in enumerate(dim):
             if not reset:
                 mom[k] = 0
-    particles.vel -= mom / particles.mass.sum()
+    shift = mom / particles.mass.sum()
+    if on_device:
+        from .. import _device, _lib
+
+        npart, ndim = particles._vel.shape
+        shift = np.ascontiguousarray(shift, dtype=np.float64)
+        _lib.call("tmd_vel_shift_scale", _device.dptr(particles._vel.device()), npart, ndim, _lib.hptr(shift),
+                  0, 1.0, _device.stream_ptr())
+        particles._vel.written_on_device()
+        return
+    particles.vel -= shift
 
 
 def _kinetic_energy_device(particles: Particles) -> np.ndarray:
@@ -226,8 +258,7 @@ def kinetic_energy(particles: Particles) -> tuple[np.ndarray, float]:
     When the velocities live on the device (an integrator wrote them and nobody has read them on
     the host since) the reduction runs there and the velocity array is not downloaded.
     """
-    mirror = particles._vel
-    if mirror.dev_valid and not mirror.host_valid and len(particles.mass) > 1:
+    if _on_device_only(particles):
         kin = _kinetic_energy_device(particles)
         return kin, kin.trace()
     vel = particles._vel.peek()
@@ -260,10 +291,49 @@ def pressure_tensor(particles: Particles, volume: float, kin_tensor=None):
 
 def generate_maxwell_velocities(particles: Particles, rgen, temperature: float = 1.0,
                                 boltzmann: float = 1.0, dof=None, momentum: bool = True):
-    """Maxwell velocities at a target temperature (particles.py:227-269)."""
+    """Maxwell velocities at a target temperature (particles.py:227-269).
+
+    With the counter-based stream (:class:`turtlemd_b200.philox.PhiloxNormal`) as ``rgen`` and a CUDA
+    device present, all three steps run on the device -- draw (``tmd_maxwell_draw``, the same numbers
+    ``rgen.normal(size=vel.shape)`` would hand out), momentum removal, rescaling -- and only the
+    momentum and the kinetic tensor (13 doubles) visit the host.  Any other generator draws on the
+    host exactly like the reference.
+    """
+    if _device_stream(rgen) and particles.npart > 1:
+        from .. import _device, _lib
+
+        npart, dim = particles._vel.shape
+        vel = particles._vel.device_uninitialised(npart * dim)
+        rng = _lib.Rng(rgen.key, rgen.position)
+        rgen.advance(npart * dim)
+        _lib.call("tmd_maxwell_draw", _device.dptr(vel), _device.dptr(particles._imass_device()), npart, dim,
+                  C.byref(rng), 0, _device.stream_ptr())
+        particles._vel.written_on_device()
+        if momentum:
+            zero_momentum(particles)
+        temp_now, _, _ = kinetic_temperature(particles, boltzmann, dof=dof)
+        scale = float(np.sqrt(temperature / temp_now))
+        _lib.call("tmd_vel_shift_scale", _device.dptr(particles._vel.device()), npart, dim, None, 1, scale,
+                  _device.stream_ptr())
+        particles._vel.written_on_device()
+        return
     vel = np.sqrt(particles.imass) * rgen.normal(loc=0.0, scale=1.0, size=particles.vel.shape)
     particles.vel = vel
     if momentum:
         zero_momentum(particles)
     temp_now, _, _ = kinetic_temperature(particles, boltzmann, dof=dof)
     particles.vel *= np.sqrt(temperature / temp_now)
+
+
+def _device_stream(rgen) -> bool:
+    """``rgen`` is the counter-based stream and there is a device to run it on."""
+    from ..philox import PhiloxNormal
+
+    if not isinstance(rgen, PhiloxNormal):
+        return False
+    from .. import _lib
+
+    try:
+        return _lib.device_count() > 0
+    except Exception:  # noqa: BLE001 - no library / no driver: the host path of the twin still works
+        return False
