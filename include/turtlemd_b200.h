@@ -78,6 +78,16 @@ typedef struct tmd_box {
     double ilength[3];       /* the STORED reciprocal 1/length, multiplied with as box.py:402 does */
 } tmd_box;
 
+/* TriclinicBox (system/box.py:183-318): what pbc_dist needs, exactly as the host object stores it.     */
+typedef struct tmd_cell {
+    int32_t dim;              /* 2 or 3                                                             */
+    int32_t reserved;
+    double matrix[9];         /* box_matrix, row-major 3x3, zero padded (box.py:244-246)            */
+    double inverse[9];        /* box_matrix_inv = np.linalg.inv(box_matrix) (:247)                  */
+    double translations[81];  /* translations[g*3+k], g < 3^dim: box_matrix @ index (:248-256)      */
+    double half_width;        /* shortest_width_half (:257-258)                                     */
+} tmd_cell;
+
 /* ---------------------------------------------------------------- library / device ---------- */
 int tmd_abi_version(void);
 const char *tmd_last_error(void);
@@ -315,6 +325,17 @@ int tmd_slab_sort(const int32_t *order, int64_t n, int32_t dim, const double *ve
 /* kinetic energy tensor 0.5 sum m v(x)v (system/particles.py:156-168) -> kin[9] (3x3 block)   */
 int tmd_kinetic_tensor(const double *vel, const double *mass, int64_t n, int32_t dim,
                        double *kin, tmd_stream_t stream);
+
+/* ---------------------------------------------------------------- triclinic cells */
+/* LennardJonesCut.{potential,force,potential_and_force} (potentials/lennardjones.py:145-273) with
+ * box = TriclinicBox: minimum image by TriclinicBox.pbc_dist (system/box.py:271-296), applied in every
+ * direction as the reference does.  Same flags / rows / outputs as tmd_lj_allpairs.                 */
+int tmd_lj_triclinic(const double *pos, const int32_t *tidx, int64_t n, const tmd_cell *cell,
+                     const double *table, int32_t ntypes, uint32_t flags, int64_t first, int64_t count,
+                     double *force, double *vw, tmd_stream_t stream);
+/* the same with host buffers (ptype already mapped to 0..ntypes-1)                                 */
+int tmd_host_lj_triclinic(const double *pos, const int64_t *tidx, int64_t n, const tmd_cell *cell,
+                          const double *table, int32_t ntypes, uint32_t flags, double *force, double *vw);
 
 /* ---------------------------------------------------------------- velocity set-up */
 /* generate_maxwell_velocities step 1 (system/particles.py:260-262):

@@ -296,6 +296,47 @@ def test_langevin_doublewell_replicas(kind, dim, draws):
     assert rgen.position == 11 * 64 * dim * (2 if kind == "inertia" else 1)  # 11 steps were taken
 
 
+@pytest.mark.parametrize("tag", ["3d_150", "3d_90_longcut", "2d_80"])
+def test_lj_in_a_triclinic_box(tag):
+    """LennardJonesCut with box = TriclinicBox (Mezei reduction + 3^dim image scan, box.py:271-296) against the
+    reference: host-buffer entry points and the device-resident path, plus the host mirror of pbc_dist."""
+    from oracle import turtle_oracle as to
+    from turtlemd_b200.system import Particles, System, TriclinicBox
+
+    k = _pkg()
+    g = load_golden(f"triclinic_lj_{tag}.npz")
+    alpha, beta, gamma = (None if np.isnan(a) else float(a) for a in g["angles"])
+    box = TriclinicBox(high=list(g["high"]), alpha=alpha, beta=beta, gamma=gamma)
+    assert np.array_equal(box.box_matrix, g["box_matrix"])
+    cell = to.TriclinicCell(g["high"], alpha, beta, gamma)
+    rng = np.random.default_rng(5)
+    for d in rng.normal(scale=6.0, size=(50, len(g["high"]))):
+        assert np.array_equal(box.pbc_dist(d), to.tri_pbc_dist(d, cell))
+    params = {t: dict(v, rcut=v["rcut"] * float(g["rscale"]))
+              for t, v in {0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}, 1: {"sigma": 1.1, "epsilon": 0.8, "rcut": 2.2}}.items()}
+    pot = k["LennardJonesCut"](dim=len(g["high"]), shift=True, mixing="geometric")
+    pot.set_parameters(params)
+    system = System(box, Particles.from_arrays(g["pos"], ptype=g["ptype"]), [pot])
+    v, f, w = pot.potential_and_force(system)        # host buffers in, host buffers out
+    assert abs(v - float(g["v"])) <= TOL * abs(float(g["v"]))
+    assert rel_norm(f, g["f"]) < TOL and rel_norm(w, g["w"]) < TOL
+    assert abs(pot.potential(system) - float(g["v_only"])) <= TOL * abs(float(g["v_only"]))
+    f2, w2 = pot.force(system)
+    assert rel_norm(f2, g["f"]) < TOL and rel_norm(w2, g["w_only"]) < TOL
+    system.potential_and_force()                      # device-resident path (System.evaluate)
+    assert rel_norm(system.particles.force, g["f"]) < TOL
+    assert rel_norm(system.particles.virial, g["w"]) < TOL
+    assert abs(system.particles.v_pot - float(g["v"])) <= TOL * abs(float(g["v"]))
+    # size-independent properties: Newton's third law, symmetric virial; and the integrator runs on it
+    fdev = system.particles.force
+    assert np.all(np.abs(fdev.sum(axis=0)) < 1e-9 * np.abs(fdev).sum())
+    assert rel_norm(system.particles.virial, system.particles.virial.T) < 1e-12
+    integ = k["integrators"].VelocityVerlet(1e-4)
+    for _ in range(3):
+        integ(system)
+    assert np.all(np.isfinite(system.particles.pos)) and np.isfinite(system.particles.v_pot)
+
+
 @pytest.mark.parametrize("tag", ["3d_500", "1d_64", "2d_301"])
 def test_maxwell_velocities_on_the_device(tag):
     """Velocity set-up with the in-kernel stream (draw, momentum removal, rescaling on the device) against

@@ -133,8 +133,14 @@ def test_box_construction(caplog):
     assert tri.volume() > 0
     d = tri.pbc_dist(np.array([9.0, 8.0, 7.0]))
     assert np.dot(d, d) <= np.dot([9.0, 8.0, 7.0], [9.0, 8.0, 7.0])
-    with pytest.raises(NotImplementedError):
-        tri.to_abi()
+    cell = tri.to_abi()  # the tmd_cell of the triclinic pair kernel
+    assert cell.dim == 3 and cell.half_width == tri.shortest_width_half
+    assert np.array_equal(np.array(cell.matrix[:]).reshape(3, 3), tri.box_matrix)
+    assert np.array_equal(np.array(cell.translations[:]).reshape(27, 3), tri.translations)
+    from turtlemd_b200.potentials.well import DoubleWellPair as _DWP
+
+    with pytest.raises(NotImplementedError):  # the pair well is not offered in skewed cells
+        _DWP._orthogonal_box(System(tri, Particles(dim=3)))
 
 
 # ---- particles -----------------------------------------------------------------------------------------

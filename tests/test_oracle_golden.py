@@ -44,6 +44,27 @@ def test_lj_matches_reference_bitwise(name):
         assert to.lj_potential(g["pos"], tidx, *box, g["table"]) == g["v_p"]
 
 
+TRI_PARAMS = {0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}, 1: {"sigma": 1.1, "epsilon": 0.8, "rcut": 2.2}}
+
+
+@pytest.mark.parametrize("tag", ["3d_150", "3d_90_longcut", "2d_80"])
+def test_lj_in_a_triclinic_cell_matches_reference_bitwise(tag):
+    """TriclinicBox.pbc_dist (box.py:271-296) under the LJ row loops; tests/golden/make_golden_triclinic.py."""
+    g = load_golden(f"triclinic_lj_{tag}.npz")
+    alpha, beta, gamma = (None if np.isnan(a) else float(a) for a in g["angles"])
+    cell = to.TriclinicCell(g["high"], alpha, beta, gamma)
+    assert np.array_equal(cell.matrix, g["box_matrix"]) and cell.half_width == float(g["half_width"])
+    params = {k: dict(v, rcut=v["rcut"] * float(g["rscale"])) for k, v in TRI_PARAMS.items()}
+    table, types = to.lj_tables(params)
+    assert types == [0, 1]
+    tidx = np.asarray(g["ptype"])
+    v, f, w = to.lj_potential_and_force(g["pos"], tidx, cell, None, None, table)
+    assert v == g["v"] and np.array_equal(f, g["f"]) and np.array_equal(w, g["w"])
+    assert to.lj_potential(g["pos"], tidx, cell, None, None, table) == g["v_only"]
+    f2, w2 = to.lj_force(g["pos"], tidx, cell, None, None, table)
+    assert np.array_equal(f2, g["f"]) and np.array_equal(w2, g["w_only"])
+
+
 def test_lj_tables_match_reference():
     single = {0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}}
     g = load_golden("lj_fcc_108.npz")

@@ -43,6 +43,16 @@ class Box(C.Structure):
     ]
 
 
+class Cell(C.Structure):
+    """``tmd_cell``: what ``TriclinicBox.pbc_dist`` needs (system/box.py:183-318)."""
+
+    _fields_ = [
+        ("dim", C.c_int32), ("reserved", C.c_int32),
+        ("matrix", C.c_double * 9), ("inverse", C.c_double * 9),
+        ("translations", C.c_double * 81), ("half_width", C.c_double),
+    ]
+
+
 class Rng(C.Structure):
     _fields_ = [("key", C.c_uint64), ("offset", C.c_uint64)]
 
@@ -67,6 +77,7 @@ _P = C.c_void_p
 _I64, _I32, _U32, _U64, _D = C.c_int64, C.c_int32, C.c_uint32, C.c_uint64, C.c_double
 _BOX, _RNG, _LC = C.POINTER(Box), C.POINTER(Rng), C.POINTER(LangevinConsts)
 _NLB = C.POINTER(NlistBuffers)
+_CELL = C.POINTER(Cell)
 
 # name -> argtypes; every function returns int (tmd_status) unless listed in _NON_STATUS
 PROTOTYPES = {
@@ -120,6 +131,8 @@ PROTOTYPES = {
     "tmd_host_philox_normal_fill": [_P, _I64, _U64, _U64],
     "tmd_host_philox_raw_fill": [_P, _I64, _U64, _U64],
     "tmd_kinetic_tensor": [_P, _P, _I64, _I32, _P, _P],
+    "tmd_lj_triclinic": [_P, _P, _I64, _CELL, _P, _I32, _U32, _I64, _I64, _P, _P, _P],
+    "tmd_host_lj_triclinic": [_P, _P, _I64, _CELL, _P, _I32, _U32, _P, _P],
     "tmd_maxwell_draw": [_P, _P, _I64, _I32, _RNG, _I64, _P],
     "tmd_momentum": [_P, _P, _I64, _I32, _P, _P],
     "tmd_vel_shift_scale": [_P, _I64, _I32, _P, _I32, _D, _P],
@@ -200,6 +213,21 @@ def device_count() -> int:
     n = C.c_int(0)
     call("tmd_device_count", C.byref(n))
     return n.value
+
+
+def make_cell(dim: int, matrix, inverse, translations, half_width: float) -> Cell:
+    """``tmd_cell`` from the attributes ``TriclinicBox`` stores (system/box.py:244-258)."""
+    cell = Cell()
+    cell.dim = int(dim)
+    for r in range(dim):
+        for k in range(dim):
+            cell.matrix[r * 3 + k] = float(matrix[r][k])
+            cell.inverse[r * 3 + k] = float(inverse[r][k])
+    for g in range(3 ** dim):
+        for k in range(dim):
+            cell.translations[g * 3 + k] = float(translations[g][k])
+    cell.half_width = float(half_width)
+    return cell
 
 
 def make_box(dim: int, periodic, length, ilength) -> Box:

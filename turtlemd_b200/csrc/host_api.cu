@@ -78,6 +78,24 @@ int tmd_host_lj(const double *pos, const int64_t *tidx, int64_t n, const tmd_box
     return download_results(flags, fbytes, d_force, d_vw, force, vw, s);
 }
 
+int tmd_host_lj_triclinic(const double *pos, const int64_t *tidx, int64_t n, const tmd_cell *cell, const double *table,
+                          int32_t ntypes, uint32_t flags, double *force, double *vw) {
+    TMD_REQUIRE(cell && cell->dim >= 2 && cell->dim <= 3 && n >= 0, "bad cell or n");
+    TMD_REQUIRE(vw != nullptr, "vw is NULL");
+    TMD_REQUIRE(!(flags & TMD_ACCUMULATE), "TMD_ACCUMULATE is meaningless with host buffers");
+    TMD_CHECK(require_device());
+    cudaStream_t s = 0;
+    const size_t fbytes = (size_t)n * cell->dim * sizeof(double);
+    double *d_pos = nullptr, *d_force = nullptr, *d_vw = nullptr;
+    int32_t *d_t = nullptr;
+    TMD_CHECK(upload(SLOT_HOST_A, pos, fbytes, (void **)&d_pos, s));
+    TMD_CHECK(upload_types(tidx, n, ntypes, &d_t, s));
+    TMD_CHECK(arena_get(SLOT_HOST_C, fbytes + 8, (void **)&d_force));
+    TMD_CHECK(arena_get(SLOT_HOST_D, 10 * sizeof(double), (void **)&d_vw));
+    TMD_CHECK(tmd_lj_triclinic(d_pos, d_t, n, cell, table, ntypes, flags, 0, n, d_force, d_vw, s));
+    return download_results(flags, fbytes, d_force, d_vw, force, vw, s);
+}
+
 int tmd_host_doublewell(const double *pos, int64_t n, int32_t dim, double a, double b, double c, uint32_t flags,
                         double *force, double *vw) {
     TMD_REQUIRE(dim >= 1 && dim <= 3 && n >= 0, "bad dim or n");

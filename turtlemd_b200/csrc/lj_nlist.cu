@@ -369,10 +369,13 @@ __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
             // the few set bits are turned into entries.  At most 15 + kChunk entries wait: the ring cannot wrap.
             for (int j0 = jbegin; j0 < jend; j0 += kChunk) {
                 unsigned m = 0;
-                const int last = jend - 1;
+                const float4 *cand = a.xbf + j0;  // xbf is padded by kChunk records: no clamping of the index
+                float4 q16[kChunk];
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u) q16[u] = __ldg(cand + u);
 #pragma unroll
                 for (int u = 0; u < kChunk; ++u) {
-                    const float4 q = a.xbf[min(j0 + u, last)];
+                    const float4 q = q16[u];
                     float d = xs - q.x;
                     float r = d * d;
                     if (DIM > 1) { d = ys - q.y; r = fmaf(d, d, r); }
@@ -907,7 +910,8 @@ static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double
         TMD_CUDA(cudaMemsetAsync(nl->ints, 0, n_ints * sizeof(int), s));  // counts[] must start at zero
         TMD_CUDA(cudaMalloc(&nl->wrapped, (size_t)n * sizeof(double4)));
         TMD_CUDA(cudaMalloc(&nl->xb, (size_t)n * sizeof(double4)));
-        TMD_CUDA(cudaMalloc(&nl->xbf, (size_t)n * sizeof(float4)));
+        TMD_CUDA(cudaMalloc(&nl->xbf, ((size_t)n + kChunk) * sizeof(float4)));  // the list filter reads whole chunks
+        TMD_CUDA(cudaMemsetAsync(nl->xbf + n, 0x7f, (size_t)kChunk * sizeof(float4), s));  // 3.4e38: never inside the reach
         if (!nl->xs_ext) TMD_CUDA(cudaMalloc(&nl->xs, (size_t)n * sizeof(double4)));
         TMD_CUDA(cudaMalloc(&nl->image, (size_t)n * 3 * sizeof(double)));
         fresh = true;

@@ -384,6 +384,8 @@ class SlabDecomposition:
         self._table, self._ntypes = table, len(types)
         self._tidx = part._static_device(f"lj_tidx_{id(self.pot)}", tidx, np.int32) if len(types) > 1 else None
         self._box = self.system.box.to_abi()
+        if not isinstance(self._box, _lib.Box):
+            raise NotImplementedError("SlabDecomposition needs an orthogonal, fully periodic Box")
         self._half_skin2 = 0.25 * float(self.pot.skin) ** 2
         self._nl = self.pot._nlist_handle()
         _lib.call("tmd_nlist_bind_records", self._nl, _device.dptr(self.records))

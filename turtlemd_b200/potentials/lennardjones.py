@@ -179,7 +179,9 @@ class LennardJonesCut(Potential):
         cached = getattr(self, "_pass_cache", None)
         if cached is None or cached[0] != key:
             types, table, _ = self._tables(particles)
-            name = self._kernel_for(particles.npart, system.box.to_abi(), table, len(types))
+            box_abi = system.box.to_abi()
+            name = ("tmd_lj_triclinic" if isinstance(box_abi, _lib.Cell)
+                    else self._kernel_for(particles.npart, box_abi, table, len(types)))
             cached = self._pass_cache = (key, name == "tmd_lj_nlist")
         return cached[1]
 
@@ -214,6 +216,13 @@ class LennardJonesCut(Potential):
         box_abi = system.box.to_abi()
         tidx_dev = particles._static_device(f"lj_tidx_{id(self)}", tidx, np.int32) if ntyp > 1 else None
         count = npart if count is None else count
+        if isinstance(box_abi, _lib.Cell):  # TriclinicBox: the all-pairs kernel with the exact image scan
+            _lib.call(
+                "tmd_lj_triclinic", _device.dptr(pos), _device.dptr(tidx_dev) if tidx_dev is not None else None,
+                npart, C.byref(box_abi), _lib.hptr(table), ntyp, flags, first, count,
+                _device.dptr(force) if force is not None else None, _device.dptr(vw), _device.stream_ptr(),
+            )
+            return
         name = self._kernel_for(npart, box_abi, table, ntyp)
         handle = (self._nlist_handle(),) if name == "tmd_lj_nlist" else ()
         _lib.call(
@@ -233,11 +242,18 @@ class LennardJonesCut(Potential):
             _device.require_cuda()
             types, table, tidx = self._tables(particles)
             box_abi = system.box.to_abi()
-            _lib.call(
-                "tmd_host_lj", _lib.hptr(pos), _lib.hptr(tidx), particles.npart, C.byref(box_abi),
-                _lib.hptr(table), len(types), flags, _METHODS[self.method],
-                _lib.hptr(force) if force is not None else None, _lib.hptr(vw),
-            )
+            if isinstance(box_abi, _lib.Cell):
+                _lib.call(
+                    "tmd_host_lj_triclinic", _lib.hptr(pos), _lib.hptr(tidx), particles.npart, C.byref(box_abi),
+                    _lib.hptr(table), len(types), flags, _lib.hptr(force) if force is not None else None,
+                    _lib.hptr(vw),
+                )
+            else:
+                _lib.call(
+                    "tmd_host_lj", _lib.hptr(pos), _lib.hptr(tidx), particles.npart, C.byref(box_abi),
+                    _lib.hptr(table), len(types), flags, _METHODS[self.method],
+                    _lib.hptr(force) if force is not None else None, _lib.hptr(vw),
+                )
         virial = vw[1:].reshape(3, 3)[:dim, :dim].copy()
         return float(vw[0]), force, virial
 

@@ -138,7 +138,8 @@ class Box(BoxBase):
 
 
 class TriclinicBox(BoxBase):
-    """Triclinic cell (box.py:177-318).  Host-only: the CUDA pair kernels reject it."""
+    """Triclinic cell (box.py:177-318).  ``LennardJonesCut`` evaluates in it through ``tmd_lj_triclinic``
+    (all-pairs, exact image scan); the cell / neighbour-list kernels and ``DoubleWellPair`` take ``Box`` only."""
 
     def __init__(self, low=None, high=None, periodic=None, alpha=None, beta=None, gamma=None):
         super().__init__(
@@ -161,9 +162,11 @@ class TriclinicBox(BoxBase):
         self.update_box_matrix(self.length, self.alpha, self.beta, self.gamma)
 
     def to_abi(self):
-        raise NotImplementedError(
-            "TriclinicBox is outside the CUDA hot path (SURVEY.md section 8f); use Box"
-        )
+        """The ``tmd_cell`` the triclinic pair kernel takes (``tmd_lj_triclinic``)."""
+        from .. import _lib
+
+        return _lib.make_cell(self.dim, self.box_matrix, self.box_matrix_inv, self.translations,
+                              self.shortest_width_half)
 
     def update_box_matrix(self, length, alpha, beta, gamma):
         self.box_matrix = box_matrix_from_angles(length, alpha, beta, gamma, self.dim)
