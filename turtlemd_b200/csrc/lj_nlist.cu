@@ -75,7 +75,7 @@ struct NlArgs {
     int *slot_of;        // [n] atom -> slot
     double4 *wrapped;    // [n] by atom: wrapped position at build time, .w = type
     double4 *xb;         // [n] by slot: the same, in cell order (build positions)
-    float4 *xbf;         // [n] by slot: single-precision copy for the list filter
+    float4 *xbf;         // [n/2][2] by slot pair: single-precision build positions {x0 x1 y0 y1} {z0 z1 - -}
     double4 *xs;         // [n] by slot: current positions (image removed), .w = type
     double *image;       // [n*3] by atom: lattice vector removed when wrapping
     unsigned *entries;   // [rows][cap]
@@ -142,6 +142,10 @@ __device__ __forceinline__ void st_entries8(unsigned *p, const unsigned (&e)[8])
                  "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7])
                  : "memory");
 }
+
+// Single-precision build positions (NlArgs::xbf): float index of coordinate c (0..2) of slot t in the
+// 32-byte pair records {x0, x1, y0, y1, z0, z1, -, -} of two consecutive slots (see nl_list_kernel)
+__device__ __forceinline__ size_t pair_index(int t, int c) { return (size_t)(t >> 1) * 8 + 2 * c + (t & 1); }
 
 template <int DIM>
 __global__ void __launch_bounds__(256) nl_gather_check_kernel(const double *__restrict__ pos,
@@ -303,7 +307,12 @@ __global__ void __launch_bounds__(kBinThreads) nl_bin_kernel(const NlArgs a) {
         a.slot_of[i] = t;
         a.xb[t] = w;
         a.xs[t] = w;
-        a.xbf[t] = make_float4((float)w.x, (float)w.y, (float)w.z, 0.f);
+        {
+            float *xf = reinterpret_cast<float *>(a.xbf);
+            xf[pair_index(t, 0)] = (float)w.x;
+            xf[pair_index(t, 1)] = (float)w.y;
+            xf[pair_index(t, 2)] = (float)w.z;
+        }
     }
 }
 
@@ -318,10 +327,45 @@ __global__ void __launch_bounds__(kBinThreads) nl_bin_kernel(const NlArgs a) {
 // finds the entries of its next four rounds (q = l, l + 4, l + 8, l + 12) in ONE aligned 16-byte
 // load, while the four lanes of a round still work on four consecutive logical entries (nearly
 // consecutive slots, whose 32-byte records share cache lines).
-constexpr int kRing = 32;
+//
+// Filter arithmetic.  The single-precision build positions are stored as 32-byte PAIR records
+// {x0, x1, y0, y1, z0, z1, -, -} of two consecutive slots, and the distance test runs on the packed
+// FP32 pipe (FADD2 / FMUL2 / FFMA2 on sm_100a): six arithmetic instructions per two candidates, the
+// same individually rounded operations as the scalar form (d = xs - x; r = d d; r = fma(dy, dy, r); ...).
+//
+// Ring drains.  A lane's ring holds 64 entries.  Lanes fill at different rates; if each drained whenever
+// it had a block waiting, a warp would run the drain code after nearly every filter round with one or two
+// lanes active.  Instead the lanes that are converged vote: when any of them could overflow in the next
+// round, ALL write their complete blocks.
+constexpr int kRing = 64;
 constexpr int kBlockEntries = 16;
-constexpr int kChunk = 16;  // candidates per filter round
-static_assert(kBlockEntries - 1 + kChunk <= kRing, "the ring must hold a waiting partial block plus one filter round");
+constexpr int kChunk = 16;  // candidates per filter round (eight pair records)
+constexpr int kDrainAt = kRing - kBlockEntries - kChunk;  // vote to drain when a lane holds more than this
+static_assert(kDrainAt >= kBlockEntries - 1 && kDrainAt + kChunk <= kRing, "a filter round must always fit into the ring");
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 
 __device__ __forceinline__ int block_position(int q) { return (q & 3) * 4 + (q >> 2); }  // its own inverse
 
@@ -339,7 +383,8 @@ __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
     for (int64_t row = (int64_t)blockIdx.x * kNlThreads + tid; row < a.count; row += gthreads) {
         const int slot = whole ? (int)row : (a.row_mode ? (int)(a.first + row) : a.slot_of[a.first + row]);
         const int atom = (whole || a.row_mode) ? a.order[slot] : (int)(a.first + row);
-        const float4 me = a.xbf[slot];
+        const float *xf = reinterpret_cast<const float *>(a.xbf);
+        const float mex = xf[pair_index(slot, 0)], mey = xf[pair_index(slot, 1)], mez = xf[pair_index(slot, 2)];
         const int cell = a.cell_of[atom];
         const int c0 = cell % g.nc[0], c1 = (cell / g.nc[0]) % g.nc[1], c2 = cell / (g.nc[0] * g.nc[1]);
         unsigned *list = a.entries + (size_t)row * cap;  // cap is a multiple of 16: rows are 64-byte aligned
@@ -360,30 +405,37 @@ __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
             }
         };
         for_each_run<DIM>(g, a.starts, c0, c1, c2, [&](int jbegin, int jend, int code) {
-            const float xs = me.x - (code % 3 - 1) * lx;
-            const float ys = me.y - ((code / 3) % 3 - 1) * ly;
-            const float zs = me.z - (code / 9 - 1) * lz;
+            const float xs = mex - (code % 3 - 1) * lx;
+            const float ys = mey - ((code / 3) % 3 - 1) * ly;
+            const float zs = mez - (code / 9 - 1) * lz;
+            const unsigned long long xs2 = pack2(xs, xs), ys2 = pack2(ys, ys), zs2 = pack2(zs, zs);
             const unsigned tag = (unsigned)code << 27;
-            // kChunk candidates at a time: distances first (loads not predicated: the index is clamped and
-            // the bits of candidates beyond the run are masked afterwards), hits recorded as bits, then
-            // the few set bits are turned into entries.  At most 15 + kChunk entries wait: the ring cannot wrap.
-            for (int j0 = jbegin; j0 < jend; j0 += kChunk) {
+            // kChunk candidates = eight pair records at a time, starting at the pair that holds jbegin (loads
+            // not predicated: xbf is padded, and the bits of candidates outside the run are masked afterwards);
+            // hits recorded as bits, then the few set bits are turned into entries.
+            for (int p0 = jbegin >> 1; 2 * p0 < jend; p0 += kChunk / 2) {
+                const float4 *rec = a.xbf + 2 * (size_t)p0;
                 unsigned m = 0;
-                const float4 *cand = a.xbf + j0;  // xbf is padded by kChunk records: no clamping of the index
-                float4 q16[kChunk];
 #pragma unroll
-                for (int u = 0; u < kChunk; ++u) q16[u] = __ldg(cand + u);
-#pragma unroll
-                for (int u = 0; u < kChunk; ++u) {
-                    const float4 q = q16[u];
-                    float d = xs - q.x;
-                    float r = d * d;
-                    if (DIM > 1) { d = ys - q.y; r = fmaf(d, d, r); }
-                    if (DIM > 2) { d = zs - q.z; r = fmaf(d, d, r); }
-                    if (r < reach2) m |= 1u << u;
+                for (int u = 0; u < kChunk / 2; ++u) {
+                    const float4 qa = __ldg(rec + 2 * u);  // x0 x1 y0 y1
+                    unsigned long long d = sub2(xs2, pack2(qa.x, qa.y));
+                    unsigned long long r = mul2(d, d);
+                    if (DIM > 1) { d = sub2(ys2, pack2(qa.z, qa.w)); r = fma2(d, d, r); }
+                    if (DIM > 2) {
+                        const float4 qb = __ldg(rec + 2 * u + 1);  // z0 z1 - -
+                        d = sub2(zs2, pack2(qb.x, qb.y));
+                        r = fma2(d, d, r);
+                    }
+                    float r0, r1;
+                    unpack2(r, r0, r1);
+                    if (r0 < reach2) m |= 1u << (2 * u);
+                    if (r1 < reach2) m |= 2u << (2 * u);
                 }
+                const int j0 = 2 * p0;
                 const int left = jend - j0;
                 if (left < kChunk) m &= (1u << left) - 1u;
+                if (j0 < jbegin) m &= ~1u;  // the first pair record may start one slot before the run
                 const unsigned self = (unsigned)(slot - j0);
                 if (self < (unsigned)kChunk) m &= ~(1u << self);
                 while (m) {
@@ -392,9 +444,10 @@ __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
                     s_ring[cnt & (kRing - 1)][tid] = tag | (unsigned)(j0 + b);
                     ++cnt;
                 }
-                drain();
+                if (__any_sync(__activemask(), cnt - flushed > kDrainAt)) drain();
             }
         });
+        drain();
         if (cnt <= cap) {  // the 0..15 entries of the last, partial block (same transposed positions)
             for (int k = flushed; k < cnt; ++k) list[flushed + block_position(k - flushed)] = s_ring[k & (kRing - 1)][tid];
         } else {
@@ -910,8 +963,9 @@ static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double
         TMD_CUDA(cudaMemsetAsync(nl->ints, 0, n_ints * sizeof(int), s));  // counts[] must start at zero
         TMD_CUDA(cudaMalloc(&nl->wrapped, (size_t)n * sizeof(double4)));
         TMD_CUDA(cudaMalloc(&nl->xb, (size_t)n * sizeof(double4)));
-        TMD_CUDA(cudaMalloc(&nl->xbf, ((size_t)n + kChunk) * sizeof(float4)));  // the list filter reads whole chunks
-        TMD_CUDA(cudaMemsetAsync(nl->xbf + n, 0x7f, (size_t)kChunk * sizeof(float4), s));  // 3.4e38: never inside the reach
+        // pair records (two float4 per two slots); the list filter reads eight of them at a time: pad
+        TMD_CUDA(cudaMalloc(&nl->xbf, ((size_t)(n + 1) / 2 + kChunk / 2) * 2 * sizeof(float4)));
+        TMD_CUDA(cudaMemsetAsync(nl->xbf, 0, ((size_t)(n + 1) / 2 + kChunk / 2) * 2 * sizeof(float4), s));
         if (!nl->xs_ext) TMD_CUDA(cudaMalloc(&nl->xs, (size_t)n * sizeof(double4)));
         TMD_CUDA(cudaMalloc(&nl->image, (size_t)n * 3 * sizeof(double)));
         fresh = true;
