@@ -411,13 +411,63 @@ def bench_replicas(args, cfg, rank, world):
     }
     if rank != 0:
         return None
-    bytes_per_launch = 48.0 * n  # x, v, F read + written once per launch
+    # 32 B per replica-step (x, v read + written), whatever the kernel does; the fused kernel
+    # keeps a replica in registers for `inner` steps, so what it really moves is 48 B per replica per launch
+    bytes_per_launch = 32.0 * n * inner
     out["roofline"] = {"bound": "hbm", "achieved": bytes_per_launch / (sec / args.steps) / 1e9,
                        "peak": peak_hbm(), "unit": "GB/s", "traffic": None,
-                       "note": "compute-bound by Philox + log/sincos at 10 steps per launch; see DESIGN.md"}
+                       "kernel": "inertia_doublewell_pair_kernel<1,true>",
+                       "algorithmic_bytes_per_launch": bytes_per_launch,
+                       "moved_bytes_per_launch_estimate": 48.0 * n,
+                       "note": "algorithmic bytes = 32 B per replica-step x replica-steps per launch (SURVEY.md 8d); "
+                               f"with {inner} steps fused per launch the kernel is bound by the FP64 / integer work "
+                               "of the noise (Philox4x64 + log / sincos), not by HBM; see DESIGN.md"}
     out["roofline"]["frac"] = out["roofline"]["achieved"] / out["roofline"]["peak"]
-    del C, _device, _lib
+    if world == 1 and not args.quick:
+        # e2e: host arrays in and out around every launch through the public API
+        part = system.particles
+        hx, hv, hf = (_device.pinned_array(x0.shape) for _ in range(3))
+        np.copyto(hx, part.pos)
+        np.copyto(hv, part.vel)
+        np.copyto(hf, part.force)
+
+        def e2e_step():
+            part.pos, part.vel, part.force = hx, hv, hf
+            integ.run(system, inner, first=first, n_global=n_global)
+            _ = part.pos, part.vel, part.force, part.v_pot
+
+        for _ in range(2):
+            e2e_step()
+        esteps = max(3, min(args.steps, 20))
+        esec = timed(e2e_step, esteps, 1)
+        out["e2e"] = {"value": n * inner * esteps / esec, "unit": cfg["unit"],
+                      "h2d_bytes_per_step": 3 * x0.nbytes, "d2h_bytes_per_step": 3 * x0.nbytes + 80,
+                      "ms_per_step": esec / esteps * 1e3,
+                      "api": f"LangevinInertia.run(system, {inner}) with particles.pos/vel/force re-bound from "
+                             "page-locked host arrays and read back after every call"}
+        out["cpu_baseline"] = cpu_baseline_replicas(cfg)
+    del C, _lib
     return out
+
+
+def cpu_baseline_replicas(cfg, sample=20000, budget_s=10.0):
+    """The NumPy oracle's LangevinInertia step (restated reference: one Python-level draw per particle,
+    integrators.py:284-315) over a sample of the replicas, one core."""
+    from oracle import turtle_oracle as to
+
+    ff = to.ForceField(np.array([np.inf]), np.array([0.0]), [False], [("dw", (1.0, 2.0, 0.0))])
+    st = to.State(np.full((sample, 1), -1.0), np.zeros((sample, 1)), np.ones(sample))
+    st.force, st.virial = ff.force(st.pos)
+    stepper = to.InertiaStepper(cfg["dt"], 0.3, 1.0 / 0.07, np.random.default_rng(0))
+    stepper.step(st, ff)  # builds the per-particle constants
+    steps, t0 = 0, time.perf_counter()
+    while steps < 1 or time.perf_counter() - t0 < budget_s:
+        stepper.step(st, ff)
+        steps += 1
+    sec = time.perf_counter() - t0
+    return {"value": sample * steps / sec, "unit": "replica-steps/s", "cores": 1, "kind": "port",
+            "sample": f"NumPy oracle LangevinInertia + DoubleWell on {sample} of {cfg['n']} replicas, {steps} steps in "
+                      f"{sec:.1f} s (throughput does not depend on the ensemble size); host has {os.cpu_count()} cores"}
 
 
 def peak_hbm():

@@ -18,4 +18,7 @@ prof() {  # workload  kernel-regex
 }
 prof lj1m nl_force_kernel
 prof lj32k lj_allpairs_sym_kernel
+# the list build: the first launch of a run is a real rebuild (later ones return at the gate)
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:nl_list_kernel -c 1 \
+    -o $OUT/prof_list_$TAG -f python bench.py --workload lj1m --steps 3 --warmup 3 --quick > $OUT/ncu_full_list.log 2>&1
 ls -la $OUT | tail -12
