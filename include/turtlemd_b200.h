@@ -333,6 +333,14 @@ int tmd_kinetic_tensor(const double *vel, const double *mass, int64_t n, int32_t
 int tmd_lj_triclinic(const double *pos, const int32_t *tidx, int64_t n, const tmd_cell *cell,
                      const double *table, int32_t ntypes, uint32_t flags, int64_t first, int64_t count,
                      double *force, double *vw, tmd_stream_t stream);
+/* DoubleWellPair.potential / .force (potentials/well.py:230-286) with box = TriclinicBox; arguments as
+ * tmd_dwpair / tmd_host_dwpair.                                                                       */
+int tmd_dwpair_triclinic(const double *pos, int64_t n, const tmd_cell *cell, const int32_t *idx0, int32_t n0,
+                         const int32_t *idx1, int32_t n1, int32_t same_type, double rwidth, double width2,
+                         double height, uint32_t flags, double *force, double *vw, tmd_stream_t stream);
+int tmd_host_dwpair_triclinic(const double *pos, const int64_t *ptype, int64_t n, const tmd_cell *cell,
+                              int64_t type0, int64_t type1, double rwidth, double width2, double height,
+                              uint32_t flags, double *force, double *vw);
 /* the same with host buffers (ptype already mapped to 0..ntypes-1)                                 */
 int tmd_host_lj_triclinic(const double *pos, const int64_t *tidx, int64_t n, const tmd_cell *cell,
                           const double *table, int32_t ntypes, uint32_t flags, double *force, double *vw);

@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 
 import make_golden as mg  # noqa: F401  (puts the reference and the repo on sys.path)
-from turtlemd.potentials import LennardJonesCut
+from turtlemd.potentials import DoubleWellPair, LennardJonesCut
 from turtlemd.system import System
 from turtlemd.system.box import TriclinicBox
 
@@ -49,6 +49,17 @@ def main():
                 angles=np.array([np.nan if a is None else a for a in (alpha, beta, gamma)]),
                 rscale=rscale, v=v, f=f, w=w, v_only=v_only, w_only=w_only,
                 box_matrix=box.box_matrix, half_width=box.shortest_width_half)
+        # DoubleWellPair in the same skewed cell (potentials/well.py:230-286 with TriclinicBox.pbc_dist)
+        if n <= 100:
+            for types in ((1, 1), (0, 1)):
+                dw = DoubleWellPair(types=types, dim=dim)
+                dw.set_parameters({"rzero": 1.2, "width": 0.3, "height": 5.0})
+                sys_dw = System(box, mg.bulk_particles(pos, ptype=ptype), [dw])
+                fd, wd = dw.force(sys_dw)
+                mg.save(f"triclinic_dwpair_{tag}_types{types[0]}{types[1]}.npz", pos=pos, ptype=ptype,
+                        high=np.array(high, dtype=float),
+                        angles=np.array([np.nan if a is None else a for a in (alpha, beta, gamma)]),
+                        types=np.array(types), rzero=1.2, width=0.3, height=5.0, v=dw.potential(sys_dw), f=fd, w=wd)
         near = np.sum(np.abs(f) > 0) // dim
         print(tag, "V", v, "atoms with force", near, "half width", box.shortest_width_half,
               "max rc", max(p["rcut"] for p in params.values()))

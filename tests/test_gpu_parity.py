@@ -337,6 +337,38 @@ def test_lj_in_a_triclinic_box(tag):
     assert np.all(np.isfinite(system.particles.pos)) and np.isfinite(system.particles.v_pot)
 
 
+@pytest.mark.parametrize("name", ["3d_90_longcut_types11", "3d_90_longcut_types01", "2d_80_types11", "2d_80_types01"])
+def test_doublewell_pair_in_a_triclinic_box(name):
+    """DoubleWellPair with box = TriclinicBox against the reference, host-buffer entry point and device path,
+    alone and summed with LennardJonesCut by System (system.py:58-99)."""
+    from turtlemd_b200.system import Particles, System, TriclinicBox
+
+    k = _pkg()
+    g = load_golden(f"triclinic_dwpair_{name}.npz")
+    alpha, beta, gamma = (None if np.isnan(a) else float(a) for a in g["angles"])
+    box = TriclinicBox(high=list(g["high"]), alpha=alpha, beta=beta, gamma=gamma)
+    dw = k["DoubleWellPair"](types=tuple(int(t) for t in g["types"]), dim=len(g["high"]))
+    dw.set_parameters({"rzero": float(g["rzero"]), "width": float(g["width"]), "height": float(g["height"])})
+    system = System(box, Particles.from_arrays(g["pos"], ptype=g["ptype"]), [dw])
+    assert abs(dw.potential(system) - float(g["v"])) <= TOL * abs(float(g["v"]))
+    f, w = dw.force(system)
+    assert rel_norm(f, g["f"]) < TOL and rel_norm(w, g["w"]) < TOL
+    system.potential_and_force()
+    assert rel_norm(system.particles.force, g["f"]) < TOL and rel_norm(system.particles.virial, g["w"]) < TOL
+    # with the Lennard-Jones fluid of the same fixture family on top
+    lj_tag = name.rsplit("_types", 1)[0]
+    gl = load_golden(f"triclinic_lj_{lj_tag}.npz")
+    params = {t: dict(v, rcut=v["rcut"] * float(gl["rscale"]))
+              for t, v in {0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}, 1: {"sigma": 1.1, "epsilon": 0.8, "rcut": 2.2}}.items()}
+    lj = k["LennardJonesCut"](dim=len(g["high"]), shift=True, mixing="geometric")
+    lj.set_parameters(params)
+    both = System(box, Particles.from_arrays(g["pos"], ptype=g["ptype"]), [lj, dw])
+    both.potential_and_force()
+    assert rel_norm(both.particles.force, gl["f"] + g["f"]) < TOL
+    assert rel_norm(both.particles.virial, gl["w"] + g["w"]) < TOL
+    assert abs(both.particles.v_pot - float(gl["v"]) - float(g["v"])) <= TOL * (abs(float(gl["v"])) + abs(float(g["v"])))
+
+
 @pytest.mark.parametrize("tag", ["3d_500", "1d_64", "2d_301"])
 def test_maxwell_velocities_on_the_device(tag):
     """Velocity set-up with the in-kernel stream (draw, momentum removal, rescaling on the device) against

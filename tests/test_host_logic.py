@@ -137,10 +137,6 @@ def test_box_construction(caplog):
     assert cell.dim == 3 and cell.half_width == tri.shortest_width_half
     assert np.array_equal(np.array(cell.matrix[:]).reshape(3, 3), tri.box_matrix)
     assert np.array_equal(np.array(cell.translations[:]).reshape(27, 3), tri.translations)
-    from turtlemd_b200.potentials.well import DoubleWellPair as _DWP
-
-    with pytest.raises(NotImplementedError):  # the pair well is not offered in skewed cells
-        _DWP._orthogonal_box(System(tri, Particles(dim=3)))
 
 
 # ---- particles -----------------------------------------------------------------------------------------

@@ -140,6 +140,19 @@ def test_doublewell_pair(types):
     assert np.array_equal(f, g["f"]) and np.array_equal(w, g["w"])
 
 
+@pytest.mark.parametrize("name", ["3d_90_longcut_types11", "3d_90_longcut_types01", "2d_80_types11", "2d_80_types01"])
+def test_doublewell_pair_in_a_triclinic_cell(name):
+    """well.py:230-286 with TriclinicBox.pbc_dist (box.py:271-296); tests/golden/make_golden_triclinic.py."""
+    g = load_golden(f"triclinic_dwpair_{name}.npz")
+    alpha, beta, gamma = (None if np.isnan(a) else float(a) for a in g["angles"])
+    cell = to.TriclinicCell(g["high"], alpha, beta, gamma)
+    par = to.dwpair_params(float(g["rzero"]), float(g["width"]), float(g["height"]))
+    tt = tuple(int(t) for t in g["types"])
+    assert to.dwpair_potential(g["pos"], g["ptype"], cell, None, None, tt, par) == g["v"]
+    f, w = to.dwpair_force(g["pos"], g["ptype"], cell, None, None, tt, par)
+    assert np.array_equal(f, g["f"]) and np.array_equal(w, g["w"])
+
+
 def test_doublewell_pair_reference_known_answer():
     """tests/potentials/test_wellwca.py:12-14,35-45,87-110."""
     k = load_golden("reference_kats.npz")

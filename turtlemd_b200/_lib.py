@@ -133,6 +133,8 @@ PROTOTYPES = {
     "tmd_kinetic_tensor": [_P, _P, _I64, _I32, _P, _P],
     "tmd_lj_triclinic": [_P, _P, _I64, _CELL, _P, _I32, _U32, _I64, _I64, _P, _P, _P],
     "tmd_host_lj_triclinic": [_P, _P, _I64, _CELL, _P, _I32, _U32, _P, _P],
+    "tmd_dwpair_triclinic": [_P, _I64, _CELL, _P, _I32, _P, _I32, _I32, _D, _D, _D, _U32, _P, _P, _P],
+    "tmd_host_dwpair_triclinic": [_P, _P, _I64, _CELL, _I64, _I64, _D, _D, _D, _U32, _P, _P],
     "tmd_maxwell_draw": [_P, _P, _I64, _I32, _RNG, _I64, _P],
     "tmd_momentum": [_P, _P, _I64, _I32, _P, _P],
     "tmd_vel_shift_scale": [_P, _I64, _I32, _P, _I32, _D, _P],

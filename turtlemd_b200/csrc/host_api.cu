@@ -112,10 +112,27 @@ int tmd_host_doublewell(const double *pos, int64_t n, int32_t dim, double a, dou
     return download_results(flags, fbytes, d_force, d_vw, force, vw, s);
 }
 
+static int host_dwpair(const double *pos, const int64_t *ptype, int64_t n, int dim, const tmd_box *box,
+                       const tmd_cell *cell, int64_t type0, int64_t type1, double rwidth, double width2,
+                       double height, uint32_t flags, double *force, double *vw);
+
 int tmd_host_dwpair(const double *pos, const int64_t *ptype, int64_t n, const tmd_box *box, int64_t type0,
                     int64_t type1, double rwidth, double width2, double height, uint32_t flags, double *force,
                     double *vw) {
     TMD_REQUIRE(box && box->dim >= 1 && box->dim <= 3 && n >= 0, "bad box or n");
+    return host_dwpair(pos, ptype, n, box->dim, box, nullptr, type0, type1, rwidth, width2, height, flags, force, vw);
+}
+
+int tmd_host_dwpair_triclinic(const double *pos, const int64_t *ptype, int64_t n, const tmd_cell *cell,
+                              int64_t type0, int64_t type1, double rwidth, double width2, double height,
+                              uint32_t flags, double *force, double *vw) {
+    TMD_REQUIRE(cell && cell->dim >= 2 && cell->dim <= 3 && n >= 0, "bad cell or n");
+    return host_dwpair(pos, ptype, n, cell->dim, nullptr, cell, type0, type1, rwidth, width2, height, flags, force, vw);
+}
+
+static int host_dwpair(const double *pos, const int64_t *ptype, int64_t n, int dim, const tmd_box *box,
+                       const tmd_cell *cell, int64_t type0, int64_t type1, double rwidth, double width2,
+                       double height, uint32_t flags, double *force, double *vw) {
     TMD_REQUIRE(ptype != nullptr || n == 0, "ptype is NULL");
     TMD_REQUIRE(vw != nullptr, "vw is NULL");
     TMD_REQUIRE(!(flags & TMD_ACCUMULATE), "TMD_ACCUMULATE is meaningless with host buffers");
@@ -127,7 +144,7 @@ int tmd_host_dwpair(const double *pos, const int64_t *ptype, int64_t n, const tm
         else if (ptype[i] == type1) idx1.push_back((int32_t)i);
     }
     const int same = type0 == type1;
-    const size_t fbytes = (size_t)n * box->dim * sizeof(double);
+    const size_t fbytes = (size_t)n * dim * sizeof(double);
     double *d_pos = nullptr, *d_force = nullptr, *d_vw = nullptr;
     int32_t *d_i0 = nullptr, *d_i1 = nullptr;
     TMD_CHECK(upload(SLOT_HOST_A, pos, fbytes, (void **)&d_pos, s));
@@ -136,8 +153,12 @@ int tmd_host_dwpair(const double *pos, const int64_t *ptype, int64_t n, const tm
     TMD_CUDA(cudaStreamSynchronize(s));  // idx vectors are pageable temporaries
     TMD_CHECK(arena_get(SLOT_HOST_C, fbytes + 8, (void **)&d_force));
     TMD_CHECK(arena_get(SLOT_HOST_D, 10 * sizeof(double), (void **)&d_vw));
-    TMD_CHECK(tmd_dwpair(d_pos, n, box, d_i0, (int32_t)idx0.size(), d_i1, (int32_t)idx1.size(), same, rwidth,
-                         width2, height, flags, d_force, d_vw, s));
+    if (cell)
+        TMD_CHECK(tmd_dwpair_triclinic(d_pos, n, cell, d_i0, (int32_t)idx0.size(), d_i1, (int32_t)idx1.size(), same,
+                                       rwidth, width2, height, flags, d_force, d_vw, s));
+    else
+        TMD_CHECK(tmd_dwpair(d_pos, n, box, d_i0, (int32_t)idx0.size(), d_i1, (int32_t)idx1.size(), same, rwidth,
+                             width2, height, flags, d_force, d_vw, s));
     return download_results(flags, fbytes, d_force, d_vw, force, vw, s);
 }
 

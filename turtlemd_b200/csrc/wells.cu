@@ -2,6 +2,7 @@
 // atoms whose type the potential is active for).  Reference: turtlemd/potentials/well.py.
 #include "common.cuh"
 #include "doublewell.cuh"
+#include "triclinic.cuh"
 
 namespace tmd {
 
@@ -50,8 +51,9 @@ static inline BoxDev make_box(const tmd_box *box) {
 
 // One thread per active atom; it walks all its partners in index order and sums its own force,
 // half of the pair energies and half of the pair virials: no atomics, fixed order.
-template <int DIM>
-__global__ void __launch_bounds__(128) dwpair_kernel(const double *__restrict__ pos, BoxDev box,
+// TRI: the box is a TriclinicBox and the minimum image is TriclinicBox.pbc_dist (box.py:271-296).
+template <int DIM, bool TRI>
+__global__ void __launch_bounds__(128) dwpair_kernel(const double *__restrict__ pos, BoxDev box, TriCell cell,
                                                      const int32_t *__restrict__ idx0, int n0,
                                                      const int32_t *__restrict__ idx1, int n1, int same_type,
                                                      double rwidth, double width2, double height,
@@ -83,11 +85,13 @@ __global__ void __launch_bounds__(128) dwpair_kernel(const double *__restrict__ 
                 const double xj = pos[(int64_t)you * DIM + k];
                 double dk = first ? __dsub_rn(xi[k], xj) : __dsub_rn(xj, xi[k]);
                 // Box.pbc_dist: strict '>' half box, stored reciprocal (box.py:376-378)
-                if (box.per[k] && fabs(dk) > box.half[k])
+                if (!TRI && box.per[k] && fabs(dk) > box.half[k])
                     dk = __dsub_rn(dk, __dmul_rn(rint(__dmul_rn(dk, box.ilen[k])), box.len[k]));
                 d[k] = dk;
-                rsq = (k == 0) ? __dmul_rn(dk, dk) : __dadd_rn(rsq, __dmul_rn(dk, dk));
             }
+            if (TRI) tri_min_image<DIM>(cell, d);
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) rsq = (k == 0) ? __dmul_rn(d[k], d[k]) : __dadd_rn(rsq, __dmul_rn(d[k], d[k]));
             const double delr = __dsqrt_rn(rsq);
             const double diff = __dsub_rn(delr, rwidth);
             const double q = __ddiv_rn(__dmul_rn(diff, diff), width2);
@@ -148,32 +152,53 @@ int tmd_doublewell(const double *pos, int64_t n, int32_t dim, double a, double b
     return launch_reduce_vw(partials, blocks, 1.0, flags, vw, s);
 }
 
-int tmd_dwpair(const double *pos, int64_t n, const tmd_box *box, const int32_t *idx0, int32_t n0,
-               const int32_t *idx1, int32_t n1, int32_t same_type, double rwidth, double width2, double height,
-               uint32_t flags, double *force, double *vw, tmd_stream_t stream) {
-    TMD_REQUIRE(box && box->dim >= 1 && box->dim <= 3 && n >= 0, "bad box or n");
+static int launch_dwpair(const double *pos, int64_t n, int dim, const tmd_box *box, const tmd_cell *tri,
+                         const int32_t *idx0, int32_t n0, const int32_t *idx1, int32_t n1, int32_t same_type,
+                         double rwidth, double width2, double height, uint32_t flags, double *force, double *vw,
+                         cudaStream_t s) {
     TMD_REQUIRE(n0 >= 0 && n1 >= 0, "negative index count");
     TMD_REQUIRE(!(flags & TMD_WANT_F) || force, "force is NULL but TMD_WANT_F is set");
     TMD_REQUIRE(vw != nullptr, "vw is NULL");
     TMD_CHECK(require_device());
-    cudaStream_t s = as_stream(stream);
     if ((flags & TMD_WANT_F) && !(flags & TMD_ACCUMULATE))
-        TMD_CUDA(cudaMemsetAsync(force, 0, (size_t)n * box->dim * sizeof(double), s));
+        TMD_CUDA(cudaMemsetAsync(force, 0, (size_t)n * dim * sizeof(double), s));
     const int nown = same_type ? n0 : n0 + n1;
     int blocks = (nown + 127) / 128;
     if (blocks < 1) blocks = 1;
     double *partials = nullptr;
     TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)blocks * 10 * sizeof(double), (void **)&partials));
-    const BoxDev bd = make_box(box);
+    BoxDev bd = {};
+    TriCell cell = {};
+    if (tri) TMD_CHECK(load_tri_cell(tri, cell));
+    else bd = make_box(box);
     // the kernel adds into force[] (zeroed above when overwriting)
     const uint32_t kflags = flags | TMD_ACCUMULATE;
-#define TMD_DWP(D) \
-    ::tmd::count_launch(), dwpair_kernel<D><<<blocks, 128, 0, s>>>(pos, bd, idx0, n0, idx1, n1, same_type, rwidth, width2, height, kflags, force, partials)
-    if (box->dim == 1) TMD_DWP(1); else if (box->dim == 2) TMD_DWP(2); else TMD_DWP(3);
+#define TMD_DWP(D, T) \
+    ::tmd::count_launch(), dwpair_kernel<D, T><<<blocks, 128, 0, s>>>(pos, bd, cell, idx0, n0, idx1, n1, same_type, rwidth, width2, height, kflags, force, partials)
+    if (tri) { if (dim == 2) TMD_DWP(2, true); else TMD_DWP(3, true); }
+    else if (dim == 1) TMD_DWP(1, false);
+    else if (dim == 2) TMD_DWP(2, false);
+    else TMD_DWP(3, false);
 #undef TMD_DWP
     TMD_CUDA(cudaGetLastError());
     // every pair was visited from both ends
     return launch_reduce_vw(partials, blocks, 0.5, flags, vw, s);
+}
+
+int tmd_dwpair(const double *pos, int64_t n, const tmd_box *box, const int32_t *idx0, int32_t n0,
+               const int32_t *idx1, int32_t n1, int32_t same_type, double rwidth, double width2, double height,
+               uint32_t flags, double *force, double *vw, tmd_stream_t stream) {
+    TMD_REQUIRE(box && box->dim >= 1 && box->dim <= 3 && n >= 0, "bad box or n");
+    return launch_dwpair(pos, n, box->dim, box, nullptr, idx0, n0, idx1, n1, same_type, rwidth, width2, height, flags,
+                         force, vw, as_stream(stream));
+}
+
+int tmd_dwpair_triclinic(const double *pos, int64_t n, const tmd_cell *cell, const int32_t *idx0, int32_t n0,
+                         const int32_t *idx1, int32_t n1, int32_t same_type, double rwidth, double width2,
+                         double height, uint32_t flags, double *force, double *vw, tmd_stream_t stream) {
+    TMD_REQUIRE(cell && cell->dim >= 2 && cell->dim <= 3 && n >= 0, "bad cell or n");
+    return launch_dwpair(pos, n, cell->dim, nullptr, cell, idx0, n0, idx1, n1, same_type, rwidth, width2, height, flags,
+                         force, vw, as_stream(stream));
 }
 
 }  // extern "C"

@@ -147,20 +147,13 @@ class DoubleWellPair(Potential):
     def _energy_is_pass_independent(self, system) -> bool:
         return True  # one formula for V whatever else is computed (well.py)
 
-    @staticmethod
-    def _orthogonal_box(system):
-        box_abi = system.box.to_abi()
-        if not isinstance(box_abi, _lib.Box):
-            raise NotImplementedError("DoubleWellPair on the device takes an orthogonal Box (TriclinicBox: "
-                                      "LennardJonesCut only, SURVEY.md section 8f)")
-        return box_abi
-
     def _launch(self, system, pos, force, vw, flags):
         particles = system.particles
         idx0, idx1, dev0, dev1 = self._active(particles)
-        box_abi = self._orthogonal_box(system)
+        box_abi = system.box.to_abi()  # tmd_box, or tmd_cell for a TriclinicBox
+        name = "tmd_dwpair_triclinic" if isinstance(box_abi, _lib.Cell) else "tmd_dwpair"
         _lib.call(
-            "tmd_dwpair", _device.dptr(pos), particles._pos.shape[0], C.byref(box_abi),
+            name, _device.dptr(pos), particles._pos.shape[0], C.byref(box_abi),
             _device.dptr(dev0) if dev0 is not None else None, len(idx0),
             _device.dptr(dev1) if dev1 is not None else None, len(idx1),
             1 if self.types[0] == self.types[1] else 0, *self._scalars(), flags,
@@ -174,9 +167,10 @@ class DoubleWellPair(Potential):
         ptype = np.ascontiguousarray(particles.ptype, dtype=np.int64)
         force = np.zeros(pos.shape) if flags & _lib.WANT_F else None
         vw = np.zeros(10)
-        box_abi = self._orthogonal_box(system)
+        box_abi = system.box.to_abi()
+        name = "tmd_host_dwpair_triclinic" if isinstance(box_abi, _lib.Cell) else "tmd_host_dwpair"
         _lib.call(
-            "tmd_host_dwpair", _lib.hptr(pos), _lib.hptr(ptype), pos.shape[0], C.byref(box_abi),
+            name, _lib.hptr(pos), _lib.hptr(ptype), pos.shape[0], C.byref(box_abi),
             int(self.types[0]), int(self.types[1]), *self._scalars(), flags,
             _lib.hptr(force) if force is not None else None, _lib.hptr(vw),
         )

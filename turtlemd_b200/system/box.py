@@ -138,8 +138,9 @@ class Box(BoxBase):
 
 
 class TriclinicBox(BoxBase):
-    """Triclinic cell (box.py:177-318).  ``LennardJonesCut`` evaluates in it through ``tmd_lj_triclinic``
-    (all-pairs, exact image scan); the cell / neighbour-list kernels and ``DoubleWellPair`` take ``Box`` only."""
+    """Triclinic cell (box.py:177-318).  ``LennardJonesCut`` and ``DoubleWellPair`` evaluate in it through
+    ``tmd_lj_triclinic`` / ``tmd_dwpair_triclinic`` (all-pairs, exact image scan); the cell / neighbour-list
+    kernels and the multi-GPU decompositions take ``Box`` only."""
 
     def __init__(self, low=None, high=None, periodic=None, alpha=None, beta=None, gamma=None):
         super().__init__(
