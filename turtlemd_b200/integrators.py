@@ -190,14 +190,21 @@ class LangevinParameter:
     path should pay for).
     """
 
-    def __init__(self):
-        self.c0 = 0.0
-        self.a1 = 0.0
-        self.a2 = np.zeros(1)
-        self.b1 = np.zeros(1)
-        self.b2 = np.zeros(1)
+    def __init__(self, c0: float = 0.0, a1: float = 0.0, a2=None, b1=None, b2=None, mean=None, cov=None, cho=None):
+        # the reference's dataclass fields, in its order (integrators.py:170-177)
+        self.c0 = c0
+        self.a1 = a1
+        self.a2 = np.zeros(1) if a2 is None else a2
+        self.b1 = np.zeros(1) if b1 is None else b1
+        self.b2 = np.zeros(1) if b2 is None else b2
         self._cov = None
         self._lists = None
+        if mean is not None or cov is not None or cho is not None:
+            self._lists = (list(mean or []), list(cov or []), list(cho or []))
+
+    def __repr__(self) -> str:
+        return (f"LangevinParameter(c0={self.c0!r}, a1={self.a1!r}, a2={self.a2!r}, b1={self.b1!r}, "
+                f"b2={self.b2!r}, mean=[...{len(self.mean)}], cov=[...], cho=[...])")
 
     def _materialise(self):
         if self._lists is None:
