@@ -726,6 +726,35 @@ def test_lj_nlist_against_reference_fixture():
     assert abs(vh - v) <= 1e-13 * abs(v) and rel_norm(fh, f) < 1e-13 and rel_norm(wh, w) < 1e-12
 
 
+def test_lj_nlist_types_with_identical_parameters_take_the_one_type_kernel():
+    """Two particle types whose Lennard-Jones parameters coincide (a solute that differs from the solvent only in
+    its bonded terms, examples/movie-doublewell-pair.py): same numbers as the reference's one-type fixture."""
+    from turtlemd_b200.system import Box, Particles, System
+
+    k = _pkg()
+    g = load_golden("lj_fcc_4000.npz")
+    ptype = np.zeros(len(g["pos"]), dtype=int)
+    ptype[::7] = 1
+    one = {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}
+    pot = k["LennardJonesCut"](dim=3, shift=True, method="nlist")
+    pot.set_parameters({0: dict(one), 1: dict(one)})
+    system = System(Box(low=g["low"], high=g["high"]), Particles.from_arrays(g["pos"], ptype=ptype), [pot])
+    v, f, w = system.potential_and_force()
+    assert abs(v - g["v_pf"]) <= TOL * abs(g["v_pf"])
+    assert rel_norm(f, g["f_pf"]) < TOL and rel_norm(w, g["w_pf"]) < TOL
+    # parameters that differ go through the table look-ups again
+    pot2 = k["LennardJonesCut"](dim=3, shift=True, method="nlist")
+    pot2.set_parameters({0: dict(one), 1: dict(one, epsilon=0.5)})
+    system2 = System(Box(low=g["low"], high=g["high"]), Particles.from_arrays(g["pos"], ptype=ptype), [pot2])
+    ap = k["LennardJonesCut"](dim=3, shift=True, method="allpairs")
+    ap.set_parameters({0: dict(one), 1: dict(one, epsilon=0.5)})
+    system3 = System(Box(low=g["low"], high=g["high"]), Particles.from_arrays(g["pos"], ptype=ptype), [ap])
+    v2, f2, w2 = system2.potential_and_force()
+    v3, f3, w3 = system3.potential_and_force()
+    assert abs(v2 - v3) <= TOL * abs(v3) and rel_norm(f2, f3) < TOL and rel_norm(w2, w3) < TOL
+    assert rel_norm(f2, f) > 1e-3  # and they are a different force field
+
+
 def test_lj_nlist_small_box_is_refused():
     g = load_golden("lj_fcc_256.npz")
     system, pot = _lj_system(g, "lj_fcc_256.npz", method="nlist")

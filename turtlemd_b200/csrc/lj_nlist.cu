@@ -81,6 +81,7 @@ struct NlArgs {
     unsigned *entries;   // [rows][cap]
     int *nneigh;         // [rows]
     int cap;
+    int uniform_table;   // every type pair has the same six coefficients: the one-type kernel applies
     float reach2f;       // conservative single-precision filter radius^2
     double half_skin2;
     double centre[3];
@@ -814,7 +815,7 @@ static void nl_launch_force_m(const NlArgs &a, int blocks, cudaStream_t s) {
     const bool wv = a.flags & TMD_WANT_V, wf = a.flags & (TMD_WANT_F | TMD_WANT_W);
 #define TMD_NL_LAUNCH(SINGLE, WV, WF) \
     ::tmd::count_launch(), nl_force_kernel<DIM, SINGLE, 4, WV, WF, MINB><<<blocks, kNlThreads, 0, s>>>(a)
-    if (a.ntypes == 1) {
+    if (a.ntypes == 1 || a.uniform_table) {
         if (wv && wf) TMD_NL_LAUNCH(true, true, true);
         else if (wf) TMD_NL_LAUNCH(true, false, true);
         else TMD_NL_LAUNCH(true, true, false);
@@ -928,6 +929,12 @@ static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double
     const int dim = box->dim;
     double rc2max = 0.0;
     TMD_CHECK(load_lj_table(table, ntypes, a.tab, rc2max));
+    // e.g. a solute that differs from the solvent only in its bonded terms (examples/movie-doublewell-pair.py
+    // at scale): identical Lennard-Jones coefficients for every type pair need no table look-ups
+    a.uniform_table = 1;
+    for (int c = 0; c < 6; ++c)
+        for (int p = 1; p < ntypes * ntypes; ++p)
+            if (memcmp(&a.tab.c[c][p], &a.tab.c[c][0], sizeof(double)) != 0) a.uniform_table = 0;
     const double reach = sqrt(rc2max) + nl->skin;
     if (!nl_make_grid(box, reach, n, a.grid)) {
         set_error("tmd_lj_nlist: needs a fully periodic box with >= %d cells of edge (rcut+skin)/%d per direction "
