@@ -344,30 +344,6 @@ constexpr int kChunk = 16;  // candidates per filter round (eight pair records)
 constexpr int kDrainAt = kRing - kBlockEntries - kChunk;  // vote to drain when a lane holds more than this
 static_assert(kDrainAt >= kBlockEntries - 1 && kDrainAt + kChunk <= kRing, "a filter round must always fit into the ring");
 
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
 __device__ __forceinline__ int block_position(int q) { return (q & 3) * 4 + (q >> 2); }  // its own inverse
 
 template <int DIM>
