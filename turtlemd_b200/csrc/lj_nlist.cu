@@ -87,6 +87,7 @@ struct NlArgs {
     double centre[3];
     double *force;
     double *partial_vw;
+    double *vw;          // (V, W) of the call, written by the traversal block that finishes last
     LjTable tab;
 };
 
@@ -697,9 +698,34 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
         for (int k = 1; k < 10; ++k) red[k] = 0.0;
     }
     block_sum<10, kNlThreads>(red, s_red);
+    // The block that finishes last adds up the partials of all blocks (no second launch).  The order of
+    // the sum is fixed by block index and thread index, not by who arrives when: deterministic.
+    __shared__ int s_last;
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < 10; ++k) a.partial_vw[(size_t)blockIdx.x * 10 + k] = red[k];
+        __threadfence();
+        s_last = atomicInc(reinterpret_cast<unsigned *>(&a.nlflags[7]), gridDim.x - 1) == gridDim.x - 1;  // wraps to 0
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    constexpr int kLanes = kNlThreads / 10;  // 12 partial sums per component, then those in index order
+    __shared__ double s_fin[10][kLanes];
+    if (tid < 10 * kLanes) {
+        const int k = tid % 10, q = tid / 10;
+        double sum = 0.0;
+        for (int b = q; b < (int)gridDim.x; b += kLanes) sum += __ldcg(a.partial_vw + (size_t)b * 10 + k);
+        s_fin[k][q] = sum;
+    }
+    __syncthreads();
+    if (tid < 10) {
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < kLanes; ++q) sum += s_fin[tid][q];
+        // every pair was seen from both atoms: halve; quantities that were not asked for stay untouched
+        if (tid == 0 ? (flags & TMD_WANT_V) : (flags & TMD_WANT_W))
+            a.vw[tid] = ((flags & TMD_ACCUMULATE) ? a.vw[tid] : 0.0) + 0.5 * sum;
     }
 }
 
@@ -1016,13 +1042,14 @@ static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double
 static int nl_traverse(NlArgs &a, int dim, uint32_t flags, double *force, double *vw, cudaStream_t s) {
     a.flags = flags;
     a.force = force;
+    a.vw = vw;
     const int fblocks = nl_force_blocks(a.count, dim);
     TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)fblocks * 10 * sizeof(double), (void **)&a.partial_vw));
     if (dim == 1) nl_launch_force<1>(a, fblocks, s);
     else if (dim == 2) nl_launch_force<2>(a, fblocks, s);
     else nl_launch_force<3>(a, fblocks, s);
     TMD_CUDA(cudaGetLastError());
-    return launch_reduce_vw(a.partial_vw, fblocks, 0.5, flags, vw, s);
+    return TMD_OK;  // the traversal reduces (V, W) itself
 }
 
 int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t n, const tmd_box *box,
