@@ -1,5 +1,5 @@
 #!/bin/bash
-# Tuning sweep of the neighbour-list path: stencil half width (TMD_NL_H) x lanes per atom (TMD_NL_G)
+# Tuning sweep of the neighbour-list path (historic, r01c): stencil half width (TMD_NL_H) x lanes per atom (TMD_NL_G, fixed at 4 since r01p)
 # x resident blocks (TMD_NL_MINB).   usage: sweep_nlist.sh "H list" "G list" "MINB list"
 OUT=gpurun_out/sweep_nlist.txt
 : > $OUT

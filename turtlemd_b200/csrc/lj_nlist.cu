@@ -13,11 +13,13 @@
 //             phases separated by grid syncs: bin a wrapped copy into cells (edge >=
 //             (rcut+skin)/H, H = 1), exclusive scan, scatter, per-cell ordering by atom index (so
 //             nothing depends on how the ranking atomics resolved).  (2) one thread per row atom walks
-//             the (2H+1)^dim cells around it with a conservative SINGLE-precision filter and appends
-//             to its row-major list eight entries per 32-byte store, ascending by (stencil row, slot).
-//   traverse  G lanes per row atom, persistent blocks; 6 FP64 instructions per candidate to the exact
+//             the (2H+1)^dim cells around it with a conservative SINGLE-precision filter on the packed
+//             FP32 pipe and appends to its row-major list, logically ascending by (stencil row, slot),
+//             stored in transposed blocks of 16 entries (two 32-byte stores per block).
+//   traverse  four lanes per row atom, persistent blocks; 6 FP64 instructions per candidate to the exact
 //             cut-off test (strict rsq < rcut2, lennardjones.py:291-294), ~70 % pass.  Per-lane force
-//             accumulators, shuffle reduction in a fixed order, no atomics -> bit-reproducible.
+//             accumulators, shuffle reduction in a fixed order, no atomics -> bit-reproducible.  The
+//             block that finishes last reduces the per-block (V, W) partials.
 //
 // Virial.  The reference sums f (x) delta over pairs (lennardjones.py:272).  With delta_ij =
 // x_i - x_j - S_ij (S = the lattice vector of the image) and f_ij = -f_ji this equals
