@@ -755,6 +755,43 @@ def test_lj_nlist_types_with_identical_parameters_take_the_one_type_kernel():
     assert rel_norm(f2, f) > 1e-3  # and they are a different force field
 
 
+def test_positions_downloaded_under_the_force_evaluation_are_the_step_positions():
+    """A caller that re-binds page-locked host arrays and reads them back after every step (bench.py's e2e
+    loop) gets the positions through an asynchronous download that overlaps the force evaluation; they must be
+    the very positions a device-resident run produces."""
+    from turtlemd_b200 import _device
+    from turtlemd_b200.system import Box, Particles, System
+
+    k = _pkg()
+    g = load_golden("lj_fcc_4000.npz")
+    vel0 = 0.3 * np.random.default_rng(4).standard_normal(g["pos"].shape)
+
+    def make():
+        pot = k["LennardJonesCut"](dim=3, shift=True, method="nlist")
+        pot.set_parameters({0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}})
+        system = System(Box(low=g["low"], high=g["high"]), Particles.from_arrays(g["pos"], vel=vel0), [pot])
+        system.potential_and_force()
+        return system
+
+    a, b = make(), make()
+    integ_a, integ_b = k["integrators"].VelocityVerlet(0.004), k["integrators"].VelocityVerlet(0.004)
+    hp, hv, hf = (_device.pinned_array(g["pos"].shape) for _ in range(3))
+    np.copyto(hp, a.particles.pos)
+    np.copyto(hv, a.particles.vel)
+    np.copyto(hf, a.particles.force)
+    prefetched = 0
+    for _ in range(6):
+        a.particles.pos, a.particles.vel, a.particles.force = hp, hv, hf
+        integ_a(a)
+        prefetched += a.particles._pos._prefetch is not None
+        pos_a, vel_a, force_a = a.particles.pos, a.particles.vel, a.particles.force
+        integ_b(b)
+        assert np.array_equal(pos_a, b.particles._pos.peek())
+        assert np.array_equal(vel_a, b.particles._vel.peek())
+        assert np.array_equal(force_a, b.particles._force.peek())
+    assert prefetched >= 4  # from the second step on the download rides under the force evaluation
+
+
 def test_lj_nlist_small_box_is_refused():
     g = load_golden("lj_fcc_256.npz")
     system, pot = _lj_system(g, "lj_fcc_256.npz", method="nlist")

@@ -79,6 +79,17 @@ def pinned_array(shape) -> np.ndarray:
     return t.zeros(int(np.prod(shape)), dtype=t.float64, pin_memory=True).numpy().reshape(shape)
 
 
+_side = None
+
+
+def _side_stream():
+    """One extra stream per process for downloads that overlap kernels (Mirror.prefetch_host)."""
+    global _side
+    if _side is None:
+        _side = torch().cuda.Stream()
+    return _side
+
+
 def to_device(array: np.ndarray, dtype=None):
     """Host array -> new device tensor (flattened, contiguous)."""
     t = torch()
@@ -89,19 +100,23 @@ def to_device(array: np.ndarray, dtype=None):
 class Mirror:
     """One logical float64 array with a host (NumPy) and a device (torch) copy."""
 
-    __slots__ = ("_host", "_dev", "host_valid", "dev_valid")
+    __slots__ = ("_host", "_dev", "host_valid", "dev_valid", "_host_read", "_wants_host", "_prefetch")
 
     def __init__(self, host: np.ndarray):
         self._host = host
         self._dev = None
         self.host_valid = True
         self.dev_valid = False
+        self._host_read = False   # the user has looked at the host array since the last device write
+        self._wants_host = False  # ... and had done so for the value before that one: worth prefetching
+        self._prefetch = None     # event of an asynchronous download in flight
 
     # -- host side ---------------------------------------------------------------------------
     def host(self) -> np.ndarray:
         """The array for the USER: current, and assumed modified after this call."""
         self.refresh_host()
         self.dev_valid = False
+        self._host_read = True
         return self._host
 
     def peek(self) -> np.ndarray:
@@ -109,8 +124,43 @@ class Mirror:
         self.refresh_host()
         return self._host
 
+    def prefetch_host(self) -> None:
+        """Start downloading the device copy on a side stream, behind everything queued so far on the
+        current stream.  Integrators call this right after the kernel that wrote the array when other
+        kernels that only READ it follow (positions: the whole force evaluation), so that a user who reads
+        the array after every step does not wait for the copy afterwards.  Only when that user exists (the
+        previous value was read), and only into a page-locked array of the right shape."""
+        if self.host_valid or not self._wants_host or self._dev is None or self._prefetch is not None:
+            return
+        t = torch()
+        host = self._host
+        if not (host.size == self._dev.numel() and host.dtype == np.float64 and host.flags.writeable
+                and host.flags.c_contiguous):
+            return
+        target = t.from_numpy(host.reshape(-1))
+        if not target.is_pinned():
+            return
+        side = _side_stream()
+        side.wait_stream(t.cuda.current_stream())
+        with t.cuda.stream(side):
+            target.copy_(self._dev, non_blocking=True)
+            self._prefetch = side.record_event()
+
+    def _finish_prefetch(self, on_device: bool) -> None:
+        """Wait for a download in flight: the host (default) or, on_device, the current stream."""
+        if self._prefetch is not None:
+            if on_device:
+                torch().cuda.current_stream().wait_event(self._prefetch)
+            else:
+                self._prefetch.synchronize()
+
     def refresh_host(self) -> None:
         if self.host_valid:
+            return
+        if self._prefetch is not None:  # the download was started when the array was written
+            self._prefetch.synchronize()
+            self._prefetch = None
+            self.host_valid = True
             return
         t = torch()
         host = self._host
@@ -124,13 +174,19 @@ class Mirror:
 
     def set_host(self, array) -> None:
         """Rebind, as ``particles.vel = array`` does in the reference."""
+        self._finish_prefetch(on_device=False)  # it may be writing into the very array that comes back
+        self._prefetch = None
         self._host = np.asarray(array)
         self.host_valid = True
         self.dev_valid = False
 
     # -- device side -------------------------------------------------------------------------
-    def device(self):
-        """Current device tensor (flat float64); uploads when the host copy is newer."""
+    def device(self, read_only: bool = False):
+        """Current device tensor (flat float64); uploads when the host copy is newer.  ``read_only``: the
+        caller's kernels only read it (they may run beside a download in flight); anybody else may be
+        about to overwrite the tensor, so the current stream first waits for that download."""
+        if not read_only:
+            self._finish_prefetch(on_device=True)
         if not self.dev_valid:
             host = np.ascontiguousarray(self._host, dtype=np.float64)
             if self._dev is None or self._dev.numel() != host.size:
@@ -149,6 +205,8 @@ class Mirror:
     def written_on_device(self, shape=None) -> None:
         self.dev_valid = True
         self.host_valid = False
+        self._prefetch = None  # (already waited for in device(): what it fetched is stale now)
+        self._wants_host, self._host_read = self._host_read, False
         if shape is not None and tuple(self._host.shape) != tuple(shape):
             self._host = np.zeros(shape)
 

@@ -107,6 +107,7 @@ class VelocityVerlet(MDIntegrator):
                   _device.dptr(imass), n, dim, dt, stream)
         part._pos.written_on_device()
         part._vel.written_on_device()
+        part._pos.prefetch_host()  # a caller that reads pos after every step gets it under the force evaluation
         system.evaluate(_ALL)
         _lib.call("tmd_vv_kick", _device.dptr(vel), _device.dptr(part._force.device()),
                   _device.dptr(imass), n, dim, dt, stream)
@@ -327,6 +328,7 @@ class LangevinInertia(MDIntegrator):
                   _device.dptr(nvel) if nvel is not None else None, stream)
         part._pos.written_on_device()
         part._vel.written_on_device()
+        part._pos.prefetch_host()
         # force() and, after the velocity update, potential() -- at the same positions
         # (integrators.py:280-282): one traversal when that gives the same numbers
         one_pass = system.energy_rides_with_forces()

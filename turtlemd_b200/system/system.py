@@ -47,7 +47,7 @@ class System:
             return False
         _device.require_cuda()
         size = int(np.prod(particles._pos.shape))
-        pos = particles._pos.device()
+        pos = particles._pos.device(read_only=True)  # potentials never write positions
         force = particles._force.device_uninitialised(size) if flags & _lib.WANT_F else None
         vw = particles._vw_buffer()
         first = True
