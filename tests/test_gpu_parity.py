@@ -1185,6 +1185,50 @@ def test_two_real_ranks_match_single_gpu(kind, graph):
 # ---- observables ------------------------------------------------------------------------
 
 
+def test_degenerate_sizes():
+    """One and two particles, a type nobody has, a potential list that is empty: the reference's answers
+    (zeros, no exception) through the device path and the host-buffer path."""
+    from oracle import turtle_oracle as to
+    from turtlemd_b200.system import Box, Particles, System
+
+    k = _pkg()
+    box = Box(low=[0.0, 0.0, 0.0], high=[6.0, 6.0, 6.0])
+    one = {0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}}
+    length, ilength = to.box_lengths([0, 0, 0], [6, 6, 6], [True] * 3)
+    table, _ = to.lj_tables(one)
+    for pos in (np.array([[1.0, 2.0, 3.0]]), np.array([[1.0, 2.0, 3.0], [1.9, 2.4, 5.8]])):
+        lj = k["LennardJonesCut"](dim=3, shift=True)
+        lj.set_parameters(one)
+        dw = k["DoubleWellPair"](types=(0, 0), dim=3)
+        dw.set_parameters({"rzero": 1.0, "width": 0.25, "height": 6.0})
+        system = System(box, Particles.from_arrays(pos), [lj, dw])
+        v, f, w = system.potential_and_force()
+        tidx = np.zeros(len(pos), dtype=int)
+        v_lj, f_lj, w_lj = to.lj_potential_and_force(pos, tidx, length, ilength, [True] * 3, table)
+        par = to.dwpair_params(1.0, 0.25, 6.0)
+        v_dw = to.dwpair_potential(pos, tidx, length, ilength, [True] * 3, (0, 0), par)
+        f_dw, w_dw = to.dwpair_force(pos, tidx, length, ilength, [True] * 3, (0, 0), par)
+        assert v == pytest.approx(v_lj + v_dw, rel=1e-12, abs=1e-300)
+        assert np.allclose(f, f_lj + f_dw, rtol=1e-12, atol=0) and np.allclose(w, w_lj + w_dw, rtol=1e-12, atol=0)
+        assert np.allclose(lj.force(system)[0], f_lj, rtol=1e-12, atol=0)
+        for integ in (k["integrators"].VelocityVerlet(0.001), k["integrators"].Verlet(0.001)):
+            integ(system)
+        assert np.all(np.isfinite(system.particles.pos))
+    # a pair potential whose types are absent: zeros
+    system = System(box, Particles.from_arrays(np.array([[1.0, 1.0, 1.0], [2.0, 2.0, 2.0]])),
+                    [k["DoubleWellPair"](types=(5, 6), dim=3)])
+    system.potentials[0].set_parameters({"rzero": 1.0, "width": 0.25, "height": 6.0})
+    v, f, w = system.potential_and_force()
+    assert v == 0.0 and not f.any() and not w.any()
+    # one-dimensional replicas, a single one
+    reps = System(Box(periodic=[False]), Particles.from_arrays(np.array([[-1.0]])), [k["DoubleWell"](a=1.0, b=2.0, c=0.0)])
+    reps.potential_and_force()
+    from turtlemd_b200.philox import PhiloxNormal
+
+    k["integrators"].LangevinInertia(timestep=0.002, gamma=0.3, beta=1.0 / 0.07, rgen=PhiloxNormal(3)).run(reps, 7)
+    assert np.isfinite(reps.particles.pos).all() and reps.particles.pos.shape == (1, 1)
+
+
 def test_thermo_uses_the_device_reduction_and_matches_the_host_formula():
     """System.thermo() after device-resident steps: kinetic tensor reduced on the GPU (velocities are
     not downloaded), same numbers as the reference's NumPy expressions (system.py:101-130)."""
