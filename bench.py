@@ -203,7 +203,7 @@ def bench_lj(args, cfg, rank, world):
         integ = VelocityVerlet(cfg["dt"])
         describe += f", VelocityVerlet dt={cfg['dt']}"
     graphed, parallelism, stepper = False, "single GPU", None
-    if world > 1 or os.environ.get("TMD_BENCH_DECOMP") == "slab1":
+    if world > 1 or os.environ.get("TMD_BENCH_DECOMP") in ("slab1", "atoms1"):
         from turtlemd_b200.parallel import AtomDecomposition, SlabDecomposition
 
         if os.environ.get("TMD_BENCH_DECOMP", "atoms") in ("slab", "slab1") and cfg["method"] == "nlist" and not cfg.get("dimer"):
