@@ -198,7 +198,7 @@ def bench_lj(args, cfg, rank, world):
         from turtlemd_b200.philox import PhiloxNormal
 
         integ = LangevinInertia(timestep=cfg["dt"], gamma=0.3, beta=1.0 / 0.8, rgen=PhiloxNormal(key=0))
-        describe += ", LangevinInertia gamma=0.3 T=0.8 (force() + potential() per step as in the reference)"
+        describe += ", LangevinInertia gamma=0.3 T=0.8"
     else:
         integ = VelocityVerlet(cfg["dt"])
         describe += f", VelocityVerlet dt={cfg['dt']}"
@@ -232,11 +232,11 @@ def bench_lj(args, cfg, rank, world):
         step()
     launches0 = _lib.launch_count()
     with ClockSampler(torch.cuda.current_device()) as clocks:
-        if stepper is None and isinstance(integ, VelocityVerlet):
-            # the multi-step entry point of the integrator: the closing half kick of a step and the opening
-            # half kick + drift of the next one are a single pass over the state (same roundings, same trajectory)
+        if stepper is None:
+            # the multi-step entry point of the integrator: the closing velocity update of a step and the opening
+            # update of the next one are a single pass over the state (same roundings, same trajectory)
             sec = timed(lambda: integ.run(system, args.steps), 1, world)
-            parallelism += f", VelocityVerlet.run(system, {args.steps})"
+            parallelism += f", {type(integ).__name__}.run(system, {args.steps})"
         else:
             sec = timed(step, args.steps, world)
     launches = _lib.launch_count() - launches0

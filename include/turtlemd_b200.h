@@ -274,6 +274,11 @@ int tmd_langevin_inertia_pre(double *pos, double *vel, const double *force, cons
                              const tmd_rng *rng, int64_t first,
                              const double *noise_pos, const double *noise_vel,
                              tmd_stream_t stream);
+/* part 2 of one step and part 1 of the next in one pass over the state (both use the same F): what
+ * LangevinInertia.run() issues between two force evaluations; in-kernel stream only.              */
+int tmd_langevin_inertia_post_pre(double *pos, double *vel, const double *force, const double *imass,
+                                  int64_t n, int32_t dim, const tmd_langevin_consts *consts,
+                                  const tmd_rng *rng, int64_t first, tmd_stream_t stream);
 /* ... part 2 (after force()): v = v' + b2_i * F                                                  */
 int tmd_langevin_inertia_post(double *vel, const double *force, const double *imass,
                               int64_t n, int32_t dim, const tmd_langevin_consts *consts,

@@ -429,6 +429,37 @@ def test_langevin_fused_multi_step_equals_single_steps():
         assert np.array_equal(shard.particles.pos, full_pos[sl])
 
 
+@pytest.mark.parametrize("method", ["allpairs", "nlist"])
+def test_langevin_multi_step_run_on_a_pair_force_field_is_bit_identical(method):
+    """LangevinInertia.run(system, k) on a Lennard-Jones system (one fused pass between force evaluations,
+    potential() once at the end) leaves exactly the state of k integration_step calls."""
+    from turtlemd_b200.philox import PhiloxNormal
+    from turtlemd_b200.system import Box, Particles, System
+
+    k = _pkg()
+    g = load_golden("lj_fcc_4000.npz" if method == "nlist" else "lj_fcc_108.npz")
+    vel0 = 0.3 * np.random.default_rng(8).standard_normal(g["pos"].shape)
+
+    def make():
+        pot = k["LennardJonesCut"](dim=3, shift=True, method=method)
+        pot.set_parameters({0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}})
+        system = System(Box(low=g["low"], high=g["high"]), Particles.from_arrays(g["pos"], vel=vel0), [pot])
+        system.potential_and_force()
+        integ = k["integrators"].LangevinInertia(timestep=0.002, gamma=0.3, beta=1.25, rgen=PhiloxNormal(key=21))
+        return system, integ
+
+    a, integ_a = make()
+    b, integ_b = make()
+    integ_a.run(a, 6)
+    for _ in range(6):
+        integ_b(b)
+    assert integ_a.rgen.position == integ_b.rgen.position
+    for name in ("pos", "vel", "force"):
+        assert np.array_equal(getattr(a.particles, name), getattr(b.particles, name)), name
+    assert a.particles.v_pot == b.particles.v_pot
+    assert np.array_equal(a.particles.virial, b.particles.virial)
+
+
 def test_langevin_inertia_lj_trajectory():
     k = _pkg()
     from turtlemd_b200.philox import PhiloxNormal

@@ -125,6 +125,7 @@ PROTOTYPES = {
     "tmd_langevin_overdamped": [_P, _P, _P, _P, _I64, _I32, _D, _D, _D, _RNG, _I64, _P, _P],
     "tmd_langevin_inertia_constants": [_D, _D, _D, _LC],
     "tmd_langevin_inertia_pre": [_P, _P, _P, _P, _I64, _I32, _LC, _RNG, _I64, _P, _P, _P],
+    "tmd_langevin_inertia_post_pre": [_P, _P, _P, _P, _I64, _I32, _LC, _RNG, _I64, _P],
     "tmd_langevin_inertia_post": [_P, _P, _P, _I64, _I32, _LC, _P],
     "tmd_langevin_inertia_doublewell": [_P, _P, _P, _P, _I64, _I32, _D, _D, _D, _LC, _RNG, _I64, _I64, _I32, _P, _P],
     "tmd_philox_normal_fill": [_P, _I64, _RNG, _P],

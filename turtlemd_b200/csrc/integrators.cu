@@ -175,7 +175,9 @@ __global__ void __launch_bounds__(256) overdamped_kernel(double *__restrict__ po
 }
 
 // ---- Langevin with inertia ----------------------------------------------------------------------
-template <int DIM, bool VEC, bool HOSTNOISE>
+// POST: the closing velocity update of the previous step, v = v' + b2 F (integrators.py:281), is applied
+// first -- the same F as this step's opening update uses -- so a run of steps needs one pass per step.
+template <int DIM, bool VEC, bool HOSTNOISE, bool POST = false>
 __global__ void __launch_bounds__(256) inertia_pre_kernel(double *__restrict__ pos, double *__restrict__ vel,
                                                           const double *__restrict__ force,
                                                           const double *__restrict__ imass, int64_t total,
@@ -187,6 +189,10 @@ __global__ void __launch_bounds__(256) inertia_pre_kernel(double *__restrict__ p
     const D2 im = ld_imass<DIM>(imass, e, two);
     D2 x = ld2<VEC>(pos, e, two);
     D2 v = ld2<VEC>(vel, e, two);
+    if (POST) {  // exactly inertia_post_kernel's arithmetic
+        v.a = __dadd_rn(v.a, __dmul_rn(__dmul_rn(c.b2f, im.a), f.a));
+        v.b = __dadd_rn(v.b, __dmul_rn(__dmul_rn(c.b2f, im.b), f.b));
+    }
     const InertiaPerParticle pa = inertia_constants(c, im.a);
     const InertiaPerParticle pb = (im.b == im.a) ? pa : inertia_constants(c, im.b);
     D2 xr, vr;
@@ -506,6 +512,28 @@ int tmd_langevin_inertia_pre(double *pos, double *vel, const double *force, cons
     if (dim == 1) TMD_IP_D(1); else if (dim == 2) TMD_IP_D(2); else TMD_IP_D(3);
 #undef TMD_IP_D
 #undef TMD_IP
+    TMD_CUDA(cudaGetLastError());
+    return TMD_OK;
+}
+
+int tmd_langevin_inertia_post_pre(double *pos, double *vel, const double *force, const double *imass, int64_t n,
+                                  int32_t dim, const tmd_langevin_consts *consts, const tmd_rng *rng, int64_t first,
+                                  tmd_stream_t stream) {
+    TMD_REQUIRE(dim >= 1 && dim <= 3 && n >= 0 && first >= 0, "dim must be 1..3, n >= 0, first >= 0");
+    TMD_REQUIRE(consts != nullptr && rng != nullptr, "consts and rng are required");
+    TMD_CHECK(require_device());
+    const int64_t total = n * dim;
+    if (total == 0) return TMD_OK;
+    const bool vec = aligned16(pos) && aligned16(vel) && aligned16(force);
+    const Launch l = ew_launch(total);
+    const uint64_t q_base = rng->offset + 2ull * (uint64_t)first * (uint64_t)dim;
+    cudaStream_t s = as_stream(stream);
+#define TMD_IPP(D, V) \
+    ::tmd::count_launch(), inertia_pre_kernel<D, V, false, true><<<l.blocks, l.threads, 0, s>>>(pos, vel, force, imass, total, *consts, rng->key, q_base, nullptr, nullptr)
+    if (dim == 1) { if (vec) TMD_IPP(1, true); else TMD_IPP(1, false); }
+    else if (dim == 2) { if (vec) TMD_IPP(2, true); else TMD_IPP(2, false); }
+    else { if (vec) TMD_IPP(3, true); else TMD_IPP(3, false); }
+#undef TMD_IPP
     TMD_CUDA(cudaGetLastError());
     return TMD_OK;
 }

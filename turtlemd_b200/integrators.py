@@ -348,6 +348,8 @@ class LangevinInertia(MDIntegrator):
         """
         self.initiate_parameters(system)
         if not self._fusable(system):
+            if steps > 1 and _is_device_stream(self.rgen) and first == 0 and n_global is None:
+                return self._run_general(system, steps)
             for _ in range(steps):
                 self.integration_step(system)
             return
@@ -365,6 +367,43 @@ class LangevinInertia(MDIntegrator):
         part._force.written_on_device()
         part.virial = np.zeros((dim, dim))  # DoubleWell.force returns a zero virial (well.py:80-81)
         part._vw_fresh.add("v_pot")
+
+
+def _langevin_run_general(self, system, steps: int):
+    """``steps`` steps of any device force field without touching the host in between: the closing velocity
+    update of a step and the opening update of the next are one pass (``tmd_langevin_inertia_post_pre``, same
+    roundings), and ``potential()`` -- which the reference evaluates after every step (integrators.py:282) but
+    whose value only the last step leaves behind -- is evaluated once, at the end.  Same trajectory, same
+    final ``v_pot`` / ``virial`` as ``steps`` single calls."""
+    part, n, dim, pos, vel, force, imass = _arrays(system)
+    stream = _device.stream_ptr()
+    one_pass = system.energy_rides_with_forces()
+
+    def rng_now():
+        rng = _lib.Rng(self.rgen.key, self.rgen.position)
+        self.rgen.advance(2 * n * dim)
+        return rng
+
+    _lib.call("tmd_langevin_inertia_pre", _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
+              _device.dptr(imass), n, dim, C.byref(self._consts), C.byref(rng_now()), 0, None, None, stream)
+    part._pos.written_on_device()
+    part._vel.written_on_device()
+    for _ in range(steps - 1):
+        system.evaluate(_lib.WANT_F | _lib.WANT_W)
+        _lib.call("tmd_langevin_inertia_post_pre", _device.dptr(pos), _device.dptr(vel),
+                  _device.dptr(part._force.device()), _device.dptr(imass), n, dim, C.byref(self._consts),
+                  C.byref(rng_now()), 0, stream)
+        part._pos.written_on_device()
+        part._vel.written_on_device()
+    system.evaluate(_lib.WANT_F | _lib.WANT_W | (_lib.WANT_V if one_pass else 0))
+    _lib.call("tmd_langevin_inertia_post", _device.dptr(vel), _device.dptr(part._force.device()),
+              _device.dptr(imass), n, dim, C.byref(self._consts), stream)
+    part._vel.written_on_device()
+    if not one_pass:
+        system.evaluate(_lib.WANT_V | _lib.V_STANDALONE)
+
+
+LangevinInertia._run_general = _langevin_run_general
 
 
 def multivariate_normal(rgen: Generator, mean: np.ndarray, cho: np.ndarray, dim: int) -> np.ndarray:
