@@ -460,6 +460,33 @@ def test_langevin_multi_step_run_on_a_pair_force_field_is_bit_identical(method):
     assert np.array_equal(a.particles.virial, b.particles.virial)
 
 
+def test_overdamped_multi_step_run_is_bit_identical():
+    """LangevinOverdamped.run(system, k): the intermediate potential() evaluations nobody can observe are
+    skipped; the state after k steps is that of k integration_step calls."""
+    from turtlemd_b200.philox import PhiloxNormal
+    from turtlemd_b200.system import Box, Particles, System
+
+    k = _pkg()
+    g = load_golden("lj_fcc_4000.npz")
+
+    def make():
+        pot = k["LennardJonesCut"](dim=3, shift=True, method="nlist")
+        pot.set_parameters({0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}})
+        system = System(Box(low=g["low"], high=g["high"]), Particles.from_arrays(g["pos"]), [pot])
+        system.potential_and_force()
+        return system, k["integrators"].LangevinOverdamped(timestep=1e-4, gamma=0.5, rgen=PhiloxNormal(key=9), beta=1.25)
+
+    a, integ_a = make()
+    b, integ_b = make()
+    integ_a.run(a, 5)
+    for _ in range(5):
+        integ_b(b)
+    for name in ("pos", "vel", "force"):
+        assert np.array_equal(getattr(a.particles, name), getattr(b.particles, name)), name
+    assert a.particles.v_pot == b.particles.v_pot and np.array_equal(a.particles.virial, b.particles.virial)
+    assert a.potentials[0].nlist_stats()["calls"] == 1 + 5 + 1 and b.potentials[0].nlist_stats()["calls"] == 1 + 10
+
+
 def test_langevin_inertia_lj_trajectory():
     k = _pkg()
     from turtlemd_b200.philox import PhiloxNormal
