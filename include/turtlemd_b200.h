@@ -160,6 +160,26 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
                  int64_t first, int64_t count,
                  double *force, double *vw, tmd_stream_t stream);
 
+/* Fused force + kick + drift: `steps` VelocityVerlet steps (integrators.py:84-94, the loop of
+ * simulation/mdsimulation.py:69-90) over a LennardJonesCut force field in ONE call, resident on the
+ * device.  pos / vel / force / imass are the device arrays of the reference's particles (atom order,
+ * (n, dim) row-major; force = the forces at pos, as VelocityVerlet expects to find them).  The state is
+ * moved into the list's cell order once; each step is then one list traversal whose epilogue applies the
+ * closing half kick of the step and the opening half kick + drift of the next to the row atom, writes the
+ * record the next traversal gathers and does the Verlet-list displacement test; rebuilds are decided on
+ * the device (gated launches, no host read).  On return pos, vel, force and vw = (V, W) hold the state
+ * after `steps` steps.  Roundings, list builds and summation order are those of
+ * tmd_vv_kick_drift + tmd_lj_nlist + tmd_vv_kick on the same handle: the trajectory is bit-identical. */
+int tmd_nlist_run_vv(tmd_nlist *nl, double *pos, double *vel, double *force, const double *imass,
+                     const int32_t *tidx, int64_t n, const tmd_box *box, const double *table, int32_t ntypes,
+                     double dt, int32_t steps, double *vw, tmd_stream_t stream);
+
+/* Measurement hook for bench.py's roofline: while on, tmd_nlist_run_vv brackets every traversal launch with
+ * CUDA events on its stream, waits for the run at the end (so: never inside a timed region) and accumulates
+ * the kernel time; tmd_nlist_timing returns the sum in milliseconds and the number of launches in it. */
+int tmd_nlist_set_timing(tmd_nlist *nl, int32_t on);
+int tmd_nlist_timing(tmd_nlist *nl, double *traversal_ms, int64_t *traversals);
+
 /* Slab path (multi-GPU; also the sorted single-GPU run).  The rows of a rank are the
  * cell-order SLOTS [slot_first, slot_first+slot_count) of the list's own ordering -- a spatially
  * compact slab -- and the rank's state lives in slot order: `records` (n x 4 doubles: x, y, z with

@@ -108,6 +108,9 @@ PROTOTYPES = {
     "tmd_lj_nlist_usable": [_I64, _BOX, _P, _I32, _D, C.POINTER(C.c_int)],
     "tmd_nlist_stats": [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I32)],
     "tmd_lj_nlist": [_P, _P, _P, _I64, _BOX, _P, _I32, _U32, _I64, _I64, _P, _P, _P],
+    "tmd_nlist_run_vv": [_P, _P, _P, _P, _P, _P, _I64, _BOX, _P, _I32, _D, _I32, _P, _P],
+    "tmd_nlist_set_timing": [_P, _I32],
+    "tmd_nlist_timing": [_P, C.POINTER(_D), C.POINTER(_I64)],
     "tmd_nlist_bind_records": [_P, _P],
     "tmd_nlist_build_slots": [_P, _P, _P, _I64, _BOX, _P, _I32, _I64, _I64, _I32, _P],
     "tmd_nlist_force_slots": [_P, _U32, _P, _P, _P],

@@ -34,8 +34,10 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "lj_common.cuh"
+#include "integrator_math.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -44,6 +46,7 @@ namespace tmd {
 constexpr int kNlThreads = 128;
 constexpr unsigned kSlotMask = 0x07FFFFFFu;
 constexpr int kHomeCode = 13;  // (0,0,0) shift
+constexpr int kNlFlagWords = 16;  // nlflags[]: see NlArgs; [8], [9] = the two gate words of a resident run
 constexpr int kNeverHi = 0x7FF80BAD;  // high word of a NaN payload no arithmetic produces (see nl_force_kernel)
 constexpr int kBinThreads = 256;           // cooperative binning kernel
 constexpr int kScanChunk = kBinThreads * 8;
@@ -90,6 +93,19 @@ struct NlArgs {
     double *force;
     double *partial_vw;
     double *vw;          // (V, W) of the call, written by the traversal block that finishes last
+    const int *gate;     // the build kernels return at once unless *gate != 0 (nlflags[0], or a resident run's flag word)
+    // ---- resident run (tmd_nlist_run_vv): slot-ordered state advanced by the traversal's epilogue ----
+    double *xu;          // [n*dim] by slot: unwrapped positions (the reference's particles.pos, never wrapped)
+    double *vs;          // [n*dim] by slot: velocities
+    double *fs;          // [n*dim] by slot: forces of the last evaluation
+    const double *fx;    // [n*dim] by slot or NULL: forces of the other potentials of the system, added to fs
+    const double *imass_s;  // [n] by slot
+    const double *image_s;  // [n*3] by slot: lattice vector removed at build time (image[] in slot order)
+    double4 *xs_next;    // [n] by slot: records of the NEXT step (double buffer; xs is read by every block)
+    int *flag_next;      // set when an atom has moved more than skin/2: gates the build of the next step
+    int *flag_clear;     // the word that gated this step's build: cleared for its next use
+    double dt, half_dt;
+    int epi_last;        // 1: last step of the run, closing half kick only
     LjTable tab;
 };
 
@@ -119,6 +135,14 @@ struct tmd_nlist {
     int row_mode;         // signature: 0 = atom rows, 1 = slot rows
     double4 *xs_ext;      // caller-owned current-position records used instead of xs (exchange buffer)
     tmd::NlArgs *saved;   // launch arguments of the last slot build, reused by the traversal
+    // resident runs (tmd_nlist_run_vv): slot-ordered state, owned
+    double4 *xs2;         // second record buffer (the epilogue of a step writes the records of the next)
+    double *md;           // xu, vs, fs, fx, image_s (3 doubles per slot each), imass_s (1)
+    int64_t cap_md;
+    // measurement (tmd_nlist_set_timing): CUDA events around every traversal launch of a resident run
+    int timing;
+    double traversal_ms;
+    int64_t traversals;
 };
 
 namespace tmd {
@@ -225,7 +249,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp, int &tot
 // Binning (phases 1-4 of a rebuild) in one cooperative launch; gated on the rebuild flag.
 template <int DIM>
 __global__ void __launch_bounds__(kBinThreads) nl_bin_kernel(const NlArgs a) {
-    if (a.nlflags[0] == 0) return;  // same answer in every block: nobody writes the flag while this kernel runs
+    if (*a.gate == 0) return;  // same answer in every block: nobody writes the flag while this kernel runs
     cg::grid_group grid = cg::this_grid();
     __shared__ int s_warp[kBinThreads / 32];
     const NlGrid &g = a.grid;
@@ -351,7 +375,7 @@ __device__ __forceinline__ int block_position(int q) { return (q & 3) * 4 + (q >
 
 template <int DIM>
 __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
-    if (a.nlflags[0] == 0) return;
+    if (*a.gate == 0) return;
     __shared__ unsigned s_ring[kRing][kNlThreads];
     const NlGrid &g = a.grid;
     const int tid = threadIdx.x;
@@ -479,7 +503,14 @@ __device__ __forceinline__ double group_sum(double v) {
 // persistent (grid-stride over groups of kNlThreads/G rows): the energy / virial partials stay in
 // registers for the whole kernel and are reduced once.  SINGLE: one particle type (coefficients in
 // registers, the shift `offset` applied once per lane from its hit count).
-template <int DIM, bool SINGLE, int G, bool WV, bool WF, int MINB>
+//
+// EPI = 1 (resident run, tmd_nlist_run_vv): rows are cell-order slots and the state lives in slot order.
+// When a row's force is complete, lanes 0 .. DIM-1 of its group each take one coordinate of the
+// VelocityVerlet update (integrators.py:84-94): the closing half kick of this step and -- unless this is
+// the last step of the run -- the opening half kick and the drift of the next one, the new 32-byte
+// record for the next traversal (double buffer) and the Verlet-list displacement test.  Same roundings,
+// in the same order, as tmd_vv_kick_kick_drift + nl_gather_check_kernel: bit-identical trajectories.
+template <int DIM, bool SINGLE, int G, bool WV, bool WF, int MINB, int EPI = 0>
 __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs a) {
     static_assert(G * 4 == kBlockEntries, "the block layout of the lists is for four lanes per row atom");
     __shared__ double s_tab[SINGLE ? 1 : 6 * kMaxT2];
@@ -493,15 +524,16 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
 #pragma unroll
     for (int w = 0; w < 6; ++w) s_w[w][tid] = 0.0;
     const int l = tid % G, grp = tid / G;
-    const bool whole = a.first == 0 && a.count == a.n;
+    const bool whole = EPI ? false : (a.first == 0 && a.count == a.n);
     const int ntypes = a.ntypes;
     if (!SINGLE) {
         for (int k = tid; k < 6 * kMaxT2; k += kNlThreads) s_tab[k] = a.tab.c[k / kMaxT2][k % kMaxT2];
         __syncthreads();
     }
     if (blockIdx.x == 0 && tid == 0) {  // the gated build of this call is behind us in the stream
-        if (a.nlflags[0]) {
-            a.nlflags[0] = 0;
+        int *gate_word = EPI ? a.flag_clear : a.nlflags;  // (EPI: this step's epilogues raise a.flag_next, another word)
+        if (*gate_word) {
+            *gate_word = 0;
             a.nlflags[2] += 1;
         }
         a.nlflags[3] += 1;
@@ -527,7 +559,7 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
         Row r;
         const int64_t row = base + grp;
         r.valid = row < a.count;
-        r.slot = !r.valid ? 0 : (whole ? (int)row : (a.row_mode ? (int)(a.first + row) : a.slot_of[a.first + row]));
+        r.slot = !r.valid ? 0 : (whole ? (int)row : ((EPI || a.row_mode) ? (int)(a.first + row) : a.slot_of[a.first + row]));
         r.me = a.xs[r.slot];
         r.nn = r.valid ? a.nneigh[row] : 0;
         // first entries of the row, whatever its length (cap >= 16: in bounds; unused words are never dereferenced)
@@ -654,7 +686,7 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
         } else {
             // list capacity exceeded at build time: walk the build-time cells (every pair now inside
             // rcut was inside rcut + skin then, hence in this stencil)
-            const int cell = a.cell_of[(whole || a.row_mode) ? a.order[slot] : (int)(a.first + row)];
+            const int cell = a.cell_of[(whole || a.row_mode || EPI) ? a.order[slot] : (int)(a.first + row)];
             const int c0 = cell % a.grid.nc[0], c1 = (cell / a.grid.nc[0]) % a.grid.nc[1],
                       c2 = cell / (a.grid.nc[0] * a.grid.nc[1]);
             for_each_run<DIM>(a.grid, a.starts, c0, c1, c2, [&](int jbegin, int jend, int code) {
@@ -667,8 +699,46 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
         double f[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int k = 0; k < DIM; ++k) f[k] = group_sum<G>(facc[k]);
+        if (EPI) {
+            static_assert(!EPI || G >= 3, "one lane per coordinate");
+            // lane l < DIM owns coordinate l of this row
+            const bool mine = valid && l < DIM;
+            const int64_t e = (int64_t)slot * DIM + (l < DIM ? l : 0);
+            const double fl = l == 0 ? f[0] : (l == 1 ? f[1] : f[2]);
+            double fk = fl, v = 0.0, x = 0.0, im = 0.0, shift = 0.0;
+            if (mine) {
+                if (a.fx) fk = a.fx[e] + fl;  // the system's other potentials were evaluated into fx before this launch
+                v = a.vs[e];
+                im = a.imass_s[slot];
+                a.fs[e] = fk;
+                v = kick(v, fk, im, a.half_dt);  // integrators.py:94 of this step
+                if (!a.epi_last) {
+                    x = a.xu[e];
+                    shift = a.image_s[(int64_t)slot * 3 + l];
+                    v = kick(v, fk, im, a.half_dt);          // :88 of the next step
+                    x = __dadd_rn(x, __dmul_rn(a.dt, v));    // :90
+                    a.xu[e] = x;
+                }
+                a.vs[e] = v;
+            }
+            if (!a.epi_last) {  // block-uniform
+                const double rec = __dsub_rn(x, shift);  // what nl_gather_check_kernel forms: pos - image
+                const int base = (tid & 31) & ~(G - 1);
+                const double ry = __shfl_sync(0xffffffffu, rec, base + (DIM > 1 ? 1 : 0));
+                const double rz = __shfl_sync(0xffffffffu, rec, base + (DIM > 2 ? 2 : 0));
+                if (l == 0 && valid) {
+                    const double4 b = a.xb[slot];
+                    const double4 nr = make_double4(rec, DIM > 1 ? ry : 0.0, DIM > 2 ? rz : 0.0, me.w);
+                    a.xs_next[slot] = nr;
+                    double r = (nr.x - b.x) * (nr.x - b.x);
+                    if (DIM > 1) r = fma(nr.y - b.y, nr.y - b.y, r);
+                    if (DIM > 2) r = fma(nr.z - b.z, nr.z - b.z, r);
+                    if (!(r <= a.half_skin2)) *a.flag_next = 1;  // also catches NaN
+                }
+            }
+        }
         if (l == 0 && valid) {
-            if (flags & TMD_WANT_F) {
+            if (!EPI && (flags & TMD_WANT_F)) {
                 const int atom = a.row_mode ? slot : (whole ? a.order[slot] : (int)(a.first + row));
                 double *dst = a.force + (int64_t)atom * DIM;
 #pragma unroll
@@ -731,6 +801,87 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
     }
 }
 
+// ---- resident runs: atom order <-> slot order ---------------------------------------------------------
+// gate == NULL: always; otherwise only when *gate != 0 (the rebuild of a step, decided on the device)
+template <int DIM>
+__global__ void __launch_bounds__(256) md_import_kernel(const int *__restrict__ order, int64_t n,
+                                                        const double *__restrict__ pos, const double *__restrict__ vel,
+                                                        const double *__restrict__ force,
+                                                        const double *__restrict__ imass,
+                                                        const double *__restrict__ image, double *__restrict__ xu,
+                                                        double *__restrict__ vs, double *__restrict__ fs,
+                                                        double *__restrict__ imass_s, double *__restrict__ image_s,
+                                                        const int *gate) {
+    if (gate && *gate == 0) return;
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    const int64_t atom = order[slot];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        xu[slot * DIM + k] = pos[atom * DIM + k];
+        vs[slot * DIM + k] = vel[atom * DIM + k];
+        if (force) fs[slot * DIM + k] = force[atom * DIM + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) image_s[slot * 3 + k] = image[atom * 3 + k];
+    imass_s[slot] = imass[atom];
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) md_export_kernel(const int *__restrict__ order, int64_t n,
+                                                        const double *__restrict__ xu, const double *__restrict__ vs,
+                                                        const double *__restrict__ fs, double *__restrict__ pos,
+                                                        double *__restrict__ vel, double *__restrict__ force,
+                                                        const int *gate) {
+    if (gate && *gate == 0) return;
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    const int64_t atom = order[slot];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        pos[atom * DIM + k] = xu[slot * DIM + k];
+        vel[atom * DIM + k] = vs[slot * DIM + k];
+        if (force) force[atom * DIM + k] = fs[slot * DIM + k];
+    }
+}
+
+// opening half kick + drift of the first step of a run (integrators.py:88-90) on slot-ordered state, the
+// records the first traversal reads and the displacement test against the build positions
+template <int DIM>
+__global__ void __launch_bounds__(256) md_pre_kernel(int64_t n, double *__restrict__ xu, double *__restrict__ vs,
+                                                     const double *__restrict__ fs,
+                                                     const double *__restrict__ imass_s,
+                                                     const double *__restrict__ image_s,
+                                                     const double4 *__restrict__ xb, double4 *__restrict__ xs,
+                                                     double dt, double half, double half_skin2, int *flag) {
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    const double im = imass_s[slot];
+    const double4 b = xb[slot];
+    double rec[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        const double v = kick(vs[slot * DIM + k], fs[slot * DIM + k], im, half);
+        const double x = __dadd_rn(xu[slot * DIM + k], __dmul_rn(dt, v));
+        vs[slot * DIM + k] = v;
+        xu[slot * DIM + k] = x;
+        rec[k] = __dsub_rn(x, image_s[slot * 3 + k]);
+    }
+    xs[slot] = make_double4(rec[0], rec[1], rec[2], b.w);
+    double r = (rec[0] - b.x) * (rec[0] - b.x);
+    if (DIM > 1) r = fma(rec[1] - b.y, rec[1] - b.y, r);
+    if (DIM > 2) r = fma(rec[2] - b.z, rec[2] - b.z, r);
+    if (!(r <= half_skin2)) *flag = 1;
+}
+
+// after an ungated build outside a traversal: what the traversal's block 0 does with the rebuild flag
+__global__ void md_built_kernel(int *nlflags) {
+    if (nlflags[0]) {
+        nlflags[0] = 0;
+        nlflags[2] += 1;
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 
 static void nl_release(tmd_nlist *nl) {
@@ -745,6 +896,11 @@ static void nl_release(tmd_nlist *nl) {
     cudaFree(nl->xbf);
     cudaFree(nl->xs);
     cudaFree(nl->image);
+    cudaFree(nl->xs2);
+    cudaFree(nl->md);
+    nl->xs2 = nullptr;
+    nl->md = nullptr;
+    nl->cap_md = 0;
     nl->xs = nullptr;
     nl->flags = nullptr;
     nl->entries = nullptr;
@@ -831,6 +987,14 @@ static void nl_launch_force_m(const NlArgs &a, int blocks, cudaStream_t s) {
 #undef TMD_NL_LAUNCH
 }
 
+// resident run: V, F and W every step (what VelocityVerlet's potential_and_force call computes)
+template <int DIM>
+static void nl_launch_force_epi(const NlArgs &a, int blocks, cudaStream_t s) {
+    ::tmd::count_launch();
+    if (a.ntypes == 1 || a.uniform_table) nl_force_kernel<DIM, true, 4, true, true, 5, 1><<<blocks, kNlThreads, 0, s>>>(a);
+    else nl_force_kernel<DIM, false, 4, true, true, 5, 1><<<blocks, kNlThreads, 0, s>>>(a);
+}
+
 template <int DIM>
 static void nl_launch_force(const NlArgs &a, int blocks, cudaStream_t s) {
     if (DIM == 3) {  // the occupancy variants exist for the 3-D kernel only
@@ -901,6 +1065,21 @@ int tmd_nlist_destroy(tmd_nlist *nl) {
     return TMD_OK;
 }
 
+int tmd_nlist_set_timing(tmd_nlist *nl, int32_t on) {
+    TMD_REQUIRE(nl != nullptr, "nl is NULL");
+    nl->timing = on ? 1 : 0;
+    nl->traversal_ms = 0.0;
+    nl->traversals = 0;
+    return TMD_OK;
+}
+
+int tmd_nlist_timing(tmd_nlist *nl, double *traversal_ms, int64_t *traversals) {
+    TMD_REQUIRE(nl != nullptr && traversal_ms && traversals, "NULL argument");
+    *traversal_ms = nl->traversal_ms;
+    *traversals = nl->traversals;
+    return TMD_OK;
+}
+
 int tmd_nlist_stats(tmd_nlist *nl, int64_t *builds, int64_t *calls, int32_t *overflow) {
     TMD_REQUIRE(nl != nullptr, "nl is NULL");
     int host[4] = {0, 0, 0, 0};
@@ -966,8 +1145,8 @@ static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double
         nl->cap_cells = ncells;
         const size_t n_chunks = ((size_t)ncells + kScanChunk - 1) / kScanChunk;
         const size_t n_ints = (size_t)2 * (ncells + 1) + n_chunks + (size_t)5 * n;
-        TMD_CUDA(cudaMalloc(&nl->flags, 8 * sizeof(int)));
-        TMD_CUDA(cudaMemsetAsync(nl->flags, 0, 8 * sizeof(int), s));
+        TMD_CUDA(cudaMalloc(&nl->flags, kNlFlagWords * sizeof(int)));
+        TMD_CUDA(cudaMemsetAsync(nl->flags, 0, kNlFlagWords * sizeof(int), s));
         TMD_CUDA(cudaMalloc(&nl->entries, (size_t)nl->cap * count * sizeof(unsigned)));
         TMD_CUDA(cudaMalloc(&nl->nneigh, (size_t)count * sizeof(int)));
         TMD_CUDA(cudaMalloc(&nl->ints, n_ints * sizeof(int)));
@@ -1008,6 +1187,13 @@ static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double
     a.force = nullptr;
     a.partial_vw = nullptr;
     a.nlflags = nl->flags;
+    a.gate = nl->flags;
+    a.xu = a.vs = a.fs = nullptr;
+    a.fx = a.imass_s = a.image_s = nullptr;
+    a.xs_next = nullptr;
+    a.flag_next = a.flag_clear = nullptr;
+    a.dt = a.half_dt = 0.0;
+    a.epi_last = 0;
     {
         const size_t cells1 = (size_t)nl->cap_cells + 1;
         const size_t chunks = ((size_t)nl->cap_cells + kScanChunk - 1) / kScanChunk;
@@ -1088,6 +1274,126 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
     else TMD_CHECK(nl_launch_build<3>(nl, a, s));
     // ---- traversal ----
     return nl_traverse(a, dim, flags, force, vw, s);
+}
+
+// ---- resident VelocityVerlet run -------------------------------------------------------------------
+// K steps of VelocityVerlet (integrators.py:84-94) over a LennardJonesCut force field without leaving the
+// device and without a host decision: the state is moved into cell order once, every step is [gated
+// rebuild] + ONE traversal whose epilogue integrates (nl_force_kernel<EPI = 1>), and the state is moved
+// back at the end.  The lists, their build positions and the rebuild rule are those of tmd_lj_nlist on the
+// same handle, so the trajectory is bit-identical to K x (tmd_vv_kick_drift, tmd_lj_nlist, tmd_vv_kick).
+}  // extern "C"
+
+template <int DIM>
+static int md_run_vv(tmd_nlist *nl, NlArgs &a, bool same, double *pos, double *vel, double *force,
+                     const double *imass, int64_t n, int steps, cudaStream_t s) {
+    double4 *rec[2] = {nl->xs, nl->xs2};
+    int *gates = nl->flags + 8;
+    const int nb = (int)((n + 255) / 256);
+    const int fblocks = nl_force_blocks(n, DIM);
+    TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)fblocks * 10 * sizeof(double), (void **)&a.partial_vw));
+    double *xu = a.xu, *vs = a.vs, *fs = a.fs;
+    double *imass_s = const_cast<double *>(a.imass_s), *image_s = const_cast<double *>(a.image_s);
+
+    if (!same) {  // no lists for this system yet (nl_prepare raised nlflags[0]): build them from pos as it is
+        a.gate = nl->flags;
+        a.xs = rec[0];
+        TMD_CHECK(nl_launch_build<DIM>(nl, a, s));
+        ::tmd::count_launch(), md_built_kernel<<<1, 1, 0, s>>>(nl->flags);
+    }
+    TMD_CUDA(cudaMemsetAsync(gates, 0, 2 * sizeof(int), s));
+    ::tmd::count_launch(), md_import_kernel<DIM><<<nb, 256, 0, s>>>(a.order, n, pos, vel, force, imass, a.image, xu, vs, fs,
+                                                                   imass_s, image_s, nullptr);
+    int p = 0;
+    ::tmd::count_launch(), md_pre_kernel<DIM><<<nb, 256, 0, s>>>(n, xu, vs, fs, imass_s, image_s, a.xb, rec[p], a.dt,
+                                                                a.half_dt, a.half_skin2, gates + 0);
+    std::vector<cudaEvent_t> events;
+    if (nl->timing) {
+        events.resize(2 * (size_t)steps);
+        for (auto &e : events) TMD_CUDA(cudaEventCreate(&e));
+    }
+    for (int step = 0; step < steps; ++step) {
+        const int g = step & 1;
+        const bool last = step == steps - 1;
+        // ---- rebuild, if the positions written by the previous pass say so (decided on the device) ----
+        a.gate = gates + g;
+        a.xs = rec[p];
+        static const int dbg = nl_env_int("TMD_MD_DEBUG", 0);  // diagnosis only: 1 = no gated launches, 2 = no build launches
+        if (dbg != 1) ::tmd::count_launch(), md_export_kernel<DIM><<<nb, 256, 0, s>>>(a.order, n, xu, vs, nullptr, pos, vel, nullptr, a.gate);
+        if (dbg == 0) TMD_CHECK(nl_launch_build<DIM>(nl, a, s));
+        if (dbg != 1) ::tmd::count_launch(), md_import_kernel<DIM><<<nb, 256, 0, s>>>(a.order, n, pos, vel, nullptr, imass, a.image, xu, vs,
+                                                                       nullptr, imass_s, image_s, a.gate);
+        // ---- forces + closing kick (+ opening kick and drift of the next step) ----
+        a.xs_next = rec[p ^ 1];
+        a.flag_clear = gates + g;
+        a.flag_next = gates + (g ^ 1);
+        a.epi_last = last ? 1 : 0;
+        if (nl->timing) TMD_CUDA(cudaEventRecord(events[2 * step], s));
+        nl_launch_force_epi<DIM>(a, fblocks, s);
+        if (nl->timing) TMD_CUDA(cudaEventRecord(events[2 * step + 1], s));
+        if (!last) p ^= 1;
+    }
+    ::tmd::count_launch(), md_export_kernel<DIM><<<nb, 256, 0, s>>>(a.order, n, xu, vs, fs, pos, vel, force, nullptr);
+    TMD_CUDA(cudaGetLastError());
+    if (nl->timing) {  // measurement runs only: waits for the run
+        TMD_CUDA(cudaStreamSynchronize(s));
+        for (int step = 0; step < steps; ++step) {
+            float ms = 0.f;
+            TMD_CUDA(cudaEventElapsedTime(&ms, events[2 * step], events[2 * step + 1]));
+            nl->traversal_ms += ms;
+            nl->traversals += 1;
+        }
+        for (auto &e : events) cudaEventDestroy(e);
+    }
+    return TMD_OK;
+}
+
+extern "C" {
+
+int tmd_nlist_run_vv(tmd_nlist *nl, double *pos, double *vel, double *force, const double *imass,
+                     const int32_t *tidx, int64_t n, const tmd_box *box, const double *table, int32_t ntypes,
+                     double dt, int32_t steps, double *vw, tmd_stream_t stream) {
+    TMD_REQUIRE(nl != nullptr, "nl is NULL");
+    TMD_REQUIRE(box && box->dim >= 1 && box->dim <= 3, "box->dim must be 1..3");
+    TMD_REQUIRE(n >= 2 && steps >= 1, "needs n >= 2 and steps >= 1");
+    TMD_REQUIRE(pos && vel && force && imass && vw, "NULL argument");
+    TMD_REQUIRE(ntypes == 1 || tidx, "tidx is required when ntypes > 1");
+    TMD_REQUIRE(nl->xs_ext == nullptr, "this handle is bound to a slab (tmd_nlist_bind_records)");
+    TMD_CHECK(require_device());
+    cudaStream_t s = as_stream(stream);
+    const int dim = box->dim;
+
+    NlArgs a;
+    bool same = false;
+    TMD_CHECK(nl_prepare(nl, n, box, table, ntypes, 0, n, 0, s, a, same));
+    a.pos = pos;
+    a.tidx = tidx;
+    if (nl->cap_md < nl->cap_n) {
+        TMD_CUDA(cudaStreamSynchronize(s));
+        cudaFree(nl->xs2);
+        cudaFree(nl->md);
+        nl->xs2 = nullptr;
+        nl->md = nullptr;
+        nl->cap_md = 0;
+        TMD_CUDA(cudaMalloc(&nl->xs2, (size_t)nl->cap_n * sizeof(double4)));
+        TMD_CUDA(cudaMalloc(&nl->md, (size_t)nl->cap_n * 16 * sizeof(double)));
+        nl->cap_md = nl->cap_n;
+    }
+    const size_t stride = (size_t)nl->cap_md * 3;
+    a.xu = nl->md;
+    a.vs = nl->md + stride;
+    a.fs = nl->md + 2 * stride;
+    a.fx = nullptr;  // (nl->md + 3 * stride is reserved for the forces of other potentials)
+    a.image_s = nl->md + 4 * stride;
+    a.imass_s = nl->md + 5 * stride;
+    a.dt = dt;
+    a.half_dt = dt * 0.5;  // VelocityVerlet.half_timestep (integrators.py:82)
+    a.flags = TMD_WANT_V | TMD_WANT_F | TMD_WANT_W;
+    a.force = nullptr;
+    a.vw = vw;
+    if (dim == 1) return md_run_vv<1>(nl, a, same, pos, vel, force, imass, n, steps, s);
+    if (dim == 2) return md_run_vv<2>(nl, a, same, pos, vel, force, imass, n, steps, s);
+    return md_run_vv<3>(nl, a, same, pos, vel, force, imass, n, steps, s);
 }
 
 // ---- slab path: rows are cell-order slots, state lives in slot order ------------------------------

@@ -121,6 +121,8 @@ class VelocityVerlet(MDIntegrator):
         """
         if steps <= 0:
             return
+        if steps >= 2 and self._run_resident(system, steps):
+            return
         part, n, dim, pos, vel, force, imass = _arrays(system)
         dt, stream = float(self.timestep), _device.stream_ptr()
         args = (_device.dptr(pos), _device.dptr(vel), _device.dptr(force), _device.dptr(imass), n, dim, dt, stream)
@@ -137,6 +139,35 @@ class VelocityVerlet(MDIntegrator):
         _lib.call("tmd_vv_kick", _device.dptr(vel), _device.dptr(part._force.device()),
                   _device.dptr(imass), n, dim, dt, stream)
         part._vel.written_on_device()
+
+
+def _vv_run_resident(self, system, steps: int) -> bool:
+    """The fused force + kick + drift path (``tmd_nlist_run_vv``): the whole run is ONE library call, the state
+    lives in the neighbour list's cell order and each step is a single traversal whose epilogue integrates.
+    Taken when the force field is one ``LennardJonesCut`` on its neighbour-list path; bit-identical to the
+    step-by-step path (same lists, same roundings).  Returns False when the system does not qualify."""
+    pots = system.potentials
+    if len(pots) != 1 or not hasattr(pots[0], "_resident_args") or not RESIDENT_RUNS:
+        return False
+    _device.require_cuda()
+    res = pots[0]._resident_args(system)
+    if res is None:
+        return False
+    handle, tidx, n, box_abi, table, ntyp = res
+    part, n, dim, pos, vel, force, imass = _arrays(system)
+    vw = part._vw_buffer()
+    _lib.call("tmd_nlist_run_vv", handle, _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
+              _device.dptr(imass), _device.dptr(tidx) if tidx is not None else None, n, C.byref(box_abi),
+              _lib.hptr(table), ntyp, float(self.timestep), int(steps), _device.dptr(vw), _device.stream_ptr())
+    part._pos.written_on_device()
+    part._vel.written_on_device()
+    part._force.written_on_device(shape=part._pos.shape)
+    part._vw_fresh.update(("v_pot", "virial"))
+    return True
+
+
+RESIDENT_RUNS = True  # module switch (tests compare the fused run with the step-by-step path)
+VelocityVerlet._run_resident = _vv_run_resident
 
 
 def _is_device_stream(rgen) -> bool:

@@ -231,6 +231,23 @@ class LennardJonesCut(Potential):
             _device.dptr(force) if force is not None else None, _device.dptr(vw), _device.stream_ptr(),
         )
 
+    def _resident_args(self, system):
+        """(handle, tidx, n, box, table, ntypes) for the fused resident run (``tmd_nlist_run_vv``) or None when
+        this system does not take the neighbour-list path (small, not fully periodic, triclinic)."""
+        particles = system.particles
+        npart = particles.npart
+        if npart < 2:
+            return None
+        box_abi = system.box.to_abi()
+        if isinstance(box_abi, _lib.Cell):
+            return None
+        types, table, tidx = self._tables(particles)
+        ntyp = len(types)
+        if self._kernel_for(npart, box_abi, table, ntyp) != "tmd_lj_nlist":
+            return None
+        tidx_dev = particles._static_device(f"lj_tidx_{id(self)}", tidx, np.int32) if ntyp > 1 else None
+        return self._nlist_handle(), tidx_dev, npart, box_abi, table, ntyp
+
     # ---- the plug-in boundary: host arrays in, host arrays out ----------------------------------------
     def _host_call(self, system, flags):
         particles = system.particles
