@@ -106,6 +106,10 @@ struct NlArgs {
     int *flag_clear;     // the word that gated this step's build: cleared for its next use
     double dt, half_dt;
     int epi_last;        // 1: last step of the run, closing half kick only
+    int md_rebuild;      // the build kernels move the resident state: binning reads xu / vs through the OLD slot_of and
+                         // leaves pos_w / vel_w (atom order) behind, the list kernel fills the NEW slots from them
+    double *pos_w, *vel_w;
+    const double *imass; // [n] by atom
     LjTable tab;
 };
 
@@ -164,6 +168,14 @@ __device__ __forceinline__ double4 ld_record(const double4 *p) {
     asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
     return v;
 }
+
+// 8 bytes global -> shared without a register in between (LDGSTS); completion: cp_async_wait_all()
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void st_entries8(unsigned *p, const unsigned (&e)[8]) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(e[0]), "r"(e[1]), "r"(e[2]),
@@ -264,7 +276,15 @@ __global__ void __launch_bounds__(kBinThreads) nl_bin_kernel(const NlArgs a) {
         int c[3] = {0, 0, 0};
 #pragma unroll
         for (int k = 0; k < DIM; ++k) {
-            const double v = a.pos[i * DIM + k];
+            double v;
+            if (a.md_rebuild) {  // resident run: the state lives in (old) slot order; atom order is the staging area
+                const int64_t e = (int64_t)a.slot_of[i] * DIM + k;
+                v = a.xu[e];
+                a.pos_w[i * DIM + k] = v;
+                a.vel_w[i * DIM + k] = a.vs[e];
+            } else {
+                v = a.pos[i * DIM + k];
+            }
             const double im = floor(v * g.ilen[k]) * g.len[k];
             const double w = v - im;  // into [0, L) up to rounding
             int ck = (int)(w * g.scale[k]);
@@ -458,6 +478,16 @@ __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
             atomicAdd(&a.nlflags[1], 1);  // statistics only: the traversal handles such a row exactly
         }
         a.nneigh[row] = cnt;
+        if (a.md_rebuild) {  // whole system: row == slot
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                a.xu[(int64_t)slot * DIM + k] = a.pos_w[(int64_t)atom * DIM + k];
+                a.vs[(int64_t)slot * DIM + k] = a.vel_w[(int64_t)atom * DIM + k];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) const_cast<double *>(a.image_s)[(int64_t)slot * 3 + k] = a.image[(int64_t)atom * 3 + k];
+            const_cast<double *>(a.imass_s)[slot] = a.imass[atom];
+        }
     }
 }
 
@@ -519,6 +549,9 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
     // per pair that crosses a box face, so they live in shared memory: the twelve registers they would
     // hold go to a third record buffer (deeper gather pipeline) instead.
     __shared__ double s_w[6][kNlThreads];
+    // EPI: what the epilogue of the current row needs (v, x, lattice shift, build position, 1/m, other forces) is
+    // requested when the row starts and lands here while its pairs are evaluated
+    __shared__ double s_epi[EPI ? 6 : 1][EPI ? kNlThreads : 1];
     constexpr int kRowsPerBlock = kNlThreads / G;
     const int tid = threadIdx.x;
 #pragma unroll
@@ -546,6 +579,9 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
     // virial (xx xy xz yy yz zz) = 2 F (x) x of the rows this lane leads - sum f (x) S of crossing pairs
     double vtot = 0.0;
     int hits = 0;
+    // per-atom virial term F_i (x) x_i: lane p < DIM of a group accumulates row p of the upper triangle,
+    // (p, p), (p, p+1), ... in registers; only the rare crossing corrections go through s_w
+    double wreg[3] = {0.0, 0.0, 0.0};
 
     // Everything a row needs before its first pair can be evaluated; fetched one row ahead so that
     // the dependent chain (row -> list head -> record) of the NEXT row overlaps this row's arithmetic.
@@ -580,6 +616,20 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
         const double4 me = cur.me;
         const int ti = SINGLE ? 0 : (int)__double_as_longlong(me.w);
         double facc[3] = {0.0, 0.0, 0.0};
+        if (EPI) {
+            if (valid && l < DIM) {
+                const int64_t e = (int64_t)slot * DIM + l;
+                cp_async8(&s_epi[0][tid], a.vs + e);
+                cp_async8(&s_epi[4][tid], a.imass_s + slot);
+                if (a.fx) cp_async8(&s_epi[5][tid], a.fx + e);
+                if (!a.epi_last) {
+                    cp_async8(&s_epi[1][tid], a.xu + e);
+                    cp_async8(&s_epi[2][tid], a.image_s + (int64_t)slot * 3 + l);
+                    cp_async8(&s_epi[3][tid], reinterpret_cast<const double *>(a.xb + slot) + l);
+                }
+            }
+            cp_async_commit();
+        }
 
         // A candidate is handled in two halves.  consume(): the three subtractions that read the gathered
         // record (the scoreboard wait of its load happens here).  compute(): everything else.
@@ -640,7 +690,7 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
                             if (k < DIM) facc[k] += fk;
 #pragma unroll
                             for (int b = k; b < 3; ++b, ++w)
-                                if (b < DIM) s_w[w][tid] = fma(-fk, S[b], s_w[w][tid]);
+                                if (b < DIM && S[b] != 0.0) s_w[w][tid] = fma(-fk, S[b], s_w[w][tid]);
                         }
                     }
                 }
@@ -705,34 +755,34 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
             const bool mine = valid && l < DIM;
             const int64_t e = (int64_t)slot * DIM + (l < DIM ? l : 0);
             const double fl = l == 0 ? f[0] : (l == 1 ? f[1] : f[2]);
-            double fk = fl, v = 0.0, x = 0.0, im = 0.0, shift = 0.0;
+            double fk = fl, v = 0.0, x = 0.0, bk = 0.0;
+            cp_async_wait_all();  // this lane's own requests of the row start
             if (mine) {
-                if (a.fx) fk = a.fx[e] + fl;  // the system's other potentials were evaluated into fx before this launch
-                v = a.vs[e];
-                im = a.imass_s[slot];
+                if (a.fx) fk = s_epi[5][tid] + fl;  // the system's other potentials were evaluated into fx before this launch
+                v = s_epi[0][tid];
+                const double im = s_epi[4][tid];
                 a.fs[e] = fk;
                 v = kick(v, fk, im, a.half_dt);  // integrators.py:94 of this step
                 if (!a.epi_last) {
-                    x = a.xu[e];
-                    shift = a.image_s[(int64_t)slot * 3 + l];
-                    v = kick(v, fk, im, a.half_dt);          // :88 of the next step
-                    x = __dadd_rn(x, __dmul_rn(a.dt, v));    // :90
+                    v = kick(v, fk, im, a.half_dt);                      // :88 of the next step
+                    x = __dadd_rn(s_epi[1][tid], __dmul_rn(a.dt, v));    // :90
                     a.xu[e] = x;
+                    x = __dsub_rn(x, s_epi[2][tid]);  // the record: what nl_gather_check_kernel forms, pos - image
+                    bk = s_epi[3][tid];
                 }
                 a.vs[e] = v;
             }
             if (!a.epi_last) {  // block-uniform
-                const double rec = __dsub_rn(x, shift);  // what nl_gather_check_kernel forms: pos - image
                 const int base = (tid & 31) & ~(G - 1);
-                const double ry = __shfl_sync(0xffffffffu, rec, base + (DIM > 1 ? 1 : 0));
-                const double rz = __shfl_sync(0xffffffffu, rec, base + (DIM > 2 ? 2 : 0));
+                const double ry = __shfl_sync(0xffffffffu, x, base + (DIM > 1 ? 1 : 0));
+                const double rz = __shfl_sync(0xffffffffu, x, base + (DIM > 2 ? 2 : 0));
+                const double by = __shfl_sync(0xffffffffu, bk, base + (DIM > 1 ? 1 : 0));
+                const double bz = __shfl_sync(0xffffffffu, bk, base + (DIM > 2 ? 2 : 0));
                 if (l == 0 && valid) {
-                    const double4 b = a.xb[slot];
-                    const double4 nr = make_double4(rec, DIM > 1 ? ry : 0.0, DIM > 2 ? rz : 0.0, me.w);
-                    a.xs_next[slot] = nr;
-                    double r = (nr.x - b.x) * (nr.x - b.x);
-                    if (DIM > 1) r = fma(nr.y - b.y, nr.y - b.y, r);
-                    if (DIM > 2) r = fma(nr.z - b.z, nr.z - b.z, r);
+                    a.xs_next[slot] = make_double4(x, DIM > 1 ? ry : 0.0, DIM > 2 ? rz : 0.0, me.w);
+                    double r = (x - bk) * (x - bk);
+                    if (DIM > 1) r = fma(ry - by, ry - by, r);
+                    if (DIM > 2) r = fma(rz - bz, rz - bz, r);
                     if (!(r <= a.half_skin2)) *a.flag_next = 1;  // also catches NaN
                 }
             }
@@ -744,15 +794,16 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) dst[k] = (flags & TMD_ACCUMULATE) ? dst[k] + f[k] : f[k];
             }
-            if (flags & TMD_WANT_W) {
-                const double x[3] = {me.x - a.centre[0], me.y - a.centre[1], me.z - a.centre[2]};
-                int w = 0;
-#pragma unroll
-                for (int p = 0; p < 3; ++p)
-#pragma unroll
-                    for (int q = p; q < 3; ++q, ++w)
-                        if (q < DIM) s_w[w][tid] = fma(2.0 * f[p], x[q], s_w[w][tid]);
-            }
+        }
+        if (WF && (flags & TMD_WANT_W)) {
+            const double xc[3] = {me.x - a.centre[0], me.y - a.centre[1], me.z - a.centre[2]};
+            const double f2 = 2.0 * (l == 0 ? f[0] : (l == 1 ? f[1] : (l == 2 ? f[2] : 0.0)));
+            const double x0 = l == 0 ? xc[0] : (l == 1 ? xc[1] : xc[2]);
+            const double x1 = l == 0 ? xc[1] : (l == 1 ? xc[2] : 0.0);
+            const double x2 = l == 0 ? xc[2] : 0.0;
+            wreg[0] = fma(f2, x0, wreg[0]);
+            if (DIM > 1) wreg[1] = fma(f2, x1, wreg[1]);
+            if (DIM > 2) wreg[2] = fma(f2, x2, wreg[2]);
         }
     }
 
@@ -762,6 +813,9 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
     double wtot[6];
 #pragma unroll
     for (int w = 0; w < 6; ++w) wtot[w] = s_w[w][tid];
+    if (l == 0) { wtot[0] += wreg[0]; wtot[1] += wreg[1]; wtot[2] += wreg[2]; }
+    if (l == 1 && DIM > 1) { wtot[3] += wreg[0]; wtot[4] += wreg[1]; }
+    if (l == 2 && DIM > 2) wtot[5] += wreg[0];
     red[1] = wtot[0]; red[2] = wtot[1]; red[3] = wtot[2];
     red[4] = wtot[1]; red[5] = wtot[3]; red[6] = wtot[4];
     red[7] = wtot[2]; red[8] = wtot[4]; red[9] = wtot[5];
@@ -1194,6 +1248,9 @@ static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double
     a.flag_next = a.flag_clear = nullptr;
     a.dt = a.half_dt = 0.0;
     a.epi_last = 0;
+    a.md_rebuild = 0;
+    a.pos_w = a.vel_w = nullptr;
+    a.imass = nullptr;
     {
         const size_t cells1 = (size_t)nl->cap_cells + 1;
         const size_t chunks = ((size_t)nl->cap_cells + kScanChunk - 1) / kScanChunk;
@@ -1318,11 +1375,12 @@ static int md_run_vv(tmd_nlist *nl, NlArgs &a, bool same, double *pos, double *v
         // ---- rebuild, if the positions written by the previous pass say so (decided on the device) ----
         a.gate = gates + g;
         a.xs = rec[p];
-        static const int dbg = nl_env_int("TMD_MD_DEBUG", 0);  // diagnosis only: 1 = no gated launches, 2 = no build launches
-        if (dbg != 1) ::tmd::count_launch(), md_export_kernel<DIM><<<nb, 256, 0, s>>>(a.order, n, xu, vs, nullptr, pos, vel, nullptr, a.gate);
-        if (dbg == 0) TMD_CHECK(nl_launch_build<DIM>(nl, a, s));
-        if (dbg != 1) ::tmd::count_launch(), md_import_kernel<DIM><<<nb, 256, 0, s>>>(a.order, n, pos, vel, nullptr, imass, a.image, xu, vs,
-                                                                       nullptr, imass_s, image_s, a.gate);
+        a.md_rebuild = 1;  // the two build kernels also carry the state from the old slots to the new ones
+        a.pos_w = pos;
+        a.vel_w = vel;
+        a.imass = imass;
+        TMD_CHECK(nl_launch_build<DIM>(nl, a, s));
+        a.md_rebuild = 0;
         // ---- forces + closing kick (+ opening kick and drift of the next step) ----
         a.xs_next = rec[p ^ 1];
         a.flag_clear = gates + g;
