@@ -20,7 +20,7 @@
  *                never synchronise and never allocate on the hot path (scratch
  *                comes from a per-device arena that only grows).  The Python
  *                package keeps the particle arrays resident in HBM and calls
- *                these; so does tmd_md_run().
+ *                these; so do the resident runs (tmd_nlist_run_vv, tmd_slabrun_*).
  *
  * Reference = infretis/turtlemd 2023.3.1; citations are file:line in its tree.
  *
@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define TMD_ABI_VERSION 1
+#define TMD_ABI_VERSION 2
 
 typedef enum tmd_status {
     TMD_OK = 0,
@@ -251,7 +251,15 @@ int tmd_verlet_step(double *pos, double *vel, double *prev, const double *force,
 typedef struct tmd_rng {
     uint64_t key;            /* Philox key word 0 (word 1 = 0), = numpy Philox(key=...)          */
     uint64_t offset;         /* index of this step's first normal in the stream                  */
+    /* ABI 2.  Optional device-side step counter, honoured by tmd_langevin_inertia_pre / _post_pre:
+     * when step_counter != NULL the kernel starts at offset + step_counter[0] * step_stride, so a
+     * step recorded once in a CUDA graph draws fresh noise at every replay (tmd_counter_add
+     * advances the counter inside the graph).  NULL: the host passes the position in `offset`.    */
+    const uint64_t *step_counter;
+    uint64_t step_stride;    /* normals one step of the WHOLE system consumes (2 n dim)           */
 } tmd_rng;
+/* counter[0] += increment on the stream (one thread)                                            */
+int tmd_counter_add(uint64_t *counter, uint64_t increment, tmd_stream_t stream);
 
 /* LangevinOverdamped (integrators.py:151-163), the part between force() and potential():
  *   xi = sigma_i * z[offset + (first+i)*dim + k] ;  x += bddt_i * F + xi ;  v = xi

@@ -1,7 +1,7 @@
 """Multi-GPU parity check, launched by torch.distributed.run (one rank per GPU, NCCL):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29533 tests/multi_gpu_check.py [slab|atoms] [rep] [steps] [graph]
+        --master-port 29533 tests/multi_gpu_check.py [slab|atoms] [rep] [steps] [graph] [vv|langevin|dimer]
 
 Every rank steps its share of one LJ fluid with the chosen decomposition; rank 0 also runs the
 plain single-GPU integrator on the same input and compares positions, velocities, forces, energy
@@ -32,19 +32,20 @@ def main():
     rep = int(sys.argv[2]) if len(sys.argv) > 2 else 24
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 40
     graph = len(sys.argv) > 4 and sys.argv[4] == "graph"
+    physics = sys.argv[5] if len(sys.argv) > 5 else "vv"  # langevin: config #4 in small; dimer: config #5
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
-    pos, vel, size = bench.lj_inputs(rep)
+    cfg = dict(rep=rep, method="nlist", dt=0.005, dimer=physics == "dimer",
+               integrator="langevin" if physics == "langevin" else None)
+    pos, vel, size, _, _, build = bench.build_lj(cfg)
 
     def make():
-        pot = LennardJonesCut(dim=3, shift=True, method="nlist")
-        pot.set_parameters(bench.SINGLE)
-        return System(Box(low=size[:, 0], high=size[:, 1]), Particles.from_arrays(pos, vel=vel), [pot])
+        return build()[0]
 
-    system = make()
-    dec = (SlabDecomposition if kind == "slab" else AtomDecomposition)(system, VelocityVerlet(0.005))
+    system, integrator, _ = build()
+    dec = (SlabDecomposition if kind == "slab" else AtomDecomposition)(system, integrator)
     dec.prepare()
     done = 0
     if graph:
@@ -57,8 +58,7 @@ def main():
     v_pot, virial = dec.reduce_observables()
     ok, text = True, ""
     if rank == 0:
-        ref = make()
-        integ = VelocityVerlet(0.005)
+        ref, integ, _ = build()
         ref.potential_and_force()
         for _ in range(steps):
             integ(ref)
@@ -70,7 +70,7 @@ def main():
         ok = errs["pos"] < 1e-11 and errs["vel"] < 1e-9 and errs["force"] < 1e-9 and errs["v_pot"] < 1e-10 \
             and errs["virial"] < 1e-9
         extra = f" rebuilds={dec.rebuilds} halo={dec.halo}" if kind == "slab" else ""
-        text = (f"MULTI_GPU_CHECK {'ok' if ok else 'FAILED'} kind={kind} world={world} n={len(pos)} steps={steps} "
+        text = (f"MULTI_GPU_CHECK {'ok' if ok else 'FAILED'} kind={kind} physics={physics} world={world} n={len(pos)} steps={steps} "
                 f"graph={graph}{extra} " + " ".join(f"{k}={e:.2e}" for k, e in errs.items()))
         print(text, flush=True)
     if graph:

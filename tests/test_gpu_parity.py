@@ -1218,8 +1218,10 @@ def test_slab_decomposition_refuses_thin_slabs():
         dec.prepare()
 
 
-@pytest.mark.parametrize("kind,graph", [("slab", ""), ("slab", "graph"), ("atoms", "")])
-def test_two_real_ranks_match_single_gpu(kind, graph):
+@pytest.mark.parametrize("kind,graph,physics", [("slab", "", "vv"), ("slab", "graph", "vv"), ("atoms", "", "vv"),
+                                                ("atoms", "graph", "vv"), ("atoms", "graph", "langevin"),
+                                                ("atoms", "", "langevin"), ("atoms", "graph", "dimer")])
+def test_two_real_ranks_match_single_gpu(kind, graph, physics):
     """Two processes, two GPUs, NCCL: tests/multi_gpu_check.py compares the decomposed trajectory with
     the single-GPU one.  Skipped on a one-GPU box (the emulated-rank tests above cover the logic)."""
     import socket
@@ -1235,7 +1237,7 @@ def test_two_real_ranks_match_single_gpu(kind, graph):
         port = sock.getsockname()[1]
     script = str(GOLDEN.parent / "multi_gpu_check.py")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", str(port), script, kind, "24", "40"] + ([graph] if graph else [])
+           "127.0.0.1", "--master-port", str(port), script, kind, "24", "40", graph or "eager", physics]
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
     assert proc.returncode == 0 and "MULTI_GPU_CHECK ok" in proc.stdout, proc.stdout[-3000:] + proc.stderr[-3000:]
 

@@ -57,7 +57,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} is declared in include/turtlemd_b200.h but not exported"
     assert sorted(_lib.PROTOTYPES) == names  # the ctypes binding covers exactly the header
-    assert lib.tmd_abi_version() == 1
+    assert lib.tmd_abi_version() == 2
     assert lib.tmd_status_string(3).decode().startswith("no CUDA device")
 
 
@@ -65,7 +65,7 @@ def test_struct_layouts_match_the_header():
     import ctypes as C
 
     assert C.sizeof(_lib.Box) == 4 * 4 + 8 * 6
-    assert C.sizeof(_lib.Rng) == 16
+    assert C.sizeof(_lib.Rng) == 32  # key, offset, step_counter, step_stride (ABI 2)
     assert C.sizeof(_lib.LangevinConsts) == 8 * 11
     out = _lib.LangevinConsts()
     _lib.call("tmd_langevin_inertia_constants", 0.002, 0.3, 1.0, C.byref(out))
@@ -428,3 +428,20 @@ def test_philox_twin_matches_oracle_and_numpy():
         scaled = twin.normal(1.0, np.array([[2.0], [3.0]]), size=(2, 2))
         base = pr.normals(key, 151, 4).reshape(2, 2)
         assert np.array_equal(scaled, 1.0 + np.array([[2.0], [3.0]]) * base)
+
+
+def test_langevin_run_refuses_to_shard_a_force_field_the_fused_kernel_does_not_cover():
+    """first / n_global used to be dropped silently on the general path (identical noise on
+    every shard).  Host logic only: the refusal comes before any kernel."""
+    from turtlemd_b200.integrators import LangevinInertia
+    from turtlemd_b200.philox import PhiloxNormal
+    from turtlemd_b200.potentials import DoubleWell
+    from turtlemd_b200.system import Box, Particles, System
+
+    class Other(DoubleWell):  # a subclass is not the fused kernel's potential
+        pass
+
+    system = System(Box(periodic=[False]), Particles.from_arrays(np.full((8, 1), -1.0)), [Other(a=1.0, b=2.0, c=0.0)])
+    integ = LangevinInertia(timestep=0.002, gamma=0.3, beta=1.0 / 0.07, rgen=PhiloxNormal(key=1))
+    with pytest.raises(NotImplementedError):
+        integ.run(system, 3, first=8, n_global=16)

@@ -54,7 +54,10 @@ class Cell(C.Structure):
 
 
 class Rng(C.Structure):
-    _fields_ = [("key", C.c_uint64), ("offset", C.c_uint64)]
+    """``tmd_rng``; ``step_counter`` / ``step_stride``: optional device-side step counter (CUDA graph replays)."""
+
+    _fields_ = [("key", C.c_uint64), ("offset", C.c_uint64), ("step_counter", C.c_void_p),
+                ("step_stride", C.c_uint64)]
 
 
 class LangevinConsts(C.Structure):
@@ -131,6 +134,7 @@ PROTOTYPES = {
     "tmd_langevin_inertia_post_pre": [_P, _P, _P, _P, _I64, _I32, _LC, _RNG, _I64, _P],
     "tmd_langevin_inertia_post": [_P, _P, _P, _I64, _I32, _LC, _P],
     "tmd_langevin_inertia_doublewell": [_P, _P, _P, _P, _I64, _I32, _D, _D, _D, _LC, _RNG, _I64, _I64, _I32, _P, _P],
+    "tmd_counter_add": [_P, _U64, _P],
     "tmd_philox_normal_fill": [_P, _I64, _RNG, _P],
     "tmd_host_philox_normal_fill": [_P, _I64, _U64, _U64],
     "tmd_host_philox_raw_fill": [_P, _I64, _U64, _U64],

@@ -37,7 +37,11 @@ int require_device();  // TMD_OK or TMD_ERR_NO_DEVICE
 
 // ---- per-device scratch arena -------------------------------------------------------------
 // Grows only; the hot path never allocates once the first step has run.  One arena per device,
-// several named slots so that independent kernels of one step do not alias.
+// several named slots so that independent kernels of one step do not alias.  A slot that has to grow
+// gets a new block and the old one is RETIRED, never freed while the process lives (captured CUDA
+// graphs and launches still in flight keep their pointers valid).  The slots are shared by every
+// stream of a device: callers that run the library on several streams of one device at once must
+// order those streams themselves (the Python layer uses one stream per process).
 enum ArenaSlot {
     SLOT_PARTIAL_F = 0,   // per-split force partials of the pair kernels
     SLOT_PARTIAL_VW,      // per-block (V, W) partials

@@ -71,6 +71,8 @@ static inline Launch ew_launch(int64_t total) {
     if (e >= total) return;                                               \
     const bool two = (e + 1) < total;
 
+__global__ void counter_add_kernel(uint64_t *counter, uint64_t increment) { counter[0] += increment; }
+
 // ---- Velocity Verlet -----------------------------------------------------------------------------
 template <int DIM, bool VEC, int KICKS, bool DRIFT>
 __global__ void __launch_bounds__(256) vv_kernel(double *__restrict__ pos, double *__restrict__ vel,
@@ -183,8 +185,11 @@ __global__ void __launch_bounds__(256) inertia_pre_kernel(double *__restrict__ p
                                                           const double *__restrict__ imass, int64_t total,
                                                           tmd_langevin_consts c, uint64_t key, uint64_t q_base,
                                                           const double *__restrict__ noise_pos,
-                                                          const double *__restrict__ noise_vel) {
+                                                          const double *__restrict__ noise_vel,
+                                                          const uint64_t *__restrict__ step_counter,
+                                                          uint64_t step_stride) {
     TMD_EW_PROLOGUE
+    if (step_counter) q_base += step_counter[0] * step_stride;  // graph replays: the position lives on the device
     const D2 f = ld2<VEC>(force, e, two);
     const D2 im = ld_imass<DIM>(imass, e, two);
     D2 x = ld2<VEC>(pos, e, two);
@@ -503,7 +508,7 @@ int tmd_langevin_inertia_pre(double *pos, double *vel, const double *force, cons
     const uint64_t q_base = rng ? rng->offset + 2ull * (uint64_t)first * (uint64_t)dim : 0;
     cudaStream_t s = as_stream(stream);
 #define TMD_IP(D, V, H) \
-    ::tmd::count_launch(), inertia_pre_kernel<D, V, H><<<l.blocks, l.threads, 0, s>>>(pos, vel, force, imass, total, *consts, key, q_base, noise_pos, noise_vel)
+    ::tmd::count_launch(), inertia_pre_kernel<D, V, H><<<l.blocks, l.threads, 0, s>>>(pos, vel, force, imass, total, *consts, key, q_base, noise_pos, noise_vel, rng ? rng->step_counter : nullptr, rng ? rng->step_stride : 0)
 #define TMD_IP_D(D)                                                            \
     do {                                                                       \
         if (noise_pos) { if (vec) TMD_IP(D, true, true); else TMD_IP(D, false, true); } \
@@ -529,7 +534,7 @@ int tmd_langevin_inertia_post_pre(double *pos, double *vel, const double *force,
     const uint64_t q_base = rng->offset + 2ull * (uint64_t)first * (uint64_t)dim;
     cudaStream_t s = as_stream(stream);
 #define TMD_IPP(D, V) \
-    ::tmd::count_launch(), inertia_pre_kernel<D, V, false, true><<<l.blocks, l.threads, 0, s>>>(pos, vel, force, imass, total, *consts, rng->key, q_base, nullptr, nullptr)
+    ::tmd::count_launch(), inertia_pre_kernel<D, V, false, true><<<l.blocks, l.threads, 0, s>>>(pos, vel, force, imass, total, *consts, rng->key, q_base, nullptr, nullptr, rng->step_counter, rng->step_stride)
     if (dim == 1) { if (vec) TMD_IPP(1, true); else TMD_IPP(1, false); }
     else if (dim == 2) { if (vec) TMD_IPP(2, true); else TMD_IPP(2, false); }
     else { if (vec) TMD_IPP(3, true); else TMD_IPP(3, false); }
@@ -615,6 +620,14 @@ int tmd_langevin_inertia_constants(double dt, double gamma, double beta, tmd_lan
     out->kfac = 2.0 - (3.0 - 4.0 * e + e * e) / gdt;
     out->one_minus_e2 = 1.0 - e * e;
     out->one_minus_e_sq = (1.0 - e) * (1.0 - e);
+    return TMD_OK;
+}
+
+int tmd_counter_add(uint64_t *counter, uint64_t increment, tmd_stream_t stream) {
+    TMD_REQUIRE(counter != nullptr, "counter is NULL");
+    TMD_CHECK(require_device());
+    ::tmd::count_launch(), counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(counter, increment);
+    TMD_CUDA(cudaGetLastError());
     return TMD_OK;
 }
 

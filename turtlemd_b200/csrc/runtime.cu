@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -45,6 +46,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 struct Arena {
     void *ptr[SLOT_COUNT];
     size_t cap[SLOT_COUNT];
+    std::vector<void *> retired;  // outgrown blocks: see arena_get
 };
 static constexpr int kMaxDevices = 32;
 static Arena g_arena[kMaxDevices];
@@ -61,15 +63,15 @@ int arena_get(ArenaSlot slot, size_t bytes, void **ptr) {
     std::lock_guard<std::mutex> lock(g_arena_mutex);
     Arena &a = g_arena[dev];
     if (a.cap[slot] < bytes) {
-        if (a.ptr[slot]) {
-            // earlier launches may still read the old block: drain before freeing
-            TMD_CUDA(cudaDeviceSynchronize());
-            TMD_CUDA(cudaFree(a.ptr[slot]));
-            a.ptr[slot] = nullptr;
-            a.cap[slot] = 0;
-        }
-        size_t want = bytes + bytes / 4 + 256;
-        TMD_CUDA(cudaMalloc(&a.ptr[slot], want));
+        // A slot that grows gets a NEW block; the old one is retired, not freed: CUDA graphs captured by the
+        // decompositions (parallel.py) bake scratch pointers, and kernels of another stream may still be
+        // using the old block.  Growth is geometric, so the retired blocks of a slot sum to less than its
+        // final size; they are released with the process.
+        if (a.ptr[slot]) a.retired.push_back(a.ptr[slot]);
+        const size_t want = bytes + bytes / 2 + 4096;
+        void *fresh = nullptr;
+        TMD_CUDA(cudaMalloc(&fresh, want));
+        a.ptr[slot] = fresh;
         a.cap[slot] = want;
     }
     *ptr = a.ptr[slot];

@@ -391,7 +391,14 @@ class LangevinInertia(MDIntegrator):
         """
         self.initiate_parameters(system)
         if not self._fusable(system):
-            if steps > 1 and _is_device_stream(self.rgen) and first == 0 and n_global is None:
+            if first != 0 or n_global is not None:
+                # a shard of a larger ensemble on a force field the fused kernel does not cover: the general
+                # path addresses its noise from draw 0 of this process's arrays, so every shard would see the
+                # SAME noise.  Refuse rather than correlate replicas across GPUs.
+                raise NotImplementedError(
+                    "LangevinInertia.run(first=, n_global=) shards DoubleWell-only replica ensembles driven by the "
+                    "counter-based PhiloxNormal stream; for other force fields use parallel.AtomDecomposition")
+            if steps > 1 and _is_device_stream(self.rgen):
                 return self._run_general(system, steps)
             for _ in range(steps):
                 self.integration_step(system)

@@ -34,6 +34,7 @@ import numpy as np
 from . import _device, _lib
 from .integrators import LangevinInertia, VelocityVerlet, _is_device_stream
 from .potentials.lennardjones import LennardJonesCut
+from .potentials.well import DoubleWell, DoubleWellPair
 
 _ALL = _lib.WANT_V | _lib.WANT_F | _lib.WANT_W
 
@@ -119,6 +120,9 @@ class AtomDecomposition:
         self._pos_pad = None
         self._graph = None
         self._graph_launches = 0
+        self._step_counter = None  # device-side step counter of a captured Langevin step
+        self.steps_done = 0        # integration steps taken since prepare()
+        self._counter_base = 0
 
     # ---- set-up -----------------------------------------------------------------------------------
     def prepare(self) -> None:
@@ -144,17 +148,41 @@ class AtomDecomposition:
         return tensor[lo: lo + self.plan.count * self.dim]
 
     def _evaluate(self, flags: int) -> None:
-        """All potentials for this rank's rows; vw holds this rank's share of V and W."""
+        """All potentials for this rank's rows; vw holds this rank's share of V and W.
+
+        ``LennardJonesCut``: rows ``[first, first+count)`` of the pair sum (no Newton's-third-law traffic
+        between ranks).  ``DoubleWellPair`` (well.py:262-286; a handful of active atoms, no cut-off): every
+        rank evaluates all active pairs from the replicated positions -- the forces land in the replicated
+        force array, of which a rank only ever reads its own rows -- and rank 0 alone contributes V and W to
+        the all-reduced observables.  ``DoubleWell`` (one-body, well.py:65-81): the own rows only.
+        Pair potentials first, in list order, so that the first one overwrites and the rest accumulate."""
         part = self.system.particles
         pos, force, vw = part._pos.device(), part._force.device(), part._vw_buffer()
+        want_f = bool(flags & _lib.WANT_F)
+        pots = self.system.potentials
+        ordered = [p for p in pots if isinstance(p, LennardJonesCut)] + [p for p in pots if not isinstance(p, LennardJonesCut)]
+        if not ordered or not isinstance(ordered[0], LennardJonesCut):
+            raise NotImplementedError("AtomDecomposition needs at least one LennardJonesCut potential (it defines the rows)")
         first = True
-        for pot in self.system.potentials:
-            if not isinstance(pot, LennardJonesCut):
-                raise NotImplementedError("AtomDecomposition shards LennardJonesCut force fields only")
-            pot._launch(self.system, pos, force if flags & _lib.WANT_F else None, vw,
-                   flags | (0 if first else _lib.ACCUMULATE), first=self.plan.first, count=self.plan.count)
+        for pot in ordered:
+            acc = 0 if first else _lib.ACCUMULATE
+            if isinstance(pot, LennardJonesCut):
+                pot._launch(self.system, pos, force if want_f else None, vw, flags | acc,
+                            first=self.plan.first, count=self.plan.count)
+            elif isinstance(pot, DoubleWellPair):
+                mine = flags if self.rank == 0 else flags & ~(_lib.WANT_V | _lib.WANT_W)
+                if mine & (_lib.WANT_V | _lib.WANT_F | _lib.WANT_W):
+                    pot._launch(self.system, pos, force if want_f else None, vw, mine | acc)
+            elif type(pot) is DoubleWell:
+                lo, cnt, dim = self.plan.first * self.dim, self.plan.count, self.dim
+                if cnt:
+                    _lib.call("tmd_doublewell", _device.dptr(pos[lo: lo + cnt * dim]), cnt, dim, *pot._abc(), flags | acc,
+                              _device.dptr(force[lo: lo + cnt * dim]) if want_f else None, _device.dptr(vw),
+                              _device.stream_ptr())
+            else:
+                raise NotImplementedError(f"AtomDecomposition cannot shard {type(pot).__name__}")
             first = False
-        if flags & _lib.WANT_F:
+        if want_f:
             part._force.written_on_device()
 
     def _gather_positions(self) -> None:
@@ -163,9 +191,12 @@ class AtomDecomposition:
 
     def step(self) -> None:
         """One integration step: move the own atoms, exchange positions, forces for the own rows."""
+        self.steps_done += 1
         if self._graph is not None:
             self._graph.replay()
             _lib.add_launches(self._graph_launches)
+            if self._step_counter is not None:  # keep the host-side stream position in step with the device counter
+                self.integrator.rgen.advance(2 * self.n * self.dim)
             part = self.system.particles
             part._pos.written_on_device()
             part._vel.written_on_device()
@@ -178,14 +209,20 @@ class AtomDecomposition:
     def capture(self, warm_steps: int = 3) -> bool:
         """Record one step (kernels + the NCCL all-gather) in a CUDA graph and replay it from now on:
         at 8 GPUs a step is ~100 us of device work and the Python / launch path would dominate.
-        Only for VelocityVerlet (the Langevin kernels take the stream offset as a launch parameter).
-        Returns False, leaving eager stepping in place, when capture is not possible."""
-        if not isinstance(self.integrator, VelocityVerlet) or self._graph is not None:
-            return self._graph is not None
+        LangevinInertia: the position in the noise stream is a device-side step counter that the recorded
+        step itself advances (``tmd_rng.step_counter``), so every replay draws the noise of ITS step --
+        the same numbers an eager run draws.  Returns False, leaving eager stepping in place, when capture
+        is not possible."""
+        if self._graph is not None:
+            return True
         torch = _device.torch()
         for _ in range(warm_steps):  # allocations, occupancy queries and the first list build happen here
             self.step()
         torch.cuda.synchronize()
+        langevin = isinstance(self.integrator, LangevinInertia)
+        if langevin:
+            self._step_counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+            self._counter_base = self.integrator.rgen.position
         graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
         try:
@@ -193,9 +230,16 @@ class AtomDecomposition:
                 self.step_move()
                 self._gather_positions()
                 self.step_force()
+                if langevin:
+                    _lib.call("tmd_counter_add", _device.dptr(self._step_counter), 1, _device.stream_ptr())
         except Exception:  # noqa: BLE001 - capture is an optimisation; eager stepping stays correct
             torch.cuda.synchronize()
+            self._step_counter = None
+            if langevin:
+                self.integrator.rgen.position = self._counter_base
             return False
+        if langevin:  # recording advanced the host-side position once without drawing anything
+            self.integrator.rgen.position = self._counter_base
         self._graph_launches = _lib.launch_count() - before
         _lib.add_launches(-self._graph_launches)  # recording is not launching
         self._graph = graph
@@ -207,6 +251,7 @@ class AtomDecomposition:
         if self._graph is not None:
             _device.torch().cuda.synchronize()
             self._graph = None
+            self._step_counter = None  # the host-side stream position was advanced with every replay
 
     def _step_args(self):
         part, plan = self.system.particles, self.plan
@@ -225,7 +270,11 @@ class AtomDecomposition:
                 _lib.call("tmd_vv_kick_drift", _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
                           _device.dptr(imass), plan.count, dim, float(integ.timestep), stream)
         else:
-            rng = _lib.Rng(integ.rgen.key, integ.rgen.position)
+            if self._step_counter is not None:  # being recorded: position = base + counter * (draws per step)
+                rng = _lib.Rng(integ.rgen.key, self._counter_base, _device.dptr(self._step_counter).value,
+                               2 * self.n * dim)
+            else:
+                rng = _lib.Rng(integ.rgen.key, integ.rgen.position)
             integ.rgen.advance(2 * self.n * dim)  # the stream moves on by the GLOBAL draw count on every rank
             if plan.count:
                 _lib.call("tmd_langevin_inertia_pre", _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
@@ -364,6 +413,7 @@ class SlabDecomposition:
         self.rebuilds = 0
         self._graphs = None
         self._graph_launches = {}
+        self.steps_done = 0  # integration steps taken since prepare()
 
     # ---- set-up -----------------------------------------------------------------------------------
     def prepare(self) -> None:
@@ -558,6 +608,7 @@ class SlabDecomposition:
         import torch.distributed as dist
 
         torch = _device.torch()
+        self.steps_done += 1
         g = self._graphs
         if g is not None:
             g["move"].replay()
