@@ -212,6 +212,32 @@ int tmd_nlist_build_slots(tmd_nlist *nl, const double *pos, const int32_t *tidx,
 int tmd_nlist_force_slots(tmd_nlist *nl, uint32_t flags, double *force_s, double *vw, tmd_stream_t stream);
 int tmd_nlist_view(tmd_nlist *nl, tmd_nlist_buffers *out);
 
+/* ---- resident multi-GPU VelocityVerlet run: one spatial slab per rank ----------
+ * K steps of integrators.py:84-94 over lennardjones.py:226-273 with the system cut into slabs of
+ * cell layers along z, one per rank.  Per step and rank: ONE traversal whose epilogue integrates,
+ * writes the next records and stores the two boundary layers into the neighbours' buffers (peer
+ * memory), and one barrier kernel (mailboxes in peer memory) that also ORs the ranks' "rebuild"
+ * flags; rebuilds (atom migration, ghost layers, binning, lists) are gated launches decided on
+ * the device.  No host read and no collective library inside a step.  `window` is the only memory
+ * other ranks touch: export it with tmd_ipc_get_handle, open the peers' handles, hand all of them
+ * to tmd_slabrun_connect.  The barrier spins on what peers write: ranks must sit on DIFFERENT
+ * GPUs; tests emulate ranks on one GPU phase by phase (tmd_slabrun_phase, signal and wait halves
+ * apart).  Waits are bounded (~2 s): then err has bit 1 set and the run is void, the box lives.  */
+typedef struct tmd_slabrun tmd_slabrun;
+int tmd_slabrun_create(tmd_slabrun **out, int32_t world, int32_t rank, int64_t n_global, const tmd_box *box,
+                       const double *table, int32_t ntypes, double skin, double dt);
+int tmd_slabrun_destroy(tmd_slabrun *sr);
+int tmd_slabrun_window(tmd_slabrun *sr, void **ptr, size_t *bytes);
+int tmd_slabrun_connect(tmd_slabrun *sr, void *const *windows);
+/* replicated DEVICE arrays of all n_global atoms (force valid for pos) -> slabs, ghosts, lists   */
+int tmd_slabrun_load(tmd_slabrun *sr, const double *pos, const double *vel, const double *force, const double *imass,
+                     const int32_t *tidx, tmd_stream_t stream);
+int tmd_slabrun_start(tmd_slabrun *sr, tmd_stream_t stream);
+int tmd_slabrun_step(tmd_slabrun *sr, int32_t last, tmd_stream_t stream);
+int tmd_slabrun_phase(tmd_slabrun *sr, int32_t phase, int32_t last, tmd_stream_t stream);
+int tmd_slabrun_export(tmd_slabrun *sr, double *pos, double *vel, double *force, double *vw, tmd_stream_t stream);
+int tmd_slabrun_status(tmd_slabrun *sr, int32_t *err, int64_t *n_own, int64_t *builds, int32_t *layers);
+
 /* K4. DoubleWell.potential / .force (potentials/well.py:65-81): V = sum a x^4 - b (x-c)^2 over
  * ALL n*dim coordinates, F = -4 a x^3 + 2 b (x - c), virial = 0.                                */
 int tmd_doublewell(const double *pos, int64_t n, int32_t dim, double a, double b, double c,

@@ -19,7 +19,7 @@ import torch.distributed as dist
 
 import bench
 from turtlemd_b200.integrators import VelocityVerlet
-from turtlemd_b200.parallel import AtomDecomposition, SlabDecomposition
+from turtlemd_b200.parallel import AtomDecomposition, SlabDecomposition, SlabRun
 from turtlemd_b200.potentials import LennardJonesCut
 from turtlemd_b200.system import Box, Particles, System
 
@@ -45,15 +45,28 @@ def main():
         return build()[0]
 
     system, integrator, _ = build()
-    dec = (SlabDecomposition if kind == "slab" else AtomDecomposition)(system, integrator)
-    dec.prepare()
-    done = 0
-    if graph:
-        if not dec.capture(warm_steps=3):
-            raise RuntimeError("CUDA graph capture failed")
-        done = 3
-    for _ in range(steps - done):
-        dec.step()
+    if kind == "slabrun":  # resident slab run: peer stores + device-side barriers, no NCCL inside a step
+        system.potential_and_force()
+        dec = SlabRun(system, integrator)
+        dec.prepare()
+        done = 0
+        if graph:
+            if not dec.capture():
+                raise RuntimeError("CUDA graph capture failed")
+            done = 3
+        first = (steps - done) // 2  # two runs: a second start() after a completed run
+        dec.run(first)
+        dec.run(steps - done - first)
+    else:
+        dec = (SlabDecomposition if kind == "slab" else AtomDecomposition)(system, integrator)
+        dec.prepare()
+        done = 0
+        if graph:
+            if not dec.capture(warm_steps=3):
+                raise RuntimeError("CUDA graph capture failed")
+            done = 3
+        for _ in range(steps - done):
+            dec.step()
     x, v, f = dec.gather_state()
     v_pot, virial = dec.reduce_observables()
     ok, text = True, ""
@@ -70,10 +83,12 @@ def main():
         ok = errs["pos"] < 1e-11 and errs["vel"] < 1e-9 and errs["force"] < 1e-9 and errs["v_pot"] < 1e-10 \
             and errs["virial"] < 1e-9
         extra = f" rebuilds={dec.rebuilds} halo={dec.halo}" if kind == "slab" else ""
+        if kind == "slabrun":
+            extra = f" status={dec.status()}"
         text = (f"MULTI_GPU_CHECK {'ok' if ok else 'FAILED'} kind={kind} physics={physics} world={world} n={len(pos)} steps={steps} "
                 f"graph={graph}{extra} " + " ".join(f"{k}={e:.2e}" for k, e in errs.items()))
         print(text, flush=True)
-    if graph:
+    if graph or kind == "slabrun":
         dec.release()
     dist.barrier()
     dist.destroy_process_group()

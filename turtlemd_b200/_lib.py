@@ -122,6 +122,16 @@ PROTOTYPES = {
     "tmd_slab_langevin_inertia_pre": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _LC, _RNG, _D, _P, _P],
     "tmd_slab_unsort": [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P],
     "tmd_slab_sort": [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P],
+    "tmd_slabrun_create": [C.POINTER(_P), _I32, _I32, _I64, _BOX, _P, _I32, _D, _D],
+    "tmd_slabrun_destroy": [_P],
+    "tmd_slabrun_window": [_P, C.POINTER(_P), C.POINTER(C.c_size_t)],
+    "tmd_slabrun_connect": [_P, C.POINTER(_P)],
+    "tmd_slabrun_load": [_P, _P, _P, _P, _P, _P, _P],
+    "tmd_slabrun_start": [_P, _P],
+    "tmd_slabrun_step": [_P, _I32, _P],
+    "tmd_slabrun_phase": [_P, _I32, _I32, _P],
+    "tmd_slabrun_export": [_P, _P, _P, _P, _P, _P],
+    "tmd_slabrun_status": [_P, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I32)],
     "tmd_doublewell": [_P, _I64, _I32, _D, _D, _D, _U32, _P, _P, _P],
     "tmd_dwpair": [_P, _I64, _BOX, _P, _I32, _P, _I32, _I32, _D, _D, _D, _U32, _P, _P, _P],
     "tmd_vv_kick_drift": [_P, _P, _P, _P, _I64, _I32, _D, _P],

@@ -110,6 +110,12 @@ struct NlArgs {
                          // leaves pos_w / vel_w (atom order) behind, the list kernel fills the NEW slots from them
     double *pos_w, *vel_w;
     const double *imass; // [n] by atom
+    // ---- slab runs (slabrun.cuh): sizes decided on the device, in-cell order by global index, halo push ----
+    const int *dyn;      // NULL, or [0] = atoms to bin (own atoms + ghost copies of the neighbours' boundary layers)
+    int row_cell_lo, row_cell_hi;  // row_cell_hi > 0: rows = slots of cells [lo, hi): first = starts[lo], count = starts[hi] - first
+    const int *gid;      // NULL, or global atom index by local index: slots inside a cell ascend by it
+    const int *halo;     // EPI = 2: [0] lo_begin [1] lo_end [2] dest_lo [3] hi_begin [4] hi_end [5] dest_hi (slots)
+    double4 *peer_lo_next, *peer_hi_next;  // EPI = 2: the record buffers of the next step on the two neighbouring ranks
     LjTable tab;
 };
 
@@ -269,9 +275,10 @@ __global__ void __launch_bounds__(kBinThreads) nl_bin_kernel(const NlArgs a) {
     const int64_t gtid = (int64_t)blockIdx.x * kBinThreads + tid;
     const int64_t gthreads = (int64_t)gridDim.x * kBinThreads;
     const int ncells = g.ncells;
+    const int64_t n = a.dyn ? (int64_t)a.dyn[0] : a.n;  // slab runs: the population of a rank changes from build to build
 
     // ---- 1. wrap a copy into the box, cell index, rank inside the cell (atomics) ----
-    for (int64_t i = gtid; i < a.n; i += gthreads) {
+    for (int64_t i = gtid; i < n; i += gthreads) {
         double x[3] = {0.0, 0.0, 0.0};
         int c[3] = {0, 0, 0};
 #pragma unroll
@@ -334,21 +341,26 @@ __global__ void __launch_bounds__(kBinThreads) nl_bin_kernel(const NlArgs a) {
             run += v[k];
         }
     }
-    if (gtid == 0) a.starts[ncells] = (int)a.n;
+    if (gtid == 0) a.starts[ncells] = (int)n;
     grid.sync();
 
     // ---- 3. scatter atoms to a provisional slot inside their cell ----
-    for (int64_t i = gtid; i < a.n; i += gthreads) a.order_tmp[a.starts[a.cell_of[i]] + a.rank_of[i]] = (int)i;
+    for (int64_t i = gtid; i < n; i += gthreads) a.order_tmp[a.starts[a.cell_of[i]] + a.rank_of[i]] = (int)i;
     grid.sync();
 
     // ---- 4. final slot = rank by atom index inside the cell (nothing depends on how the atomics
     //         resolved); write the records ----
-    for (int64_t p = gtid; p < a.n; p += gthreads) {
+    for (int64_t p = gtid; p < n; p += gthreads) {
         const int i = a.order_tmp[p];
         const int cell = a.cell_of[i];
         const int lo = a.starts[cell], hi = a.starts[cell + 1];
         int rank = 0;
-        for (int q = lo; q < hi; ++q) rank += a.order_tmp[q] < i;
+        if (a.gid) {  // local indices are arbitrary on a slab: order by the global atom index
+            const int mine = a.gid[i];
+            for (int q = lo; q < hi; ++q) rank += a.gid[a.order_tmp[q]] < mine;
+        } else {
+            for (int q = lo; q < hi; ++q) rank += a.order_tmp[q] < i;
+        }
         const int t = lo + rank;
         const double4 w = a.wrapped[i];
         a.order[t] = i;
@@ -400,13 +412,18 @@ __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
     const NlGrid &g = a.grid;
     const int tid = threadIdx.x;
     const int64_t gthreads = (int64_t)gridDim.x * kNlThreads;
-    const bool whole = a.first == 0 && a.count == a.n;
+    int64_t row_first = a.first, row_count = a.count;
+    if (a.row_cell_hi > 0) {  // slab runs: the rows are the slots of a range of cells, known only after binning
+        row_first = a.starts[a.row_cell_lo];
+        row_count = a.starts[a.row_cell_hi] - row_first;
+    }
+    const bool whole = a.row_cell_hi == 0 && a.first == 0 && a.count == a.n;
     const float lx = (float)g.len[0], ly = (float)g.len[1], lz = (float)g.len[2];
     const float reach2 = a.reach2f;
     const int cap = a.cap;
-    for (int64_t row = (int64_t)blockIdx.x * kNlThreads + tid; row < a.count; row += gthreads) {
-        const int slot = whole ? (int)row : (a.row_mode ? (int)(a.first + row) : a.slot_of[a.first + row]);
-        const int atom = (whole || a.row_mode) ? a.order[slot] : (int)(a.first + row);
+    for (int64_t row = (int64_t)blockIdx.x * kNlThreads + tid; row < row_count; row += gthreads) {
+        const int slot = whole ? (int)row : (a.row_mode ? (int)(row_first + row) : a.slot_of[row_first + row]);
+        const int atom = (whole || a.row_mode) ? a.order[slot] : (int)(row_first + row);
         const float *xf = reinterpret_cast<const float *>(a.xbf);
         const float mex = xf[pair_index(slot, 0)], mey = xf[pair_index(slot, 1)], mez = xf[pair_index(slot, 2)];
         const int cell = a.cell_of[atom];
@@ -557,7 +574,18 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
 #pragma unroll
     for (int w = 0; w < 6; ++w) s_w[w][tid] = 0.0;
     const int l = tid % G, grp = tid / G;
-    const bool whole = EPI ? false : (a.first == 0 && a.count == a.n);
+    int64_t row_first = a.first, row_count = a.count;
+    if (a.row_cell_hi > 0) {  // slab runs: see nl_list_kernel
+        row_first = a.starts[a.row_cell_lo];
+        row_count = a.starts[a.row_cell_hi] - row_first;
+    }
+    // EPI = 2: which of this rank's slots are copied to which slots of the two neighbouring ranks
+    int halo_lo_begin = 0, halo_lo_end = 0, halo_dest_lo = 0, halo_hi_begin = 0, halo_dest_hi = 0;
+    if (EPI == 2) {
+        halo_lo_begin = a.halo[0]; halo_lo_end = a.halo[1]; halo_dest_lo = a.halo[2];
+        halo_hi_begin = a.halo[3]; halo_dest_hi = a.halo[5];
+    }
+    const bool whole = EPI ? false : (a.row_cell_hi == 0 && a.first == 0 && a.count == a.n);
     const int ntypes = a.ntypes;
     if (!SINGLE) {
         for (int k = tid; k < 6 * kMaxT2; k += kNlThreads) s_tab[k] = a.tab.c[k / kMaxT2][k % kMaxT2];
@@ -594,8 +622,8 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
     auto fetch = [&](int64_t base) {
         Row r;
         const int64_t row = base + grp;
-        r.valid = row < a.count;
-        r.slot = !r.valid ? 0 : (whole ? (int)row : ((EPI || a.row_mode) ? (int)(a.first + row) : a.slot_of[a.first + row]));
+        r.valid = row < row_count;
+        r.slot = !r.valid ? 0 : (whole ? (int)row : ((EPI || a.row_mode) ? (int)(row_first + row) : a.slot_of[row_first + row]));
         r.me = a.xs[r.slot];
         r.nn = r.valid ? a.nneigh[row] : 0;
         // first entries of the row, whatever its length (cap >= 16: in bounds; unused words are never dereferenced)
@@ -607,9 +635,9 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
     // block-uniform trip count: the group shuffles below need every lane of the warp in the loop
     const int64_t stride = (int64_t)gridDim.x * kRowsPerBlock;
     Row next = fetch((int64_t)blockIdx.x * kRowsPerBlock);
-    for (int64_t base = (int64_t)blockIdx.x * kRowsPerBlock; base < a.count; base += stride) {
+    for (int64_t base = (int64_t)blockIdx.x * kRowsPerBlock; base < row_count; base += stride) {
         const Row cur = next;
-        if (base + stride < a.count) next = fetch(base + stride);
+        if (base + stride < row_count) next = fetch(base + stride);
         const int64_t row = base + grp;
         const bool valid = cur.valid;
         const int slot = cur.slot, nn = cur.nn;
@@ -736,7 +764,7 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
         } else {
             // list capacity exceeded at build time: walk the build-time cells (every pair now inside
             // rcut was inside rcut + skin then, hence in this stencil)
-            const int cell = a.cell_of[(whole || a.row_mode || EPI) ? a.order[slot] : (int)(a.first + row)];
+            const int cell = a.cell_of[(whole || a.row_mode || EPI) ? a.order[slot] : (int)(row_first + row)];
             const int c0 = cell % a.grid.nc[0], c1 = (cell / a.grid.nc[0]) % a.grid.nc[1],
                       c2 = cell / (a.grid.nc[0] * a.grid.nc[1]);
             for_each_run<DIM>(a.grid, a.starts, c0, c1, c2, [&](int jbegin, int jend, int code) {
@@ -779,7 +807,12 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
                 const double by = __shfl_sync(0xffffffffu, bk, base + (DIM > 1 ? 1 : 0));
                 const double bz = __shfl_sync(0xffffffffu, bk, base + (DIM > 2 ? 2 : 0));
                 if (l == 0 && valid) {
-                    a.xs_next[slot] = make_double4(x, DIM > 1 ? ry : 0.0, DIM > 2 ? rz : 0.0, me.w);
+                    const double4 rec = make_double4(x, DIM > 1 ? ry : 0.0, DIM > 2 ? rz : 0.0, me.w);
+                    a.xs_next[slot] = rec;
+                    if (EPI == 2) {  // boundary layers: the neighbours keep copies (peer stores over NVLink)
+                        if (slot < halo_lo_end) a.peer_lo_next[halo_dest_lo + (slot - halo_lo_begin)] = rec;
+                        if (slot >= halo_hi_begin) a.peer_hi_next[halo_dest_hi + (slot - halo_hi_begin)] = rec;
+                    }
                     double r = (x - bk) * (x - bk);
                     if (DIM > 1) r = fma(ry - by, ry - by, r);
                     if (DIM > 2) r = fma(rz - bz, rz - bz, r);
@@ -789,7 +822,7 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
         }
         if (l == 0 && valid) {
             if (!EPI && (flags & TMD_WANT_F)) {
-                const int atom = a.row_mode ? slot : (whole ? a.order[slot] : (int)(a.first + row));
+                const int atom = a.row_mode ? slot : (whole ? a.order[slot] : (int)(row_first + row));
                 double *dst = a.force + (int64_t)atom * DIM;
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) dst[k] = (flags & TMD_ACCUMULATE) ? dst[k] + f[k] : f[k];
@@ -1251,6 +1284,11 @@ static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double
     a.md_rebuild = 0;
     a.pos_w = a.vel_w = nullptr;
     a.imass = nullptr;
+    a.dyn = nullptr;
+    a.row_cell_lo = a.row_cell_hi = 0;
+    a.gid = nullptr;
+    a.halo = nullptr;
+    a.peer_lo_next = a.peer_hi_next = nullptr;
     {
         const size_t cells1 = (size_t)nl->cap_cells + 1;
         const size_t chunks = ((size_t)nl->cap_cells + kScanChunk - 1) / kScanChunk;
@@ -1519,3 +1557,4 @@ int tmd_nlist_view(tmd_nlist *nl, tmd_nlist_buffers *out) {
 }
 
 }  // extern "C"
+#include "slabrun.cuh"

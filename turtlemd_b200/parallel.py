@@ -702,3 +702,275 @@ class SlabDecomposition:
         part = self.system.particles
         return tuple(m.device().cpu().numpy().reshape(self.n, self.dim) for m in (part._pos, part._vel, part._force))
 
+
+
+# ---- resident slab run (csrc/slabrun.cuh) -------------------------------------------------------------------------
+
+SR_PHASES = dict(MIGRATE=0, B0_SIGNAL=1, B0_WAIT=2, COLLECT=3, B1_SIGNAL=4, B1_WAIT=5, BUILD=6, B2_SIGNAL=7, B2_WAIT=8,
+                 TRAVERSE=9, B3_SIGNAL=10, B3_WAIT=11, PRE=12, ADVANCE=13)
+SR_ERRORS = {1: "a peer did not arrive at a barrier", 2: "an atom left its slab by more than one layer between two rebuilds",
+             4: "migrant inbox full", 8: "ghost inbox full", 16: "own-atom capacity exceeded",
+             32: "own + ghost capacity exceeded", 64: "a ghost layer does not match its owner's layer"}
+
+
+def _sr_error_text(bits: int) -> str:
+    return "; ".join(text for bit, text in SR_ERRORS.items() if bits & bit) or "ok"
+
+
+class _SlabRunRank:
+    """One rank's ``tmd_slabrun`` handle plus the replicated device arrays it loads from / exports to."""
+
+    def __init__(self, system, integrator, world: int, rank: int):
+        if not isinstance(integrator, VelocityVerlet):
+            raise NotImplementedError("the resident slab run integrates with VelocityVerlet")
+        pots = system.potentials
+        if len(pots) != 1 or not isinstance(pots[0], LennardJonesCut):
+            raise NotImplementedError("the resident slab run steps systems with a single LennardJonesCut potential")
+        _device.require_cuda()
+        self.system, self.integrator, self.pot = system, integrator, pots[0]
+        self.world, self.rank = world, rank
+        part = system.particles
+        self.n, self.dim = part._pos.shape
+        if self.dim != 3:
+            raise NotImplementedError("the resident slab run needs a three-dimensional system")
+        box = system.box.to_abi()
+        if not isinstance(box, _lib.Box):
+            raise NotImplementedError("the resident slab run needs an orthogonal, fully periodic Box")
+        types, table, tidx = self.pot._tables(part)
+        self._table = np.ascontiguousarray(table, dtype=np.float64)
+        self._tidx = part._static_device(f"lj_tidx_{id(self.pot)}", tidx, np.int32) if len(types) > 1 else None
+        self.handle = C.c_void_p()
+        _lib.call("tmd_slabrun_create", C.byref(self.handle), world, rank, self.n, C.byref(box), _lib.hptr(self._table),
+                  len(types), float(self.pot.skin), float(integrator.timestep))
+        ptr, size = C.c_void_p(), C.c_size_t()
+        _lib.call("tmd_slabrun_window", self.handle, C.byref(ptr), C.byref(size))
+        self.window, self.window_bytes = ptr.value, size.value
+        self._vw = _device.zeros(10)
+
+    def connect(self, windows: list[int]) -> None:
+        arr = (C.c_void_p * self.world)(*windows)
+        _lib.call("tmd_slabrun_connect", self.handle, arr)
+
+    def load(self) -> None:
+        """Slabs, ghost layers and lists from the replicated arrays of ``system.particles`` (forces must be valid)."""
+        part = self.system.particles
+        pos, vel, force = part._pos.device(), part._vel.device(), part._force.device()
+        _lib.call("tmd_slabrun_load", self.handle, _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
+                  _device.dptr(part._imass_device()), _device.dptr(self._tidx) if self._tidx is not None else None,
+                  _device.stream_ptr())
+
+    def phase(self, name: str, last: int = 0) -> None:
+        _lib.call("tmd_slabrun_phase", self.handle, SR_PHASES[name], last, _device.stream_ptr())
+
+    def export(self):
+        """(pos, vel, force) torch tensors of n x 3 with this rank's atoms filled in and zeros elsewhere, vw share."""
+        pos, vel, force = (_device.zeros(self.n * 3) for _ in range(3))
+        _lib.call("tmd_slabrun_export", self.handle, _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
+                  _device.dptr(self._vw), _device.stream_ptr())
+        return pos, vel, force, self._vw
+
+    def status(self) -> dict:
+        err, n_own, builds = C.c_int32(), C.c_int64(), C.c_int64()
+        layers = (C.c_int32 * 2)()
+        _lib.call("tmd_slabrun_status", self.handle, C.byref(err), C.byref(n_own), C.byref(builds), layers)
+        return {"err": err.value, "error": _sr_error_text(err.value), "n_own": n_own.value, "builds": builds.value,
+                "layers_per_rank": layers[0], "layers": layers[1]}
+
+    def destroy(self) -> None:
+        if self.handle:
+            _lib.call("tmd_slabrun_destroy", self.handle)
+            self.handle = C.c_void_p()
+
+
+class SlabRun:
+    """One LJ system stepped by ``world`` GPUs, each owning a slab of cell layers, without leaving the device:
+    per step ONE traversal kernel (forces + kick + kick + drift + the records of the next step, the boundary
+    layers stored straight into the neighbours' memory) and ONE barrier kernel; list rebuilds, atom migration
+    and ghost layers are gated launches decided on the device.  See ``csrc/slabrun.cuh``.
+
+    ``system`` is the full system on every rank with valid forces (``system.potential_and_force()``).
+    ``run(k)`` = k VelocityVerlet steps (integrators.py:84-94); afterwards ``gather_state()`` returns the whole
+    system.  The trajectory equals the single-GPU one up to summation order."""
+
+    def __init__(self, system, integrator, group=None):
+        import torch.distributed as dist
+
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.system = system
+        self.r = _SlabRunRank(system, integrator, self.world, self.rank)
+        self.n = self.r.n
+        self._peers = []
+        self._graph = None
+        self._graph_launches = 0
+        self.steps_done = 0
+
+    def prepare(self) -> None:
+        import torch.distributed as dist
+
+        handle = (C.c_ubyte * 64)()
+        _lib.call("tmd_ipc_get_handle", C.c_void_p(self.r.window), handle)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, bytes(handle), group=self.group)
+        windows = []
+        for rank, blob in enumerate(everyone):
+            if rank == self.rank:
+                windows.append(self.r.window)
+                continue
+            ptr = C.c_void_p()
+            _lib.call("tmd_ipc_open_handle", (C.c_ubyte * 64).from_buffer_copy(blob), C.byref(ptr))
+            self._peers.append(ptr)
+            windows.append(ptr.value)
+        self.r.connect(windows)
+        self.r.load()
+        _device.synchronize()
+        dist.barrier(group=self.group)  # every rank's lists exist before anybody's halo stores arrive
+
+    def _step(self, last: int) -> None:
+        _lib.call("tmd_slabrun_step", self.r.handle, last, _device.stream_ptr())
+
+    def capture(self) -> bool:
+        """Two consecutive steps (both buffer parities) in one CUDA graph; ``run`` replays it."""
+        if self._graph is not None:
+            return True
+        torch = _device.torch()
+        # warm-up outside the graph: module load, occupancy queries
+        _lib.call("tmd_slabrun_start", self.r.handle, _device.stream_ptr())
+        for _ in range(2):
+            self._step(0)
+        self._step(1)
+        self.steps_done += 3
+        torch.cuda.synchronize()
+        _lib.call("tmd_slabrun_start", self.r.handle, _device.stream_ptr())
+        graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        try:
+            with torch.cuda.graph(graph):
+                self._step(0)
+                self._step(0)
+        except Exception:  # noqa: BLE001 - capture is an optimisation; eager stepping stays correct
+            torch.cuda.synchronize()
+            self._open = True
+            return False
+        self._graph_launches = _lib.launch_count() - before
+        _lib.add_launches(-self._graph_launches)
+        self._graph = graph
+        self._open = True  # start() has been enqueued: the next run continues from it
+        return True
+
+    _open = False
+
+    def run(self, steps: int) -> None:
+        """``steps`` VelocityVerlet steps; velocities and positions are at the same time afterwards."""
+        if steps < 1:
+            return
+        if not self._open:
+            _lib.call("tmd_slabrun_start", self.r.handle, _device.stream_ptr())
+        self._open = False
+        todo = steps - 1
+        if self._graph is not None:
+            while todo >= 2:
+                self._graph.replay()
+                _lib.add_launches(self._graph_launches)
+                todo -= 2
+        for _ in range(todo):
+            self._step(0)
+        self._step(1)
+        self.steps_done += steps
+
+    def status(self) -> dict:
+        return self.r.status()
+
+    def reduce_observables(self):
+        import torch.distributed as dist
+
+        vw = self.r._vw.clone()
+        dist.all_reduce(vw, group=self.group)
+        host = vw.cpu().numpy()
+        return float(host[0]), host[1:].reshape(3, 3).copy()
+
+    def gather_state(self):
+        """(pos, vel, force) of the whole system in atom order as host arrays on every rank."""
+        import torch.distributed as dist
+
+        pos, vel, force, vw = self.r.export()
+        for t in (pos, vel, force):
+            dist.all_reduce(t, group=self.group)  # every atom is owned by exactly one rank, the others hold zeros
+        status = self.status()
+        if status["err"]:
+            raise RuntimeError(f"rank {self.rank}: slab run failed: {status['error']}")
+        return tuple(t.cpu().numpy().reshape(self.n, 3) for t in (pos, vel, force))
+
+    def release(self) -> None:
+        _device.torch().cuda.synchronize()
+        self._graph = None
+        for ptr in self._peers:
+            _lib.call("tmd_ipc_close_handle", ptr)
+        self._peers = []
+        self.r.destroy()
+
+
+class SlabRunEmulation:
+    """``world`` slab-run ranks on ONE GPU, stepped phase by phase in one stream (the signal halves of a barrier
+    for all ranks, then the wait halves): the data path of :class:`SlabRun` -- migration, ghost layers, halo
+    stores into the neighbours' buffers, gate words -- without a second device.  For tests."""
+
+    def __init__(self, systems, integrator):
+        self.world = len(systems)
+        self.ranks = [_SlabRunRank(system, integrator, self.world, r) for r, system in enumerate(systems)]
+        windows = [r.window for r in self.ranks]
+        for r in self.ranks:
+            r.connect(windows)
+            r.load()
+        self.n = self.ranks[0].n
+        self._open = False
+
+    def _all(self, name: str, last: int = 0) -> None:
+        for r in self.ranks:
+            r.phase(name, last)
+
+    def _start(self) -> None:
+        self._all("B2_SIGNAL", 1)
+        self._all("B2_WAIT", 1)
+        self._all("PRE")
+        self._all("B3_SIGNAL")
+        self._all("B3_WAIT")
+        self._all("ADVANCE")
+
+    def _step(self, last: int) -> None:
+        for name in ("MIGRATE", "B0_SIGNAL", "B0_WAIT", "COLLECT", "B1_SIGNAL", "B1_WAIT", "BUILD", "B2_SIGNAL", "B2_WAIT"):
+            self._all(name)
+        self._all("TRAVERSE", last)
+        self._all("B3_SIGNAL")
+        self._all("B3_WAIT")
+        self._all("ADVANCE", last)
+
+    def run(self, steps: int) -> None:
+        if steps < 1:
+            return
+        self._start()
+        for _ in range(steps - 1):
+            self._step(0)
+        self._step(1)
+
+    def gather_state(self):
+        total = None
+        vw = np.zeros(10)
+        for r in self.ranks:
+            pos, vel, force, share = r.export()
+            parts = [t.cpu().numpy().reshape(self.n, 3) for t in (pos, vel, force)]
+            total = parts if total is None else [a + b for a, b in zip(total, parts)]
+            vw += share.cpu().numpy()
+            status = r.status()
+            if status["err"]:
+                raise RuntimeError(f"emulated rank {r.rank}: slab run failed: {status['error']}")
+        return total[0], total[1], total[2], float(vw[0]), vw[1:].reshape(3, 3).copy()
+
+    def status(self):
+        return [r.status() for r in self.ranks]
+
+    def release(self) -> None:
+        _device.synchronize()
+        for r in self.ranks:
+            r.destroy()
