@@ -262,11 +262,27 @@ def bench_lj(args, cfg, rank, world, extras=True):
     pos, vel, size, n, describe, make = build_lj(cfg, args.skin)
     system, integ, pot = make()
     graphed, parallelism, stepper, decomp = False, "single GPU", None, None
+    resident = False  # SlabRun: run(k) instead of step()
     if world > 1 or os.environ.get("TMD_BENCH_DECOMP") in ("slab1", "atoms1"):
-        from turtlemd_b200.parallel import AtomDecomposition, SlabDecomposition
+        from turtlemd_b200.parallel import AtomDecomposition, SlabDecomposition, SlabRun
 
-        decomp = os.environ.get("TMD_BENCH_DECOMP", "atoms")
-        if decomp in ("slab", "slab1") and cfg["method"] == "nlist" and not cfg.get("dimer"):
+        simple = cfg["method"] == "nlist" and not cfg.get("dimer") and cfg.get("integrator") != "langevin"
+        decomp = os.environ.get("TMD_BENCH_DECOMP", "slabrun" if simple and world > 1 else "atoms")
+        if decomp == "slabrun" and simple and world > 1:
+            try:
+                system.evaluate(7)  # the run starts from valid forces, like VelocityVerlet.run
+                stepper = SlabRun(system, integ)
+                stepper.prepare()
+                resident = True
+                st = stepper.status()
+                parallelism = (f"resident slab run x{world}: {st['layers_per_rank']} of {st['layers']} cell layers per rank, "
+                               "boundary records stored into the neighbours' buffers by the traversal epilogue (peer "
+                               "memory over NVLink), one device-side barrier per step, rebuilds / migration gated on "
+                               "the device; no NCCL call inside a step")
+            except NotImplementedError:
+                stepper = None  # fewer than two cell layers per rank: replicate positions instead
+                system, integ, pot = make()
+        if decomp in ("slab", "slab1") and simple:
             try:
                 stepper = SlabDecomposition(system, integ)
                 stepper.prepare()
@@ -280,16 +296,19 @@ def bench_lj(args, cfg, rank, world, extras=True):
             stepper = AtomDecomposition(system, integ)
             stepper.prepare()
             parallelism = f"atom-decomposition x{world}, NCCL all-gather of positions"
-        step = stepper.step
+        step = stepper.step if not resident else None
     else:
         system.evaluate(7)
         step = lambda: integ(system)  # noqa: E731
     clocks = args.clocks
     if stepper is not None:
         graphed = stepper.capture() if os.environ.get("TMD_BENCH_GRAPH", "1") == "1" else False
-        parallelism += ", step replayed from CUDA graphs" if graphed else ", step launched eagerly"
-        for _ in range(args.warmup):
-            step()
+        parallelism += ", steps replayed from CUDA graphs" if graphed else ", steps launched eagerly"
+        if resident:
+            stepper.run(max(args.warmup, 2))
+        else:
+            for _ in range(args.warmup):
+                step()
     elif args.warmup > 0:
         integ.run(system, args.warmup)  # the entry point that is timed below (allocations, first list build, module load)
     clocks.mark()
@@ -299,6 +318,9 @@ def bench_lj(args, cfg, rank, world, extras=True):
         # update of the next one are a single pass over the state (same roundings, same trajectory)
         sec = timed(lambda: integ.run(system, args.steps), 1, world)
         parallelism += f", {type(integ).__name__}.run(system, {args.steps})"
+    elif resident:
+        sec = timed(lambda: stepper.run(args.steps), 1, world)
+        parallelism += f", SlabRun.run({args.steps})"
     else:
         sec = timed(step, args.steps, world)
     launches = _lib.launch_count() - launches0
@@ -326,6 +348,8 @@ def bench_lj(args, cfg, rank, world, extras=True):
         more = max(50, min(20000, int((1.5 if extras else 0.5) / (sec / args.steps))))
         if stepper is None:
             integ.run(system, more)
+        elif resident:
+            stepper.run(more)
         else:
             for _ in range(more):
                 step()
@@ -335,9 +359,21 @@ def bench_lj(args, cfg, rank, world, extras=True):
     if stepper is not None:
         if world > 1 and extras and not args.quick:
             out["parity"] = parity_lj(stepper, make, stepper.steps_done, rank)
-            out["e2e"] = e2e_decomposed(stepper, system, n, cfg, world, args)
+            if resident:
+                out["slab_run"] = stepper.status()
         load_for_clocks()
         out["clocks"] = clocks.summary()
+        if resident and world > 1 and extras and not args.quick:
+            # end to end with host buffers: through the atom decomposition, whose state is the plain atom-ordered
+            # arrays a host shard can be copied into (the resident run keeps its state in cell order on the device)
+            stepper.release()
+            system2, integ2, _ = make()
+            stepper = AtomDecomposition(system2, integ2)
+            stepper.prepare()
+            stepper.capture()
+            out["e2e"] = e2e_decomposed(stepper, system2, n, cfg, world, args)
+        elif world > 1 and extras and not args.quick:
+            out["e2e"] = e2e_decomposed(stepper, system, n, cfg, world, args)
         stepper.release()
         return out if rank == 0 else None
 

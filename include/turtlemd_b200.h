@@ -234,6 +234,9 @@ int tmd_slabrun_load(tmd_slabrun *sr, const double *pos, const double *vel, cons
                      const int32_t *tidx, tmd_stream_t stream);
 int tmd_slabrun_start(tmd_slabrun *sr, tmd_stream_t stream);
 int tmd_slabrun_step(tmd_slabrun *sr, int32_t last, tmd_stream_t stream);
+/* start + steps - 1 full steps + one closing step; use_graph: pairs of steps replayed from a CUDA graph whose
+ * rebuild launches sit in conditional IF nodes (a step without a rebuild is two kernels)             */
+int tmd_slabrun_run(tmd_slabrun *sr, int32_t steps, int32_t use_graph, int64_t *graph_launches, tmd_stream_t stream);
 int tmd_slabrun_phase(tmd_slabrun *sr, int32_t phase, int32_t last, tmd_stream_t stream);
 int tmd_slabrun_export(tmd_slabrun *sr, double *pos, double *vel, double *force, double *vw, tmd_stream_t stream);
 int tmd_slabrun_status(tmd_slabrun *sr, int32_t *err, int64_t *n_own, int64_t *builds, int32_t *layers);

@@ -1,0 +1,14 @@
+set -u
+OUT=gpurun_out; mkdir -p $OUT
+N=${1:-2}
+for W in lj1m; do
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29561 bench.py --gpus $N --workload $W > $OUT/r02g_bench_${W}_g$N.json 2> $OUT/r02g_bench_${W}_g$N.err; echo "$W rc=$?"
+  python - <<PY
+import json
+try:
+    d=json.loads(open("$OUT/r02g_bench_${W}_g$N.json").read().strip().splitlines()[-1])
+    print("$W", "value=%.4g"%d["value"], "ms=%.4f"%d["ms_per_step"], "launches", d["gpu_launches"], "\n parity=", d.get("parity"), "\n e2e=", (d.get("e2e") or {}).get("value"), d["clocks"].get("sm_mhz"), d["clocks"].get("samples"), "\n", d["config"]["parallelism"], "\n", d.get("slab_run"))
+except Exception as e:
+    print("$W FAILED", e); print(open("$OUT/r02g_bench_${W}_g$N.err").read()[-2500:])
+PY
+done

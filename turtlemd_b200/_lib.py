@@ -129,6 +129,7 @@ PROTOTYPES = {
     "tmd_slabrun_load": [_P, _P, _P, _P, _P, _P, _P],
     "tmd_slabrun_start": [_P, _P],
     "tmd_slabrun_step": [_P, _I32, _P],
+    "tmd_slabrun_run": [_P, _I32, _I32, C.POINTER(_I64), _P],
     "tmd_slabrun_phase": [_P, _I32, _I32, _P],
     "tmd_slabrun_export": [_P, _P, _P, _P, _P, _P],
     "tmd_slabrun_status": [_P, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I32)],

@@ -66,6 +66,8 @@ int arena_get(ArenaSlot slot, size_t bytes, void **ptr);
 int num_sms();
 // every kernel launch of the library goes through this (tmd_launch_count: bench.py's gpu_launches)
 void count_launch();
+long long launch_count_value();
+void add_launches_value(long long delta);  // recording a CUDA graph is not launching: take the count back
 
 static inline cudaStream_t as_stream(tmd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

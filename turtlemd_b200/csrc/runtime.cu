@@ -41,6 +41,8 @@ int require_device() {
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count_value() { return g_launches.load(std::memory_order_relaxed); }
+void add_launches_value(long long delta) { g_launches.fetch_add(delta, std::memory_order_relaxed); }
 
 // ---- arena ---------------------------------------------------------------------------------
 struct Arena {

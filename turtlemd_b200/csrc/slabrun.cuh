@@ -287,6 +287,8 @@ struct SrBarrier {
     int *local_flag;                          // kind 3: raised by this rank's epilogues
     int *gate_out;                            // kind 3: the OR over all ranks, the gate of the next step's rebuild
     int *builds;                              // nlflags of the list handle ([2] builds)
+    cudaGraphConditionalHandle cond;          // kind 3 inside a CUDA graph: the IF node around the next step's rebuild
+    int has_cond;
 };
 
 __global__ void sr_barrier_kernel(const SrBarrier b) {
@@ -341,6 +343,7 @@ __global__ void sr_barrier_kernel(const SrBarrier b) {
                 if (b.below.info[3] != b.halo[1] - b.halo[0] || b.above.info[2] != b.halo[4] - b.halo[3])
                     atomicOr(b.self.err, SR_ERR_LAYER);
             } else if (b.kind == 3) {
+                if (b.has_cond) cudaGraphSetConditional(b.cond, flag ? 1u : 0u);
                 *b.gate_out = flag;
                 *b.local_flag = 0;
                 b.cnt->stay = 0;
@@ -349,6 +352,11 @@ __global__ void sr_barrier_kernel(const SrBarrier b) {
             }
         }
     }
+}
+
+// first node of a step graph: the IF node around the first step's rebuild takes the gate the previous launch left
+__global__ void sr_cond_kernel(cudaGraphConditionalHandle cond, const int *gate) {
+    cudaGraphSetConditional(cond, *gate != 0 ? 1u : 0u);
 }
 
 // ---- before the first step: opening half kick + drift (integrators.py:88-90), the records the first traversal
@@ -419,6 +427,11 @@ struct tmd_slabrun {
     int connected, loaded;
     int64_t step;         // host-side: steps enqueued so far (buffer and gate parity)
     int p;                // record buffer the next traversal reads
+    // two steps as one CUDA graph: the rebuild of each sits in an IF node decided on the device
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    cudaStream_t capture_stream[2];
+    int graph_failed;
 };
 
 namespace tmd {
@@ -456,11 +469,14 @@ static bool sr_make_grid(const tmd_box *box, double reach, int64_t n, int world,
     return true;
 }
 
-static void sr_launch_barrier(tmd_slabrun *sr, int kind, int mode, const int *gate, cudaStream_t st) {
+static void sr_launch_barrier(tmd_slabrun *sr, int kind, int mode, const int *gate, cudaStream_t st,
+                              const cudaGraphConditionalHandle *cond = nullptr) {
     SrBarrier b = sr->bar;
     b.kind = kind;
     b.mode = mode;
     b.gate = gate;
+    b.has_cond = cond != nullptr;
+    if (cond) b.cond = *cond;
     if (kind == 3) {
         const int g = (int)(sr->step & 1);
         b.local_flag = sr->local_flag;
@@ -483,6 +499,10 @@ enum {
 
 int tmd_slabrun_destroy(tmd_slabrun *sr) {
     if (!sr) return TMD_OK;
+    if (sr->exec) cudaGraphExecDestroy(sr->exec);
+    if (sr->graph) cudaGraphDestroy(sr->graph);
+    for (int k = 0; k < 2; ++k)
+        if (sr->capture_stream[k]) cudaStreamDestroy(sr->capture_stream[k]);
     cudaFree(sr->window);
     cudaFree(sr->priv);
     delete sr;
@@ -838,6 +858,106 @@ int tmd_slabrun_step(tmd_slabrun *sr, int32_t last, tmd_stream_t stream) {
     sr_launch_barrier(sr, 3, 3, nullptr, st);
     TMD_CUDA(cudaGetLastError());
     return tmd_slabrun_phase(sr, TMD_SR_ADVANCE, last, stream);
+}
+
+// the launches of one rebuild, ungated (inside the IF node of a step graph the decision has been taken)
+static int sr_rebuild_ungated(tmd_slabrun *sr, cudaStream_t st) {
+    SrArgs s = sr->s;
+    s.gate = nullptr;
+    const int ob = (int)((s.cap_own + 255) / 256);
+    ::tmd::count_launch(), sr_migrate_kernel<<<ob, 256, 0, st>>>(s);
+    sr_launch_barrier(sr, 0, 3, nullptr, st);
+    ::tmd::count_launch(), sr_collect_kernel<<<ob, 256, 0, st>>>(s);
+    sr_launch_barrier(sr, 1, 3, nullptr, st);
+    TMD_CHECK(sr_build(sr, nullptr, 0, st));
+    sr_launch_barrier(sr, 2, 3, nullptr, st);
+    TMD_CUDA(cudaGetLastError());
+    return TMD_OK;
+}
+
+// Two steps (gate words 0 and 1, record buffers 0 and 1: where every run starts) as one CUDA graph.  The nine
+// launches of a rebuild sit in a conditional IF node per step; its condition is set on the device, by the step
+// barrier of the step before (or, for the first step of a launch, by a one-thread kernel that reads the gate word
+// the previous launch left).  A step without a rebuild is then two kernels: traversal and barrier.
+static int sr_build_graph(tmd_slabrun *sr) {
+    for (int k = 0; k < 2; ++k)
+        if (!sr->capture_stream[k]) TMD_CUDA(cudaStreamCreateWithFlags(&sr->capture_stream[k], cudaStreamNonBlocking));
+    cudaStream_t cs = sr->capture_stream[0], bs = sr->capture_stream[1];
+    const int64_t step0 = sr->step;
+    const int p0 = sr->p;
+    TMD_REQUIRE(sr->p == 0 && (sr->step & 1) == 0, "a step graph is recorded right after tmd_slabrun_start");
+    TMD_CUDA(cudaGraphCreate(&sr->graph, 0));
+    cudaGraphConditionalHandle cond[2];
+    for (int k = 0; k < 2; ++k) TMD_CUDA(cudaGraphConditionalHandleCreate(&cond[k], sr->graph, 0, cudaGraphCondAssignDefault));
+    const long long launches0 = launch_count_value();
+    int status = TMD_OK;
+    TMD_CUDA(cudaStreamBeginCaptureToGraph(cs, sr->graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    sr_cond_kernel<<<1, 1, 0, cs>>>(cond[0], sr->gates + 0);
+    for (int k = 0; k < 2 && status == TMD_OK; ++k) {
+        // ---- IF (rebuild) ----
+        cudaStreamCaptureStatus cstat;
+        cudaGraph_t cg;
+        const cudaGraphNode_t *deps;
+        size_t ndeps;
+        if (cudaStreamGetCaptureInfo_v2(cs, &cstat, nullptr, &cg, &deps, &ndeps) != cudaSuccess) { status = TMD_ERR_CUDA; break; }
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = cond[k];
+        np.conditional.type = cudaGraphCondTypeIf;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        if (cudaGraphAddNode(&node, cg, deps, ndeps, &np) != cudaSuccess) { status = TMD_ERR_CUDA; break; }
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        if (cudaStreamUpdateCaptureDependencies(cs, &node, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) { status = TMD_ERR_CUDA; break; }
+        if (cudaStreamBeginCaptureToGraph(bs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { status = TMD_ERR_CUDA; break; }
+        status = sr_rebuild_ungated(sr, bs);
+        if (cudaStreamEndCapture(bs, nullptr) != cudaSuccess) status = TMD_ERR_CUDA;
+        if (status != TMD_OK) break;
+        // ---- traversal + step barrier (which decides the next IF) ----
+        status = sr_traverse(sr, 0, cs);
+        sr_launch_barrier(sr, 3, 3, nullptr, cs, k == 0 ? &cond[1] : nullptr);
+        sr->p ^= 1;
+        sr->step += 1;
+    }
+    cudaGraph_t done = nullptr;
+    if (cudaStreamEndCapture(cs, &done) != cudaSuccess) status = TMD_ERR_CUDA;
+    sr->step = step0;  // recording is not stepping
+    sr->p = p0;
+    add_launches_value(launches0 - launch_count_value());
+    if (status == TMD_OK && cudaGraphInstantiate(&sr->exec, sr->graph, 0) != cudaSuccess) status = TMD_ERR_CUDA;
+    if (status != TMD_OK) {
+        cudaGetLastError();
+        if (sr->graph) cudaGraphDestroy(sr->graph);
+        sr->graph = nullptr;
+        sr->exec = nullptr;
+        sr->graph_failed = 1;
+        set_error("tmd_slabrun: recording the step graph failed; stepping eagerly");
+    }
+    return status;
+}
+
+/* `steps` VelocityVerlet steps (integrators.py:84-94) on a real rank: start, steps - 1 full steps (pairs of them
+ * replayed from the step graph when use_graph != 0), one closing step.  Positions and velocities are at the same
+ * time afterwards.  graph_launches (optional) = kernels launched through graph replays (the library's launch
+ * counter only sees direct launches). */
+int tmd_slabrun_run(tmd_slabrun *sr, int32_t steps, int32_t use_graph, int64_t *graph_launches, tmd_stream_t stream) {
+    TMD_REQUIRE(sr && sr->loaded, "load the system first");
+    TMD_REQUIRE(steps >= 1, "steps must be >= 1");
+    cudaStream_t st = as_stream(stream);
+    if (graph_launches) *graph_launches = 0;
+    TMD_CHECK(tmd_slabrun_start(sr, stream));
+    int todo = steps - 1;
+    if (use_graph && todo >= 2 && !sr->exec && !sr->graph_failed) sr_build_graph(sr);  // failure: eager steps below
+    if (use_graph && sr->exec) {
+        while (todo >= 2) {
+            TMD_CUDA(cudaGraphLaunch(sr->exec, st));
+            sr->step += 2;  // (the buffer parity is back where it was)
+            todo -= 2;
+            if (graph_launches) *graph_launches += 5;  // a pair without rebuild: condition, 2 traversals, 2 barriers
+        }
+    }
+    for (; todo > 0; --todo) TMD_CHECK(tmd_slabrun_step(sr, 0, stream));
+    return tmd_slabrun_step(sr, 1, stream);
 }
 
 /* own atoms -> their entries of the atom-ordered arrays (n_global x 3; other entries untouched); vw[10] = this

@@ -802,8 +802,6 @@ class SlabRun:
         self.r = _SlabRunRank(system, integrator, self.world, self.rank)
         self.n = self.r.n
         self._peers = []
-        self._graph = None
-        self._graph_launches = 0
         self.steps_done = 0
 
     def prepare(self) -> None:
@@ -827,56 +825,22 @@ class SlabRun:
         _device.synchronize()
         dist.barrier(group=self.group)  # every rank's lists exist before anybody's halo stores arrive
 
-    def _step(self, last: int) -> None:
-        _lib.call("tmd_slabrun_step", self.r.handle, last, _device.stream_ptr())
-
     def capture(self) -> bool:
-        """Two consecutive steps (both buffer parities) in one CUDA graph; ``run`` replays it."""
-        if self._graph is not None:
-            return True
-        torch = _device.torch()
-        # warm-up outside the graph: module load, occupancy queries
-        _lib.call("tmd_slabrun_start", self.r.handle, _device.stream_ptr())
-        for _ in range(2):
-            self._step(0)
-        self._step(1)
-        self.steps_done += 3
-        torch.cuda.synchronize()
-        _lib.call("tmd_slabrun_start", self.r.handle, _device.stream_ptr())
-        graph = torch.cuda.CUDAGraph()
-        before = _lib.launch_count()
-        try:
-            with torch.cuda.graph(graph):
-                self._step(0)
-                self._step(0)
-        except Exception:  # noqa: BLE001 - capture is an optimisation; eager stepping stays correct
-            torch.cuda.synchronize()
-            self._open = True
-            return False
-        self._graph_launches = _lib.launch_count() - before
-        _lib.add_launches(-self._graph_launches)
-        self._graph = graph
-        self._open = True  # start() has been enqueued: the next run continues from it
+        """Ask :meth:`run` to replay pairs of steps from the library's step graph (recorded at the first run: two
+        steps whose rebuild launches sit in conditional IF nodes decided on the device)."""
+        self.use_graph = True
         return True
 
-    _open = False
+    use_graph = False
 
     def run(self, steps: int) -> None:
         """``steps`` VelocityVerlet steps; velocities and positions are at the same time afterwards."""
         if steps < 1:
             return
-        if not self._open:
-            _lib.call("tmd_slabrun_start", self.r.handle, _device.stream_ptr())
-        self._open = False
-        todo = steps - 1
-        if self._graph is not None:
-            while todo >= 2:
-                self._graph.replay()
-                _lib.add_launches(self._graph_launches)
-                todo -= 2
-        for _ in range(todo):
-            self._step(0)
-        self._step(1)
+        replayed = C.c_int64(0)
+        _lib.call("tmd_slabrun_run", self.r.handle, steps, 1 if self.use_graph else 0, C.byref(replayed),
+                  _device.stream_ptr())
+        _lib.add_launches(replayed.value)
         self.steps_done += steps
 
     def status(self) -> dict:
@@ -904,7 +868,6 @@ class SlabRun:
 
     def release(self) -> None:
         _device.torch().cuda.synchronize()
-        self._graph = None
         for ptr in self._peers:
             _lib.call("tmd_ipc_close_handle", ptr)
         self._peers = []
