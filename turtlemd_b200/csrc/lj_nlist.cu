@@ -574,18 +574,17 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
 #pragma unroll
     for (int w = 0; w < 6; ++w) s_w[w][tid] = 0.0;
     const int l = tid % G, grp = tid / G;
-    int64_t row_first = a.first, row_count = a.count;
-    if (a.row_cell_hi > 0) {  // slab runs: see nl_list_kernel
-        row_first = a.starts[a.row_cell_lo];
-        row_count = a.starts[a.row_cell_hi] - row_first;
-    }
+    // EPI = 2 (slab runs): the rows are the slots of a range of cells, known only after binning (see nl_list_kernel);
+    // otherwise the two are kernel parameters (constant bank, no registers: this loop is at its register limit)
+    const int64_t row_first = EPI == 2 ? (int64_t)a.starts[a.row_cell_lo] : a.first;
+    const int64_t row_count = EPI == 2 ? (int64_t)(a.starts[a.row_cell_hi] - a.starts[a.row_cell_lo]) : a.count;
     // EPI = 2: which of this rank's slots are copied to which slots of the two neighbouring ranks
     int halo_lo_begin = 0, halo_lo_end = 0, halo_dest_lo = 0, halo_hi_begin = 0, halo_dest_hi = 0;
     if (EPI == 2) {
         halo_lo_begin = a.halo[0]; halo_lo_end = a.halo[1]; halo_dest_lo = a.halo[2];
         halo_hi_begin = a.halo[3]; halo_dest_hi = a.halo[5];
     }
-    const bool whole = EPI ? false : (a.row_cell_hi == 0 && a.first == 0 && a.count == a.n);
+    const bool whole = EPI ? false : (a.first == 0 && a.count == a.n);
     const int ntypes = a.ntypes;
     if (!SINGLE) {
         for (int k = tid; k < 6 * kMaxT2; k += kNlThreads) s_tab[k] = a.tab.c[k / kMaxT2][k % kMaxT2];
@@ -859,6 +858,15 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
     block_sum<10, kNlThreads>(red, s_red);
     // The block that finishes last adds up the partials of all blocks (no second launch).  The order of
     // the sum is fixed by block index and thread index, not by who arrives when: deterministic.
+    // Resident runs (EPI): nobody can look at (V, W) between the steps of a run, so only the closing step reduces
+    // them -- the reduction is a serial tail of ~10 us during which all other SMs idle.
+    if (EPI && !a.epi_last) {
+        if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) a.partial_vw[(size_t)blockIdx.x * 10 + k] = red[k];
+        }
+        return;
+    }
     __shared__ int s_last;
     if (tid == 0) {
 #pragma unroll
@@ -869,22 +877,24 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    constexpr int kLanes = kNlThreads / 10;  // 12 partial sums per component, then those in index order
-    __shared__ double s_fin[10][kLanes];
-    if (tid < 10 * kLanes) {
-        const int k = tid % 10, q = tid / 10;
-        double sum = 0.0;
-        for (int b = q; b < (int)gridDim.x; b += kLanes) sum += __ldcg(a.partial_vw + (size_t)b * 10 + k);
-        s_fin[k][q] = sum;
-    }
-    __syncthreads();
-    if (tid < 10) {
-        double sum = 0.0;
+    // thread t sums blocks t, t + 128, ... for all ten components (ten independent chains of coalesced loads),
+    // then the block sums its 128 threads in a fixed order
+    double fin[10];
 #pragma unroll
-        for (int q = 0; q < kLanes; ++q) sum += s_fin[tid][q];
-        // every pair was seen from both atoms: halve; quantities that were not asked for stay untouched
-        if (tid == 0 ? (flags & TMD_WANT_V) : (flags & TMD_WANT_W))
-            a.vw[tid] = ((flags & TMD_ACCUMULATE) ? a.vw[tid] : 0.0) + 0.5 * sum;
+    for (int k = 0; k < 10; ++k) fin[k] = 0.0;
+    for (int b = tid; b < (int)gridDim.x; b += kNlThreads) {
+        const double *src = a.partial_vw + (size_t)b * 10;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) fin[k] += __ldcg(src + k);
+    }
+    block_sum<10, kNlThreads>(fin, s_red);
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            // every pair was seen from both atoms: halve; quantities that were not asked for stay untouched
+            if (k == 0 ? (flags & TMD_WANT_V) : (flags & TMD_WANT_W))
+                a.vw[k] = ((flags & TMD_ACCUMULATE) ? a.vw[k] : 0.0) + 0.5 * fin[k];
+        }
     }
 }
 
