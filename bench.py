@@ -607,6 +607,19 @@ def bench_replicas(args, cfg, rank, world, extras=True):
                                f"with {inner} steps fused per launch the kernel is bound by the FP64 / integer work "
                                "of the noise (Philox4x64 + log / sincos), not by HBM; see DESIGN.md"}
     out["roofline"]["frac"] = out["roofline"]["achieved"] / out["roofline"]["peak"]
+    try:  # the bound ncu shows (profiles/r02p_replicas_full.txt): the instruction stream, not HBM
+        prof = json.loads((REPO / "profiles" / "traffic.json").read_text())[f"inertia_doublewell_pair_kernel<1,true>@{n}x{inner}"]
+        sm_hz = 1e6 * float((out["clocks"].get("sm_mhz") or 1965.0))
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        ideal = prof["warp_instructions"] / (sms * 4.0 * sm_hz)
+        out["roofline"]["traffic"] = prof["bytes"]
+        out["roofline"]["issue"] = {
+            "warp_instructions_per_launch": prof["warp_instructions"], "ideal_ms": ideal * 1e3,
+            "frac": ideal / (sec / args.steps),
+            "note": "instruction-issue roofline: warp instructions of one launch (ncu) / (SMs x 4 per cycle x SM clock) over the "
+                    "measured launch time; the kernel is bound by Philox4x64 integer products + FP64 log / sincos"}
+    except (OSError, ValueError, KeyError):
+        pass
     if world == 1 and not args.quick and extras:
         # e2e: host arrays in and out around every launch through the public API
         part = system.particles

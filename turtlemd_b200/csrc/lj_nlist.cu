@@ -129,6 +129,7 @@ struct tmd_nlist {
     int dim, ntypes;
     double len[3];
     double reach;
+    const int32_t *tidx;  // the type array the records were built from (types are baked into them): a rebound array rebuilds
     // device memory, owned
     int *flags;
     unsigned *entries;
@@ -1205,7 +1206,8 @@ int tmd_lj_nlist_usable(int64_t n, const tmd_box *box, const double *table, int3
 // signature check (a change forces a rebuild), pointers.  `same` = the lists of the previous call
 // are still for this system and row range.
 static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double *table, int32_t ntypes,
-                      int64_t first, int64_t count, int row_mode, cudaStream_t s, NlArgs &a, bool &same) {
+                      int64_t first, int64_t count, int row_mode, cudaStream_t s, NlArgs &a, bool &same,
+                      const int32_t *tidx_now = nullptr) {
     const int dim = box->dim;
     double rc2max = 0.0;
     TMD_CHECK(load_lj_table(table, ntypes, a.tab, rc2max));
@@ -1242,23 +1244,31 @@ static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double
         nl->cap_cells = ncells;
         const size_t n_chunks = ((size_t)ncells + kScanChunk - 1) / kScanChunk;
         const size_t n_ints = (size_t)2 * (ncells + 1) + n_chunks + (size_t)5 * n;
-        TMD_CUDA(cudaMalloc(&nl->flags, kNlFlagWords * sizeof(int)));
+        // all or nothing: a failed allocation must not leave capacities behind that a retried call would trust
+        const size_t xbf_bytes = ((size_t)(n + 1) / 2 + kChunk / 2) * 2 * sizeof(float4);
+        bool ok = cudaMalloc(&nl->flags, kNlFlagWords * sizeof(int)) == cudaSuccess &&
+                  cudaMalloc(&nl->entries, (size_t)nl->cap * count * sizeof(unsigned)) == cudaSuccess &&
+                  cudaMalloc(&nl->nneigh, (size_t)count * sizeof(int)) == cudaSuccess &&
+                  cudaMalloc(&nl->ints, n_ints * sizeof(int)) == cudaSuccess &&
+                  cudaMalloc(&nl->wrapped, (size_t)n * sizeof(double4)) == cudaSuccess &&
+                  cudaMalloc(&nl->xb, (size_t)n * sizeof(double4)) == cudaSuccess &&
+                  cudaMalloc(&nl->xbf, xbf_bytes) == cudaSuccess &&  // pair records; the list filter reads eight at a time: padded
+                  (nl->xs_ext || cudaMalloc(&nl->xs, (size_t)n * sizeof(double4)) == cudaSuccess) &&
+                  cudaMalloc(&nl->image, (size_t)n * 3 * sizeof(double)) == cudaSuccess;
+        if (!ok) {
+            cudaGetLastError();
+            nl_release(nl);
+            nl->n = -1;
+            set_error("tmd_lj_nlist: out of device memory for the neighbour list of %lld atoms", (long long)n);
+            return TMD_ERR_NOMEM;
+        }
         TMD_CUDA(cudaMemsetAsync(nl->flags, 0, kNlFlagWords * sizeof(int), s));
-        TMD_CUDA(cudaMalloc(&nl->entries, (size_t)nl->cap * count * sizeof(unsigned)));
-        TMD_CUDA(cudaMalloc(&nl->nneigh, (size_t)count * sizeof(int)));
-        TMD_CUDA(cudaMalloc(&nl->ints, n_ints * sizeof(int)));
         TMD_CUDA(cudaMemsetAsync(nl->ints, 0, n_ints * sizeof(int), s));  // counts[] must start at zero
-        TMD_CUDA(cudaMalloc(&nl->wrapped, (size_t)n * sizeof(double4)));
-        TMD_CUDA(cudaMalloc(&nl->xb, (size_t)n * sizeof(double4)));
-        // pair records (two float4 per two slots); the list filter reads eight of them at a time: pad
-        TMD_CUDA(cudaMalloc(&nl->xbf, ((size_t)(n + 1) / 2 + kChunk / 2) * 2 * sizeof(float4)));
-        TMD_CUDA(cudaMemsetAsync(nl->xbf, 0, ((size_t)(n + 1) / 2 + kChunk / 2) * 2 * sizeof(float4), s));
-        if (!nl->xs_ext) TMD_CUDA(cudaMalloc(&nl->xs, (size_t)n * sizeof(double4)));
-        TMD_CUDA(cudaMalloc(&nl->image, (size_t)n * 3 * sizeof(double)));
+        TMD_CUDA(cudaMemsetAsync(nl->xbf, 0, xbf_bytes, s));
         fresh = true;
     }
     same = !fresh && nl->n == n && nl->first == first && nl->count == count && nl->dim == dim &&
-           nl->ntypes == ntypes && nl->reach == reach && nl->row_mode == row_mode;
+           nl->ntypes == ntypes && nl->reach == reach && nl->row_mode == row_mode && nl->tidx == tidx_now;
     for (int k = 0; k < dim && same; ++k) same = nl->len[k] == box->length[k];
     if (!same) {
         nl->n = n;
@@ -1268,6 +1278,7 @@ static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double
         nl->ntypes = ntypes;
         nl->reach = reach;
         nl->row_mode = row_mode;
+        nl->tidx = tidx_now;
         for (int k = 0; k < 3; ++k) nl->len[k] = k < dim ? box->length[k] : 0.0;
         // force a build (counts[] is zero: the scan of every build re-zeroes it)
         TMD_CUDA(cudaMemsetAsync(nl->flags, 1, sizeof(int), s));
@@ -1363,7 +1374,7 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
 
     NlArgs a;
     bool same = false;
-    TMD_CHECK(nl_prepare(nl, n, box, table, ntypes, first, count, 0, s, a, same));
+    TMD_CHECK(nl_prepare(nl, n, box, table, ntypes, first, count, 0, s, a, same, ntypes > 1 ? tidx : nullptr));
     a.pos = pos;
     a.tidx = tidx;
 
@@ -1471,7 +1482,7 @@ int tmd_nlist_run_vv(tmd_nlist *nl, double *pos, double *vel, double *force, con
 
     NlArgs a;
     bool same = false;
-    TMD_CHECK(nl_prepare(nl, n, box, table, ntypes, 0, n, 0, s, a, same));
+    TMD_CHECK(nl_prepare(nl, n, box, table, ntypes, 0, n, 0, s, a, same, ntypes > 1 ? tidx : nullptr));
     a.pos = pos;
     a.tidx = tidx;
     if (nl->cap_md < nl->cap_n) {
@@ -1526,7 +1537,7 @@ int tmd_nlist_build_slots(tmd_nlist *nl, const double *pos, const int32_t *tidx,
     const int dim = box->dim;
     NlArgs a;
     bool same = false;
-    TMD_CHECK(nl_prepare(nl, n, box, table, ntypes, slot_first, slot_count, 1, s, a, same));
+    TMD_CHECK(nl_prepare(nl, n, box, table, ntypes, slot_first, slot_count, 1, s, a, same, ntypes > 1 ? tidx : nullptr));
     a.pos = pos;
     a.tidx = tidx;
     if (!gated) TMD_CUDA(cudaMemsetAsync(nl->flags, 1, sizeof(int), s));  // any non-zero value raises the flag

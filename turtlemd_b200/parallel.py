@@ -437,7 +437,10 @@ class SlabDecomposition:
         if not isinstance(self._box, _lib.Box):
             raise NotImplementedError("SlabDecomposition needs an orthogonal, fully periodic Box")
         self._half_skin2 = 0.25 * float(self.pot.skin) ** 2
-        self._nl = self.pot._nlist_handle()
+        # a private list handle: the potential's own one may already hold lists (and must stay usable by
+        # System.evaluate); this one is bound to the slab's record buffer and dies with the decomposition
+        self._nl = C.c_void_p()
+        _lib.call("tmd_nlist_create", C.byref(self._nl), float(self.pot.skin))
         _lib.call("tmd_nlist_bind_records", self._nl, _device.dptr(self.records))
         part._pos.device()
         part._vel.device()
@@ -659,6 +662,16 @@ class SlabDecomposition:
         if self._graphs is not None:
             _device.torch().cuda.synchronize()
             self._graphs = None
+        if getattr(self, "_nl", None):
+            _device.torch().cuda.synchronize()
+            _lib.call("tmd_nlist_destroy", self._nl)
+            self._nl = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
 
     def _piece(self, name: str) -> None:
         import torch.distributed as dist
