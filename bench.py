@@ -345,7 +345,7 @@ def bench_lj(args, cfg, rank, world, extras=True):
     def load_for_clocks():
         """The same steps for ~1.5 s more, so that nvidia-smi's 100 ms readings see the benchmark's load (the
         count follows from the max-over-ranks step time: identical on every rank)."""
-        more = max(50, min(20000, int((1.5 if extras else 0.5) / (sec / args.steps))))
+        more = max(50, min(20000, int((1.5 if extras is True else 0.5) / (sec / args.steps))))
         if stepper is None:
             integ.run(system, more)
         elif resident:
@@ -363,7 +363,7 @@ def bench_lj(args, cfg, rank, world, extras=True):
                 out["slab_run"] = stepper.status()
         load_for_clocks()
         out["clocks"] = clocks.summary()
-        if resident and world > 1 and extras and not args.quick:
+        if resident and world > 1 and extras is True and not args.quick:
             # end to end with host buffers: through the atom decomposition, whose state is the plain atom-ordered
             # arrays a host shard can be copied into (the resident run keeps its state in cell order on the device)
             stepper.release()
@@ -372,7 +372,7 @@ def bench_lj(args, cfg, rank, world, extras=True):
             stepper.prepare()
             stepper.capture()
             out["e2e"] = e2e_decomposed(stepper, system2, n, cfg, world, args)
-        elif world > 1 and extras and not args.quick:
+        elif world > 1 and extras is True and not args.quick:
             out["e2e"] = e2e_decomposed(stepper, system, n, cfg, world, args)
         stepper.release()
         return out if rank == 0 else None
@@ -415,8 +415,25 @@ def bench_lj(args, cfg, rank, world, extras=True):
     }
     if cfg["method"] == "nlist":
         out["config"]["nlist"] = dict(pot.nlist_stats(), skin=pot.skin)
-        if type(integ).__name__ == "VelocityVerlet":
-            out["roofline"]["fused_step_kernel"] = "nl_force_kernel<3,1,4,1,1,5,1> (traversal + kick + kick + drift epilogue)"
+        if type(integ).__name__ == "VelocityVerlet" and not cfg.get("dimer"):
+            # the kernel that dominates the timed step is the FUSED traversal (forces + kick + kick + drift epilogue):
+            # its own launches, timed live with CUDA events on the launching stream over another args.steps steps
+            pot.time_traversals(True)
+            integ.run(system, args.steps)
+            tms, tcount = pot.traversal_time()
+            pot.time_traversals(False)
+            if tcount:
+                fused = tms / tcount * 1e-3
+                out["roofline"].update({
+                    "kernel": "nl_force_kernel<3,1,4,1,1,5,1>", "launch_ms": fused * 1e3, "achieved": flops / fused / 1e12,
+                    "frac": flops / fused / 1e12 / peak, "launches_timed": tcount,
+                    "traffic": table.get(f"nl_force_kernel<3,1,4,1,1,5,1>@{n}", {}).get("bytes") if traffic is not None else None,
+                    "force_evaluation": {"kernel": kernel, "launch_ms": ksec * 1e3, "frac": achieved / peak,
+                                         "what": "System.evaluate: gather/check pass + bare traversal + reduction"},
+                    "note": out["roofline"]["note"].replace(
+                        "launch_ms = one whole force evaluation (all kernels of System.evaluate)",
+                        "launch_ms = average duration of the fused traversal launches of a run (CUDA events around each "
+                        "launch; the kernel also integrates), force_evaluation = one whole System.evaluate")})
 
     if args.quick or not extras:
         load_for_clocks()
@@ -589,7 +606,7 @@ def bench_replicas(args, cfg, rank, world, extras=True):
     }
     if world > 1 and extras and not args.quick:
         out["parity"] = parity_replicas(system, cfg, inner, args.warmup + args.steps, rank, world)
-    for _ in range(max(10, min(20000, int((1.5 if extras else 0.5) / (sec / args.steps))))):  # load for the clock readings
+    for _ in range(max(10, min(20000, int((1.5 if extras is True else 0.5) / (sec / args.steps))))):  # load for the clock readings
         step()
     torch.cuda.synchronize()
     out["clocks"] = clocks.summary()
@@ -859,26 +876,36 @@ def reference_replicas(args, cfg, world, cores, total_steps):
 
 
 OTHER_CONFIGS = ("lj32k", "lj256k", "dimer256k", "lj1m_langevin", "replicas")
+OTHER_CONFIGS_MULTI = ("lj1m_langevin", "dimer256k", "replicas")  # BASELINE.json configs[3], [4], [2] on N > 1 GPUs
 
 
 def measure_other_configs(args, rank, world):
-    """One short device-resident measurement of every other BASELINE.json configuration (N = 1)."""
+    """One short device-resident measurement of every other BASELINE.json configuration: all five on one GPU; on
+    N > 1 GPUs the three that are defined there (config #4 LJ + LangevinInertia, config #5 dimer in solvent, the
+    replica ensemble), each with its `parity` object.  Every rank takes part; rank 0 keeps the rows."""
     import copy
     import gc
 
     import torch
 
     rows = []
-    for name in OTHER_CONFIGS:
+    for name in (OTHER_CONFIGS if world == 1 else OTHER_CONFIGS_MULTI):
         sub = copy.copy(args)
-        sub.steps, sub.warmup, sub.quick = min(args.steps, 20), 3, True
+        sub.steps, sub.warmup, sub.quick = min(args.steps, 20), 3, world == 1
         cfg = WORKLOADS[name]
         try:
-            line = (bench_replicas if name == "replicas" else bench_lj)(sub, cfg, rank, world, extras=False)
-            rows.append({"workload": name, "config": line["config"]["workload"], "value": line["value"],
-                         "unit": line["unit"], "ms_per_step": line["ms_per_step"], "steps": sub.steps,
-                         "roofline": {k: line["roofline"].get(k) for k in ("bound", "frac", "kernel", "achieved", "peak", "unit")},
-                         "clocks": line["clocks"]})
+            line = (bench_replicas if name == "replicas" else bench_lj)(sub, cfg, rank, world,
+                                                                            extras="parity" if world > 1 else False)
+            if line is not None:
+                row = {"workload": name, "config": line["config"]["workload"], "value": line["value"],
+                       "unit": line["unit"], "ms_per_step": line["ms_per_step"], "steps": sub.steps,
+                       "clocks": line["clocks"]}
+                if "roofline" in line:
+                    row["roofline"] = {k: line["roofline"].get(k) for k in ("bound", "frac", "kernel", "achieved", "peak", "unit")}
+                if world > 1:
+                    row["parallelism"] = line["config"].get("parallelism")
+                    row["parity"] = line.get("parity")
+                rows.append(row)
         except Exception as exc:  # noqa: BLE001 - one failing configuration must not cost the headline line
             rows.append({"workload": name, "error": f"{type(exc).__name__}: {exc}"})
         gc.collect()
@@ -906,9 +933,10 @@ def main():
         with ClockSampler(list(range(world)), enabled=rank == 0) as clocks:
             args.clocks = clocks
             out = (bench_replicas if args.workload == "replicas" else bench_lj)(args, cfg, rank, world)
-            if out is not None and world == 1 and args.workload == "lj1m" and not args.quick \
-                    and os.environ.get("TMD_BENCH_CONFIGS", "1") == "1":
-                out["configs"] = measure_other_configs(args, rank, world)
+            if args.workload == "lj1m" and not args.quick and os.environ.get("TMD_BENCH_CONFIGS", "1") == "1":
+                rows = measure_other_configs(args, rank, world)  # (every rank runs them; rank 0 holds the line)
+                if out is not None:
+                    out["configs"] = rows
         if out is not None:
             print(json.dumps(out), flush=True)
             out = None

@@ -148,6 +148,19 @@ class LennardJonesCut(Potential):
             _lib.call("tmd_nlist_stats", self._nlist, C.byref(builds), C.byref(calls), C.byref(slow))
         return {"builds": builds.value, "calls": calls.value, "slow_rows": slow.value}
 
+    def time_traversals(self, on: bool = True) -> None:
+        """Measurement: CUDA events around every traversal launch of a resident run (``tmd_nlist_set_timing``;
+        a timed run synchronises at its end).  Read with :meth:`traversal_time`."""
+        if self._nlist is not None:
+            _lib.call("tmd_nlist_set_timing", self._nlist, 1 if on else 0)
+
+    def traversal_time(self) -> tuple[float, int]:
+        """(milliseconds spent in traversal launches, their number) since :meth:`time_traversals`."""
+        ms, count = C.c_double(0.0), C.c_int64(0)
+        if self._nlist is not None:
+            _lib.call("tmd_nlist_timing", self._nlist, C.byref(ms), C.byref(count))
+        return ms.value, count.value
+
     def _kernel_for(self, npart, box_abi, table, ntyp) -> str:
         """Entry point for the device-resident path."""
         if self.method == "allpairs":
