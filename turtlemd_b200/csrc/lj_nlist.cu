@@ -54,7 +54,9 @@ constexpr int kScanChunk = kBinThreads * 8;
 struct NlGrid {
     int nc[3];
     int ncells;
-    int h;            // stencil half width in cells
+    int h;            // stencil half width in cells (y, z; x when the grid is not refined)
+    int hx;           // stencil half width along x in (possibly finer) x cells: cells are cut finer along x, the
+                      // direction in which the cells of a stencil row are consecutive in slot order (nl_make_grid)
     double len[3], ilen[3];
     double scale[3];  // nc / L
 };
@@ -219,8 +221,19 @@ __global__ void __launch_bounds__(256) nl_gather_check_kernel(const double *__re
 // Calls body(jbegin, jend, code) for every run of consecutive slots of the (2H+1)^DIM cells around
 // cell (c0, c1, c2); code = image shift of that run as (sx+1) + 3 (sy+1) + 9 (sz+1).  Cells of one
 // x-row are consecutive in slot order, so a row is one run (up to three where it wraps).
-template <int DIM, typename Body>
-__device__ __forceinline__ void for_each_run(const NlGrid &g, const int *__restrict__ starts, int c0, int c1, int c2,
+// xwin(dy, dz, lo, hi) -> false to skip a stencil row, else the x-cell range [lo, hi] to walk (indices may leave
+// [0, nc): the wrap is handled here); full_x_window walks the whole stencil width.
+struct full_x_window {
+    int c0, hx;
+    __device__ __forceinline__ bool operator()(int, int, int &lo, int &hi) const {
+        lo = c0 - hx;
+        hi = c0 + hx;
+        return true;
+    }
+};
+
+template <int DIM, typename XWin, typename Body>
+__device__ __forceinline__ void for_each_run(const NlGrid &g, const int *__restrict__ starts, int c1, int c2, XWin xwin,
                                              Body body) {
     const int h = g.h;
     const int hz = DIM > 2 ? h : 0, hy = DIM > 1 ? h : 0;
@@ -232,9 +245,10 @@ __device__ __forceinline__ void for_each_run(const NlGrid &g, const int *__restr
             int y = c1 + dy, sy = 0;
             if (y < 0) { y += g.nc[1]; sy = -1; }
             else if (y >= g.nc[1]) { y -= g.nc[1]; sy = 1; }
+            int lo, hi;
+            if (!xwin(dy, dz, lo, hi)) continue;
             const int rowbase = (z * g.nc[1] + y) * g.nc[0];
             const int yz = 3 * (sy + 1) + 9 * (sz + 1);
-            const int lo = c0 - h, hi = c0 + h;
             if (lo < 0) body(starts[rowbase + lo + g.nc[0]], starts[rowbase + g.nc[0]], 0 + yz);
             body(starts[rowbase + (lo < 0 ? 0 : lo)], starts[rowbase + (hi >= g.nc[0] ? g.nc[0] : hi + 1)], 1 + yz);
             if (hi >= g.nc[0]) body(starts[rowbase], starts[rowbase + hi - g.nc[0] + 1], 2 + yz);
@@ -446,7 +460,24 @@ __global__ void __launch_bounds__(kNlThreads) nl_list_kernel(const NlArgs a) {
                 flushed += kBlockEntries;
             }
         };
-        for_each_run<DIM>(g, a.starts, c0, c1, c2, [&](int jbegin, int jend, int code) {
+        // x window of a stencil row: its atoms are at least dmin away in the (y, z) plane (distance from this atom to
+        // the faces of its own cell), so only |dx| <= sqrt(reach^2 - dmin^2) can be within reach.  Single precision
+        // with a margin far above its rounding: the window is conservative, the distance filter below is what decides.
+        const float ey = DIM > 1 ? (float)(g.len[1] / g.nc[1]) : 0.f, ez = DIM > 2 ? (float)(g.len[2] / g.nc[2]) : 0.f;
+        const float fy = DIM > 1 ? fminf(fmaxf(mey - c1 * ey, 0.f), ey) : 0.f, fz = DIM > 2 ? fminf(fmaxf(mez - c2 * ez, 0.f), ez) : 0.f;
+        const float sx = (float)g.scale[0];
+        const float margin = 1e-3f * sqrtf(reach2) + 4e-6f * lx;
+        auto xwin = [&](int dy, int dz, int &lo, int &hi) {
+            const float gy = dy == 0 ? 0.f : ((dy < 0 ? fy : ey - fy) + (abs(dy) - 1) * ey);
+            const float gz = dz == 0 ? 0.f : ((dz < 0 ? fz : ez - fz) + (abs(dz) - 1) * ez);
+            const float w2 = reach2 - gy * gy - gz * gz;
+            if (w2 <= 0.f) return false;
+            const float w = sqrtf(w2) + margin;
+            lo = max((int)floorf((mex - w) * sx), c0 - g.hx);
+            hi = min((int)floorf((mex + w) * sx), c0 + g.hx);
+            return true;
+        };
+        for_each_run<DIM>(g, a.starts, c1, c2, xwin, [&](int jbegin, int jend, int code) {
             const float xs = mex - (code % 3 - 1) * lx;
             const float ys = mey - ((code / 3) % 3 - 1) * ly;
             const float zs = mez - (code / 9 - 1) * lz;
@@ -767,7 +798,7 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
             const int cell = a.cell_of[(whole || a.row_mode || EPI) ? a.order[slot] : (int)(row_first + row)];
             const int c0 = cell % a.grid.nc[0], c1 = (cell / a.grid.nc[0]) % a.grid.nc[1],
                       c2 = cell / (a.grid.nc[0] * a.grid.nc[1]);
-            for_each_run<DIM>(a.grid, a.starts, c0, c1, c2, [&](int jbegin, int jend, int code) {
+            for_each_run<DIM>(a.grid, a.starts, c1, c2, full_x_window{c0, a.grid.hx}, [&](int jbegin, int jend, int code) {
                 for (int j = jbegin + l; j < jend; j += G)
                     if (j != slot) compute(consume(a.xs[j]), code);
             });
@@ -1028,6 +1059,15 @@ static int nl_half_width() {
     return h;
 }
 
+static int nl_x_refinement() {
+    static int f = 0;
+    if (f == 0) {
+        const int v = nl_env_int("TMD_NL_FX", 4);
+        f = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4;
+    }
+    return f;
+}
+
 // Fine grid for `reach` = rcut + skin: false when the box is not fully periodic or a direction holds
 // fewer than 2H+1 cells (the stencil would then see an atom twice; use tmd_lj_allpairs).
 static bool nl_make_grid(const tmd_box *box, double reach, int64_t n, NlGrid &g) {
@@ -1051,6 +1091,21 @@ static bool nl_make_grid(const tmd_box *box, double reach, int64_t n, NlGrid &g)
         g.ilen[k] = box->ilength[k];
         g.scale[k] = g.nc[k] / len;
         ncells *= g.nc[k];
+    }
+    // Cells are cut finer along x (TMD_NL_FX = 1 | 2 | 4 | 8, default 4): the cells of a stencil row are consecutive
+    // in slot order along x, so a finer cut keeps every row ONE run of slots while the list build can clip the run to
+    // the x window that can hold neighbours at all (nl_list_kernel): ~300 instead of ~490 candidates per atom.
+    const int fx = nl_x_refinement();
+    g.hx = h * fx;
+    if (fx > 1) {
+        const long long fine = (long long)g.nc[0] * fx;
+        if (fine <= 4096) {
+            ncells = ncells / g.nc[0] * fine;
+            g.nc[0] = (int)fine;
+            g.scale[0] = g.nc[0] / g.len[0];
+        } else {
+            g.hx = h;
+        }
     }
     if (ncells > (1ll << 28)) return false;
     g.ncells = (int)ncells;
