@@ -266,7 +266,7 @@ def bench_lj(args, cfg, rank, world, extras=True):
     if world > 1 or os.environ.get("TMD_BENCH_DECOMP") in ("slab1", "atoms1"):
         from turtlemd_b200.parallel import AtomDecomposition, SlabDecomposition, SlabRun
 
-        simple = cfg["method"] == "nlist" and not cfg.get("dimer") and cfg.get("integrator") != "langevin"
+        simple = cfg["method"] == "nlist" and not cfg.get("dimer")  # one LennardJonesCut, VelocityVerlet or LangevinInertia
         decomp = os.environ.get("TMD_BENCH_DECOMP", "slabrun" if simple and world > 1 else "atoms")
         if decomp == "slabrun" and simple and world > 1:
             try:

@@ -320,6 +320,10 @@ typedef struct tmd_langevin_consts {
     double one_minus_e_sq; /* (1 - e)**2                           */
 } tmd_langevin_consts;
 int tmd_langevin_inertia_constants(double dt, double gamma, double beta, tmd_langevin_consts *out);
+/* the resident slab run (tmd_slabrun_*) with LangevinInertia instead of VelocityVerlet: noise of the counter-based
+ * stream (key, offset = position of the first step's first normal) addressed by GLOBAL atom index; call before the
+ * first tmd_slabrun_start                                                                          */
+int tmd_slabrun_set_langevin(tmd_slabrun *sr, const tmd_langevin_consts *consts, uint64_t key, uint64_t offset);
 
 /* LangevinInertia (integrators.py:265-282), part 1 (before force()):
  *   (n0, n1) = z[offset + (first+i)*2*dim + 2k + {0,1}]

@@ -1221,7 +1221,8 @@ def test_slab_decomposition_refuses_thin_slabs():
 @pytest.mark.parametrize("kind,graph,physics", [("slab", "", "vv"), ("slab", "graph", "vv"), ("atoms", "", "vv"),
                                                 ("atoms", "graph", "vv"), ("atoms", "graph", "langevin"),
                                                 ("atoms", "", "langevin"), ("atoms", "graph", "dimer"),
-                                                ("slabrun", "", "vv"), ("slabrun", "graph", "vv")])
+                                                ("slabrun", "", "vv"), ("slabrun", "graph", "vv"),
+                                                ("slabrun", "graph", "langevin")])
 def test_two_real_ranks_match_single_gpu(kind, graph, physics):
     """Two processes, two GPUs, NCCL: tests/multi_gpu_check.py compares the decomposed trajectory with
     the single-GPU one.  Skipped on a one-GPU box (the emulated-rank tests above cover the logic)."""

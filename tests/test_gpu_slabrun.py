@@ -44,14 +44,20 @@ def _make(rep, params, temperature, seed=3, masses=False):
     return build
 
 
-def _compare(build, world, chunks, dt=0.004):
-    from turtlemd_b200.integrators import VelocityVerlet
+def _compare(build, world, chunks, dt=0.004, langevin=False):
+    from turtlemd_b200.integrators import LangevinInertia, VelocityVerlet
     from turtlemd_b200.parallel import SlabRunEmulation
+    from turtlemd_b200.philox import PhiloxNormal
+
+    def integrator():
+        if langevin:
+            return LangevinInertia(timestep=dt, gamma=0.5, beta=1.0 / 1.5, rgen=PhiloxNormal(key=17))
+        return VelocityVerlet(dt)
 
     ref = build()
-    integ = VelocityVerlet(dt)
+    integ = integrator()
     system = build()
-    emu = SlabRunEmulation([system] * world, VelocityVerlet(dt))
+    emu = SlabRunEmulation([system] * world, integrator())
     try:
         for k in chunks:
             integ.run(ref, k)
@@ -81,6 +87,14 @@ def test_emulated_slab_ranks_follow_the_single_gpu_trajectory(world):
 
 def test_emulated_slab_ranks_two_types_and_masses():
     _compare(_make(12, TWO, temperature=2.0, masses=True), 2, [30])
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_emulated_slab_ranks_langevin_inertia(world):
+    """BASELINE.json configs[3] in small: LangevinInertia on slabs.  The noise of a coordinate is addressed by its global
+    atom index, so the decomposed run retraces the single-GPU ``LangevinInertia.run`` (integrators.py:265-282)."""
+    status = _compare(_make(12, SINGLE, temperature=1.5, masses=True), world, [22, 15], langevin=True)
+    assert all(s["builds"] >= 1 for s in status), status
 
 
 def test_slab_run_refuses_too_many_ranks():

@@ -127,6 +127,7 @@ PROTOTYPES = {
     "tmd_slabrun_window": [_P, C.POINTER(_P), C.POINTER(C.c_size_t)],
     "tmd_slabrun_connect": [_P, C.POINTER(_P)],
     "tmd_slabrun_load": [_P, _P, _P, _P, _P, _P, _P],
+    "tmd_slabrun_set_langevin": [_P, _LC, _U64, _U64],
     "tmd_slabrun_start": [_P, _P],
     "tmd_slabrun_step": [_P, _I32, _P],
     "tmd_slabrun_run": [_P, _I32, _I32, C.POINTER(_I64), _P],

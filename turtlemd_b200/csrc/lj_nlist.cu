@@ -61,6 +61,19 @@ struct NlGrid {
     double scale[3];  // nc / L
 };
 
+// Step barrier of a multi-GPU slab run (slabrun.cuh), executed by the traversal block that finishes last: device-resident
+// description of where the ranks' mailboxes are and which words of this rank the barrier maintains.
+constexpr int kNlMaxWorld = 16;
+struct NlStepBarrier {
+    int world, rank;
+    unsigned long long *mail[kNlMaxWorld];  // every rank's mailbox [2][world] (peer memory)
+    unsigned long long *epoch;              // this rank's barrier count
+    int *local_flag;                        // raised by this rank's epilogues: an atom moved more than skin / 2
+    int *gates;                             // [2]: the rebuild gates of even / odd steps
+    int *counters;                          // [5]: append counters of a rebuild, zeroed here
+    int *err;
+};
+
 struct NlArgs {
     const double *pos;
     const int32_t *tidx;
@@ -118,6 +131,11 @@ struct NlArgs {
     const int *gid;      // NULL, or global atom index by local index: slots inside a cell ascend by it
     const int *halo;     // EPI = 2: [0] lo_begin [1] lo_end [2] dest_lo [3] hi_begin [4] hi_end [5] dest_hi (slots)
     double4 *peer_lo_next, *peer_hi_next;  // EPI = 2: the record buffers of the next step on the two neighbouring ranks
+    int *work;                 // EPI = 2: next unclaimed chunk of rows (steps that need no (V, W) hand rows out dynamically)
+    const NlStepBarrier *bar;  // EPI = 2: non-NULL = the block that finishes last runs the step barrier (real ranks)
+    int bar_gate_out;          //          which gate word receives the OR of the ranks' flags
+    int bar_has_cond;          //          inside a step graph: also decide the IF node around the next step's rebuild
+    cudaGraphConditionalHandle bar_cond;
     LjTable tab;
 };
 
@@ -569,6 +587,47 @@ __global__ void nl_reach_kernel(const NlArgs a, int dim) {
     a.nlflags[6] = most;
 }
 
+// The step barrier (one warp, lane r talks to rank r): fence, write (epoch << 1 | flag) into every rank's mailbox, wait for
+// all ranks of this epoch (bounded: ~2 s, then the run is marked failed), OR of the flags -> the gate of the next step's
+// rebuild.  Mailboxes are double-buffered by epoch parity: a rank that is one barrier ahead writes the other half.
+__device__ __forceinline__ void nl_step_barrier(const NlStepBarrier &b, int gate_out, int has_cond,
+                                                cudaGraphConditionalHandle cond, int lane) {
+    const unsigned long long e = *b.epoch + 1;
+    const int mine = *b.local_flag != 0;
+    __syncwarp();
+    __threadfence_system();
+    if (lane < b.world) {
+        volatile unsigned long long *dst = b.mail[lane] + (e & 1ull) * b.world + b.rank;
+        *dst = (e << 1) | (unsigned long long)mine;
+    }
+    int flag = 0, failed = 0;
+    if (lane < b.world) {
+        volatile unsigned long long *src = b.mail[b.rank] + (e & 1ull) * b.world + lane;
+        unsigned long long t0, now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned long long v = *src;
+        while ((v >> 1) != e) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 2000000000ull) { failed = 1; break; }
+            __nanosleep(32);
+            v = *src;
+        }
+        flag = (int)(v & 1ull);
+    }
+    failed = __any_sync(0xffffffffu, failed);
+    flag = __any_sync(0xffffffffu, flag);
+    __threadfence_system();
+    if (lane == 0) {
+        if (failed) atomicOr(b.err, 1);
+        if (has_cond) cudaGraphSetConditional(cond, flag ? 1u : 0u);
+        b.gates[gate_out] = flag;
+        *b.local_flag = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) b.counters[k] = 0;
+        *b.epoch = e;
+    }
+}
+
 template <int G>
 __device__ __forceinline__ double group_sum(double v) {
 #pragma unroll
@@ -589,8 +648,14 @@ __device__ __forceinline__ double group_sum(double v) {
 // the last step of the run -- the opening half kick and the drift of the next one, the new 32-byte
 // record for the next traversal (double buffer) and the Verlet-list displacement test.  Same roundings,
 // in the same order, as tmd_vv_kick_kick_drift + nl_gather_check_kernel: bit-identical trajectories.
+//
+// EPI = 2 (slab run, VelocityVerlet): as 1, rows = the slots of this rank's cell layers, boundary records also stored into
+// the neighbours' buffers, optional in-kernel step barrier.  EPI = 3 (slab run, other integrators): the slab's rows, forces
+// by slot, NO integration (a separate pass integrates and pushes the halo).
 template <int DIM, bool SINGLE, int G, bool WV, bool WF, int MINB, int EPI = 0>
 __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs a) {
+    constexpr bool kInt = EPI == 1 || EPI == 2;  // the epilogue integrates
+    constexpr bool kSlab = EPI >= 2;             // rows decided on the device (slab runs)
     static_assert(G * 4 == kBlockEntries, "the block layout of the lists is for four lanes per row atom");
     __shared__ double s_tab[SINGLE ? 1 : 6 * kMaxT2];
     __shared__ double s_red[10 * (kNlThreads / 32)];
@@ -600,7 +665,7 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
     __shared__ double s_w[6][kNlThreads];
     // EPI: what the epilogue of the current row needs (v, x, lattice shift, build position, 1/m, other forces) is
     // requested when the row starts and lands here while its pairs are evaluated
-    __shared__ double s_epi[EPI ? 6 : 1][EPI ? kNlThreads : 1];
+    __shared__ double s_epi[kInt ? 6 : 1][kInt ? kNlThreads : 1];
     constexpr int kRowsPerBlock = kNlThreads / G;
     const int tid = threadIdx.x;
 #pragma unroll
@@ -608,8 +673,8 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
     const int l = tid % G, grp = tid / G;
     // EPI = 2 (slab runs): the rows are the slots of a range of cells, known only after binning (see nl_list_kernel);
     // otherwise the two are kernel parameters (constant bank, no registers: this loop is at its register limit)
-    const int64_t row_first = EPI == 2 ? (int64_t)a.starts[a.row_cell_lo] : a.first;
-    const int64_t row_count = EPI == 2 ? (int64_t)(a.starts[a.row_cell_hi] - a.starts[a.row_cell_lo]) : a.count;
+    const int64_t row_first = kSlab ? (int64_t)a.starts[a.row_cell_lo] : a.first;
+    const int64_t row_count = kSlab ? (int64_t)(a.starts[a.row_cell_hi] - a.starts[a.row_cell_lo]) : a.count;
     // EPI = 2: which of this rank's slots are copied to which slots of the two neighbouring ranks
     int halo_lo_begin = 0, halo_lo_end = 0, halo_dest_lo = 0, halo_hi_begin = 0, halo_dest_hi = 0;
     if (EPI == 2) {
@@ -663,19 +728,33 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
         return r;
     };
 
-    // block-uniform trip count: the group shuffles below need every lane of the warp in the loop
+    // Warp-uniform trip count: the group shuffles below need every lane of the warp in the loop.  Rows are dealt out
+    // statically (block b takes row groups b, b + gridDim, ...: per-block (V, W) partials are then reproducible), except
+    // on the steps of a slab run that need no (V, W): there every warp claims its next chunk of 32 / G rows from a
+    // counter, so that no SM idles while another still has a whole iteration to go (the rows per rank are few).
     const int64_t stride = (int64_t)gridDim.x * kRowsPerBlock;
-    Row next = fetch((int64_t)blockIdx.x * kRowsPerBlock);
-    for (int64_t base = (int64_t)blockIdx.x * kRowsPerBlock; base < row_count; base += stride) {
+    const bool dynamic = kSlab && !a.epi_last;
+    constexpr int kRowsPerWarp = 32 / G;
+    const int64_t limit = kSlab ? row_count - (int64_t)(tid >> 5) * kRowsPerWarp : row_count;
+    auto claim = [&]() -> int64_t {  // base of this warp's next chunk, such that row = base + grp
+        int c = 0;
+        if ((tid & 31) == 0) c = atomicAdd(a.work, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        return ((int64_t)c - (tid >> 5)) * kRowsPerWarp;
+    };
+    int64_t base = dynamic ? claim() : (int64_t)blockIdx.x * kRowsPerBlock, base_next = 0;
+    Row next = fetch(base);
+    for (; base < limit; base = base_next) {
         const Row cur = next;
-        if (base + stride < row_count) next = fetch(base + stride);
+        base_next = dynamic ? claim() : base + stride;
+        if (base_next < limit) next = fetch(base_next);
         const int64_t row = base + grp;
         const bool valid = cur.valid;
         const int slot = cur.slot, nn = cur.nn;
         const double4 me = cur.me;
         const int ti = SINGLE ? 0 : (int)__double_as_longlong(me.w);
         double facc[3] = {0.0, 0.0, 0.0};
-        if (EPI) {
+        if (kInt) {
             if (valid && l < DIM) {
                 const int64_t e = (int64_t)slot * DIM + l;
                 cp_async8(&s_epi[0][tid], a.vs + e);
@@ -808,8 +887,8 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
         double f[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int k = 0; k < DIM; ++k) f[k] = group_sum<G>(facc[k]);
-        if (EPI) {
-            static_assert(!EPI || G >= 3, "one lane per coordinate");
+        if (kInt) {
+            static_assert(!kInt || G >= 3, "one lane per coordinate");
             // lane l < DIM owns coordinate l of this row
             const bool mine = valid && l < DIM;
             const int64_t e = (int64_t)slot * DIM + (l < DIM ? l : 0);
@@ -852,7 +931,7 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
             }
         }
         if (l == 0 && valid) {
-            if (!EPI && (flags & TMD_WANT_F)) {
+            if (!kInt && (flags & TMD_WANT_F)) {
                 const int atom = a.row_mode ? slot : (whole ? a.order[slot] : (int)(row_first + row));
                 double *dst = a.force + (int64_t)atom * DIM;
 #pragma unroll
@@ -887,17 +966,20 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
 #pragma unroll
         for (int k = 1; k < 10; ++k) red[k] = 0.0;
     }
+    if (EPI == 2) __threadfence_system();  // this thread's stores into the neighbours' buffers are ahead of the barrier below
     block_sum<10, kNlThreads>(red, s_red);
     // The block that finishes last adds up the partials of all blocks (no second launch).  The order of
     // the sum is fixed by block index and thread index, not by who arrives when: deterministic.
     // Resident runs (EPI): nobody can look at (V, W) between the steps of a run, so only the closing step reduces
     // them -- the reduction is a serial tail of ~10 us during which all other SMs idle.
-    if (EPI && !a.epi_last) {
+    const bool reduce_now = !(EPI && !a.epi_last);
+    const bool barrier_here = EPI == 2 && a.bar != nullptr;
+    if (!reduce_now && !barrier_here) {
         if (tid == 0) {
 #pragma unroll
             for (int k = 0; k < 10; ++k) a.partial_vw[(size_t)blockIdx.x * 10 + k] = red[k];
         }
-        return;
+        return;  // (emulated ranks of a slab run: the separate barrier kernel that follows resets the row counter)
     }
     __shared__ int s_last;
     if (tid == 0) {
@@ -909,6 +991,12 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    if (kSlab) {
+        if (tid == 0) *a.work = 0;  // every block is past its loop: the counter is ready for the next launch
+        if (barrier_here && tid < 32) nl_step_barrier(*a.bar, a.bar_gate_out, a.bar_has_cond, a.bar_cond, tid);
+        if (!reduce_now) return;
+        __syncthreads();
+    }
     // thread t sums blocks t, t + 128, ... for all ten components (ten independent chains of coalesced loads),
     // then the block sums its 128 threads in a fixed order
     double fin[10];
@@ -1365,6 +1453,9 @@ static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double
     a.gid = nullptr;
     a.halo = nullptr;
     a.peer_lo_next = a.peer_hi_next = nullptr;
+    a.work = nullptr;
+    a.bar = nullptr;
+    a.bar_gate_out = a.bar_has_cond = 0;
     {
         const size_t cells1 = (size_t)nl->cap_cells + 1;
         const size_t chunks = ((size_t)nl->cap_cells + kScanChunk - 1) / kScanChunk;

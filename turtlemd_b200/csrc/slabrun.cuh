@@ -287,6 +287,9 @@ struct SrBarrier {
     int *local_flag;                          // kind 3: raised by this rank's epilogues
     int *gate_out;                            // kind 3: the OR over all ranks, the gate of the next step's rebuild
     int *builds;                              // nlflags of the list handle ([2] builds)
+    int *work;                                // kind 3: the traversal's row counter, reset for the next launch
+    unsigned long long *noise_steps;          // kind 3, Langevin: steps whose noise has been drawn (advance != 0: + 1)
+    int noise_advance;
     cudaGraphConditionalHandle cond;          // kind 3 inside a CUDA graph: the IF node around the next step's rebuild
     int has_cond;
 };
@@ -346,6 +349,8 @@ __global__ void sr_barrier_kernel(const SrBarrier b) {
                 if (b.has_cond) cudaGraphSetConditional(b.cond, flag ? 1u : 0u);
                 *b.gate_out = flag;
                 *b.local_flag = 0;
+                *b.work = 0;
+                if (b.noise_advance) *b.noise_steps += 1;
                 b.cnt->stay = 0;
                 b.cnt->out[0] = b.cnt->out[1] = 0;
                 b.cnt->ghost[0] = b.cnt->ghost[1] = 0;
@@ -389,6 +394,53 @@ __global__ void __launch_bounds__(256) sr_pre_kernel(const SrArgs s, double4 *__
     if (!(d2 <= half_skin2)) *flag = 1;
 }
 
+// LangevinInertia on the own slots (integrators.py:265-282).  mode bit 0: the closing update v = v' + b2 F of the step
+// whose forces were just computed (:281); bit 1: the opening update of the next step (:270-279) with the noise of a
+// coordinate addressed by its GLOBAL atom index (draws 2 (atom dim + k) and + 1 of the step, as the reference consumes
+// them: any decomposition retraces the single-GPU trajectory), the records of the next traversal, the halo copies and
+// the displacement test.  The step's position in the stream is offset + step_counter[0] * stride (device-resident).
+__global__ void __launch_bounds__(256) sr_langevin_kernel(const SrArgs s, double4 *__restrict__ rec, double4 *peer_lo,
+                                                          double4 *peer_hi, tmd_langevin_consts c, uint64_t key,
+                                                          uint64_t offset, const unsigned long long *step_counter,
+                                                          uint64_t stride, int mode, double half_skin2, int *flag) {
+    const int first = s.halo[0], count = s.halo[4] - first;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int slot = first + t;
+    const double im = s.imass_s[slot];
+    const InertiaPerParticle p = inertia_constants(c, im);
+    const uint64_t q_base = offset + (uint64_t)step_counter[0] * stride;
+    const int64_t atom = s.gid_s[slot];
+    const double4 b = s.xb[slot];
+    double r[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double f = s.fs[(int64_t)slot * 3 + k];
+        double v = s.vs[(int64_t)slot * 3 + k];
+        double x = s.xu[(int64_t)slot * 3 + k];
+        if (mode & 1) v = __dadd_rn(v, __dmul_rn(__dmul_rn(c.b2f, im), f));  // exactly inertia_post_kernel
+        if (mode & 2) {
+            double n0, n1;
+            two_normals(key, q_base + 2ull * (uint64_t)(atom * 3 + k), true, n0, n1);
+            const double xr = __dmul_rn(p.l00, n0);  // norm @ cho.T  (integrators.py:315)
+            const double vr = __dadd_rn(__dmul_rn(p.l10, n0), __dmul_rn(p.l11, n1));
+            inertia_pre_update(x, v, f, xr, vr, c, p);
+            s.xu[(int64_t)slot * 3 + k] = x;
+        }
+        s.vs[(int64_t)slot * 3 + k] = v;
+        r[k] = __dsub_rn(x, s.image_s[(int64_t)slot * 3 + k]);
+    }
+    if (!(mode & 2)) return;
+    const double4 out = make_double4(r[0], r[1], r[2], b.w);
+    rec[slot] = out;
+    if (slot < s.halo[1]) peer_lo[s.halo[2] + (slot - first)] = out;
+    if (slot >= s.halo[3]) peer_hi[s.halo[5] + (slot - s.halo[3])] = out;
+    double d2 = (r[0] - b.x) * (r[0] - b.x);
+    d2 = fma(r[1] - b.y, r[1] - b.y, d2);
+    d2 = fma(r[2] - b.z, r[2] - b.z, d2);
+    if (!(d2 <= half_skin2)) *flag = 1;
+}
+
 // own atoms -> the entries of the global, atom-ordered arrays (the caller sums / gathers over the ranks)
 __global__ void __launch_bounds__(256) sr_export_kernel(const SrArgs s, double *__restrict__ pos, double *__restrict__ vel,
                                                         double *__restrict__ force) {
@@ -421,7 +473,13 @@ struct tmd_slabrun {
     tmd::SrBarrier bar;
     double4 *rec_self[2], *rec_below[2], *rec_above[2];
     int *flags;           // nlflags[16] | dyn[4] | gates[2] | local_flag[2] | halo[8]
-    int *gates, *local_flag;
+    int *gates, *local_flag, *work;
+    tmd::NlStepBarrier *step_bar;  // device copy: the traversal's last block runs the step barrier on real ranks
+    // LangevinInertia instead of VelocityVerlet (tmd_slabrun_set_langevin)
+    int langevin;
+    tmd_langevin_consts lconsts;
+    uint64_t noise_key, noise_offset, noise_stride;
+    unsigned long long *noise_steps;
     double *partial_vw, *vw;
     int fblocks, bin_blocks, list_blocks;
     int connected, loaded;
@@ -470,8 +528,9 @@ static bool sr_make_grid(const tmd_box *box, double reach, int64_t n, int world,
 }
 
 static void sr_launch_barrier(tmd_slabrun *sr, int kind, int mode, const int *gate, cudaStream_t st,
-                              const cudaGraphConditionalHandle *cond = nullptr) {
+                              const cudaGraphConditionalHandle *cond = nullptr, int noise_advance = 0) {
     SrBarrier b = sr->bar;
+    b.noise_advance = noise_advance;
     b.kind = kind;
     b.mode = mode;
     b.gate = gate;
@@ -583,6 +642,8 @@ int tmd_slabrun_create(tmd_slabrun **out, int32_t world, int32_t rank, int64_t n
     const size_t o_flags = reserve(64 * sizeof(int));
     const size_t o_cnt = reserve(sizeof(SrCounters));
     const size_t o_epoch = reserve(sizeof(unsigned long long));
+    const size_t o_stepbar = reserve(sizeof(NlStepBarrier));
+    const size_t o_noise = reserve(sizeof(unsigned long long));
     const size_t o_ints = reserve((2 * ncells1 + chunks + 5 * (size_t)L) * sizeof(int));
     const size_t o_wrapped = reserve((size_t)L * sizeof(double4));
     const size_t o_xb = reserve((size_t)L * sizeof(double4));
@@ -607,6 +668,10 @@ int tmd_slabrun_create(tmd_slabrun **out, int32_t world, int32_t rank, int64_t n
     sr->flags = reinterpret_cast<int *>(base + o_flags);
     sr->gates = sr->flags + 20;
     sr->local_flag = sr->flags + 22;
+    sr->work = sr->flags + 32;
+    sr->step_bar = reinterpret_cast<NlStepBarrier *>(base + o_stepbar);
+    sr->noise_steps = reinterpret_cast<unsigned long long *>(base + o_noise);
+    sr->noise_stride = 2ull * (uint64_t)n_global * 3ull;
     s.dyn = sr->flags + 16;
     s.halo = sr->flags + 24;
     s.cnt = reinterpret_cast<SrCounters *>(base + o_cnt);
@@ -661,6 +726,7 @@ int tmd_slabrun_create(tmd_slabrun **out, int32_t world, int32_t rank, int64_t n
     a.row_cell_hi = s.z1 * s.layer;
     a.gid = s.gid_w;
     a.halo = s.halo;
+    a.work = sr->work;
     {
         double lmax = fmax(box->length[0], fmax(box->length[1], box->length[2]));
         const double rf = reach + lmax * (1.0 / 1048576.0);
@@ -697,6 +763,8 @@ int tmd_slabrun_create(tmd_slabrun **out, int32_t world, int32_t rank, int64_t n
     b.cnt = s.cnt;
     b.halo = s.halo;
     b.builds = sr->flags;
+    b.work = sr->work;
+    b.noise_steps = sr->noise_steps;
     *out = sr;
     return TMD_OK;
 }
@@ -727,6 +795,17 @@ int tmd_slabrun_connect(tmd_slabrun *sr, void *const *windows) {
         sr->rec_below[k] = s.below.rec[k];
         sr->rec_above[k] = s.above.rec[k];
     }
+    NlStepBarrier nb;
+    memset(&nb, 0, sizeof(nb));
+    nb.world = w;
+    nb.rank = sr->rank;
+    for (int r = 0; r < w; ++r) nb.mail[r] = sr->bar.mail[r];
+    nb.epoch = sr->bar.epoch;
+    nb.local_flag = sr->local_flag;
+    nb.gates = sr->gates;
+    nb.counters = reinterpret_cast<int *>(s.cnt);
+    nb.err = s.self.err;
+    TMD_CUDA(cudaMemcpy(sr->step_bar, &nb, sizeof(nb), cudaMemcpyHostToDevice));
     sr->connected = 1;
     return TMD_OK;
 }
@@ -772,9 +851,17 @@ int tmd_slabrun_load(tmd_slabrun *sr, const double *pos, const double *vel, cons
     return TMD_OK;
 }
 
-static int sr_traverse(tmd_slabrun *sr, int last, cudaStream_t st) {
+// fused != 0 (real ranks): the traversal block that finishes last also runs the step barrier -- one launch per step
+static int sr_traverse(tmd_slabrun *sr, int last, cudaStream_t st, int fused = 0,
+                       const cudaGraphConditionalHandle *cond = nullptr) {
     NlArgs a = sr->a;
     const int g = (int)(sr->step & 1), p = sr->p;
+    if (fused) {
+        a.bar = sr->step_bar;
+        a.bar_gate_out = g ^ 1;
+        a.bar_has_cond = cond != nullptr;
+        if (cond) a.bar_cond = *cond;
+    }
     a.xs = sr->rec_self[p];
     a.xs_next = sr->rec_self[p ^ 1];
     a.peer_lo_next = sr->rec_below[p ^ 1];
@@ -782,6 +869,22 @@ static int sr_traverse(tmd_slabrun *sr, int last, cudaStream_t st) {
     a.flag_clear = sr->gates + g;
     a.flag_next = sr->local_flag;
     a.epi_last = last ? 1 : 0;
+    if (sr->langevin) {
+        // forces by slot (no integration in the traversal), then ONE pass over the own slots: closing update of this
+        // step + (unless this is the last step) opening update of the next, records, halo copies, displacement test
+        a.bar = nullptr;
+        a.force = sr->s.fs;
+        ::tmd::count_launch();
+        if (a.ntypes == 1 || a.uniform_table) nl_force_kernel<3, true, 4, true, true, 5, 3><<<sr->fblocks, kNlThreads, 0, st>>>(a);
+        else nl_force_kernel<3, false, 4, true, true, 5, 3><<<sr->fblocks, kNlThreads, 0, st>>>(a);
+        const int ob = (int)((sr->s.cap_own + 255) / 256);
+        ::tmd::count_launch(), sr_langevin_kernel<<<ob, 256, 0, st>>>(
+            sr->s, sr->rec_self[p ^ 1], sr->rec_below[p ^ 1], sr->rec_above[p ^ 1], sr->lconsts, sr->noise_key, sr->noise_offset,
+            sr->noise_steps, sr->noise_stride, last ? 1 : 3, sr->a.half_skin2, sr->local_flag);
+        if (fused) sr_launch_barrier(sr, 3, 3, nullptr, st, cond, last ? 0 : 1);  // (cannot ride in the traversal here)
+        TMD_CUDA(cudaGetLastError());
+        return TMD_OK;
+    }
     ::tmd::count_launch();
     if (a.ntypes == 1 || a.uniform_table) nl_force_kernel<3, true, 4, true, true, 5, 2><<<sr->fblocks, kNlThreads, 0, st>>>(a);
     else nl_force_kernel<3, false, 4, true, true, 5, 2><<<sr->fblocks, kNlThreads, 0, st>>>(a);
@@ -810,16 +913,22 @@ int tmd_slabrun_phase(tmd_slabrun *sr, int32_t phase, int32_t last, tmd_stream_t
         case TMD_SR_B2_SIGNAL: sr_launch_barrier(sr, 2, 1, last ? nullptr : gate, st); break;  // last = 1: ungated (start)
         case TMD_SR_B2_WAIT: sr_launch_barrier(sr, 2, 2, last ? nullptr : gate, st); break;
         case TMD_SR_TRAVERSE: TMD_CHECK(sr_traverse(sr, last, st)); break;
+        // (last != 0: the step that ran was a closing one or none at all: no noise was drawn)
         case TMD_SR_B3_SIGNAL: sr_launch_barrier(sr, 3, 1, nullptr, st); break;
-        case TMD_SR_B3_WAIT: sr_launch_barrier(sr, 3, 2, nullptr, st); break;
+        case TMD_SR_B3_WAIT: sr_launch_barrier(sr, 3, 2, nullptr, st, nullptr, sr->langevin && !last ? 1 : 0); break;
         case TMD_SR_PRE: {
             // before step 0: drift to the positions of the first force evaluation.  A run always starts in record
             // buffer 0 and on gate word 0 (so a CUDA graph of two steps recorded after one start fits after any
             // other): the flag of this pass gates the rebuild of step 0, hence the barrier that follows must
             // write gates[0] -- it runs with step = -1.
             sr->p = 0;
-            ::tmd::count_launch(), sr_pre_kernel<<<ob, 256, 0, st>>>(s, sr->rec_self[0], sr->rec_below[0], sr->rec_above[0],
-                                                                   sr->dt, sr->dt * 0.5, sr->a.half_skin2, sr->local_flag);
+            if (sr->langevin)
+                ::tmd::count_launch(), sr_langevin_kernel<<<ob, 256, 0, st>>>(
+                    s, sr->rec_self[0], sr->rec_below[0], sr->rec_above[0], sr->lconsts, sr->noise_key, sr->noise_offset,
+                    sr->noise_steps, sr->noise_stride, 2, sr->a.half_skin2, sr->local_flag);
+            else
+                ::tmd::count_launch(), sr_pre_kernel<<<ob, 256, 0, st>>>(s, sr->rec_self[0], sr->rec_below[0], sr->rec_above[0],
+                                                                       sr->dt, sr->dt * 0.5, sr->a.half_skin2, sr->local_flag);
             sr->step = -1;
             break;
         }
@@ -830,6 +939,20 @@ int tmd_slabrun_phase(tmd_slabrun *sr, int32_t phase, int32_t last, tmd_stream_t
         default: set_error("tmd_slabrun_phase: unknown phase %d", phase); return TMD_ERR_INVALID;
     }
     TMD_CUDA(cudaGetLastError());
+    return TMD_OK;
+}
+
+/* LangevinInertia (integrators.py:166-297) instead of VelocityVerlet: constants from tmd_langevin_inertia_constants, noise =
+ * the counter-based stream (key, offset = position of the first step's first normal); every step consumes 2 n_global 3
+ * normals whatever the number of ranks.  Call before tmd_slabrun_start. */
+int tmd_slabrun_set_langevin(tmd_slabrun *sr, const tmd_langevin_consts *consts, uint64_t key, uint64_t offset) {
+    TMD_REQUIRE(sr && consts, "NULL argument");
+    TMD_REQUIRE(sr->exec == nullptr, "set the integrator before the first run");
+    sr->langevin = 1;
+    sr->lconsts = *consts;
+    sr->noise_key = key;
+    sr->noise_offset = offset;
+    TMD_CUDA(cudaMemset(sr->noise_steps, 0, sizeof(unsigned long long)));
     return TMD_OK;
 }
 
@@ -854,8 +977,7 @@ int tmd_slabrun_step(tmd_slabrun *sr, int32_t last, tmd_stream_t stream) {
     sr_launch_barrier(sr, 1, 3, gate, st);
     TMD_CHECK(tmd_slabrun_phase(sr, TMD_SR_BUILD, 0, stream));
     sr_launch_barrier(sr, 2, 3, gate, st);
-    TMD_CHECK(tmd_slabrun_phase(sr, TMD_SR_TRAVERSE, last, stream));
-    sr_launch_barrier(sr, 3, 3, nullptr, st);
+    TMD_CHECK(sr_traverse(sr, last, st, 1));
     TMD_CUDA(cudaGetLastError());
     return tmd_slabrun_phase(sr, TMD_SR_ADVANCE, last, stream);
 }
@@ -914,8 +1036,7 @@ static int sr_build_graph(tmd_slabrun *sr) {
         if (cudaStreamEndCapture(bs, nullptr) != cudaSuccess) status = TMD_ERR_CUDA;
         if (status != TMD_OK) break;
         // ---- traversal + step barrier (which decides the next IF) ----
-        status = sr_traverse(sr, 0, cs);
-        sr_launch_barrier(sr, 3, 3, nullptr, cs, k == 0 ? &cond[1] : nullptr);
+        status = sr_traverse(sr, 0, cs, 1, k == 0 ? &cond[1] : nullptr);
         sr->p ^= 1;
         sr->step += 1;
     }
@@ -953,7 +1074,7 @@ int tmd_slabrun_run(tmd_slabrun *sr, int32_t steps, int32_t use_graph, int64_t *
             TMD_CUDA(cudaGraphLaunch(sr->exec, st));
             sr->step += 2;  // (the buffer parity is back where it was)
             todo -= 2;
-            if (graph_launches) *graph_launches += 5;  // a pair without rebuild: condition, 2 traversals, 2 barriers
+            if (graph_launches) *graph_launches += 3;  // a pair without rebuild: condition kernel + 2 traversals
         }
     }
     for (; todo > 0; --todo) TMD_CHECK(tmd_slabrun_step(sr, 0, stream));

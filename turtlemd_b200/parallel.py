@@ -734,8 +734,10 @@ class _SlabRunRank:
     """One rank's ``tmd_slabrun`` handle plus the replicated device arrays it loads from / exports to."""
 
     def __init__(self, system, integrator, world: int, rank: int):
-        if not isinstance(integrator, VelocityVerlet):
-            raise NotImplementedError("the resident slab run integrates with VelocityVerlet")
+        if not isinstance(integrator, (VelocityVerlet, LangevinInertia)):
+            raise NotImplementedError("the resident slab run integrates with VelocityVerlet or LangevinInertia")
+        if isinstance(integrator, LangevinInertia) and not _is_device_stream(integrator.rgen):
+            raise NotImplementedError("sharded Langevin dynamics needs the counter-based PhiloxNormal stream")
         pots = system.potentials
         if len(pots) != 1 or not isinstance(pots[0], LennardJonesCut):
             raise NotImplementedError("the resident slab run steps systems with a single LennardJonesCut potential")
@@ -759,6 +761,12 @@ class _SlabRunRank:
         _lib.call("tmd_slabrun_window", self.handle, C.byref(ptr), C.byref(size))
         self.window, self.window_bytes = ptr.value, size.value
         self._vw = _device.zeros(10)
+        self.draws_per_step = 0
+        if isinstance(integrator, LangevinInertia):
+            integrator.initiate_parameters(system)
+            _lib.call("tmd_slabrun_set_langevin", self.handle, C.byref(integrator._consts), integrator.rgen.key,
+                      integrator.rgen.position)
+            self.draws_per_step = 2 * self.n * 3  # the stream moves on by the GLOBAL draw count on every rank
 
     def connect(self, windows: list[int]) -> None:
         arr = (C.c_void_p * self.world)(*windows)
@@ -855,6 +863,8 @@ class SlabRun:
                   _device.stream_ptr())
         _lib.add_launches(replayed.value)
         self.steps_done += steps
+        if self.r.draws_per_step:
+            self.r.integrator.rgen.advance(steps * self.r.draws_per_step)
 
     def status(self) -> dict:
         return self.r.status()
@@ -919,7 +929,7 @@ class SlabRunEmulation:
             self._all(name)
         self._all("TRAVERSE", last)
         self._all("B3_SIGNAL")
-        self._all("B3_WAIT")
+        self._all("B3_WAIT", last)
         self._all("ADVANCE", last)
 
     def run(self, steps: int) -> None:
@@ -929,6 +939,8 @@ class SlabRunEmulation:
         for _ in range(steps - 1):
             self._step(0)
         self._step(1)
+        if self.ranks[0].draws_per_step:  # one integrator object (one stream) for all emulated ranks
+            self.ranks[0].integrator.rgen.advance(steps * self.ranks[0].draws_per_step)
 
     def gather_state(self):
         total = None
