@@ -131,6 +131,7 @@ struct NlArgs {
     const int *gid;      // NULL, or global atom index by local index: slots inside a cell ascend by it
     const int *halo;     // EPI = 2: [0] lo_begin [1] lo_end [2] dest_lo [3] hi_begin [4] hi_end [5] dest_hi (slots)
     double4 *peer_lo_next, *peer_hi_next;  // EPI = 2: the record buffers of the next step on the two neighbouring ranks
+    int dynamic_rows;          // EPI >= 2: hand rows out dynamically on steps that need no (V, W)
     int *work;                 // EPI = 2: next unclaimed chunk of rows (steps that need no (V, W) hand rows out dynamically)
     const NlStepBarrier *bar;  // EPI = 2: non-NULL = the block that finishes last runs the step barrier (real ranks)
     int bar_gate_out;          //          which gate word receives the OR of the ranks' flags
@@ -733,7 +734,7 @@ __global__ void __launch_bounds__(kNlThreads, MINB) nl_force_kernel(const NlArgs
     // on the steps of a slab run that need no (V, W): there every warp claims its next chunk of 32 / G rows from a
     // counter, so that no SM idles while another still has a whole iteration to go (the rows per rank are few).
     const int64_t stride = (int64_t)gridDim.x * kRowsPerBlock;
-    const bool dynamic = kSlab && !a.epi_last;
+    const bool dynamic = kSlab && !a.epi_last && a.dynamic_rows;
     constexpr int kRowsPerWarp = 32 / G;
     const int64_t limit = kSlab ? row_count - (int64_t)(tid >> 5) * kRowsPerWarp : row_count;
     auto claim = [&]() -> int64_t {  // base of this warp's next chunk, such that row = base + grp
@@ -1454,6 +1455,7 @@ static int nl_prepare(tmd_nlist *nl, int64_t n, const tmd_box *box, const double
     a.halo = nullptr;
     a.peer_lo_next = a.peer_hi_next = nullptr;
     a.work = nullptr;
+    a.dynamic_rows = 0;
     a.bar = nullptr;
     a.bar_gate_out = a.bar_has_cond = 0;
     {

@@ -637,6 +637,7 @@ int tmd_slabrun_create(tmd_slabrun **out, int32_t world, int32_t rank, int64_t n
     const size_t ncells1 = (size_t)g.ncells + 1;
     const size_t chunks = ((size_t)g.ncells + kScanChunk - 1) / kScanChunk;
     sr->fblocks = nl_force_blocks((n_global + world - 1) / world, 3);
+    if (nl_env_int("TMD_SR_FBLOCKS", 0) > 0) sr->fblocks = nl_env_int("TMD_SR_FBLOCKS", 0);  // tuning runs
     size_t off = 0;
     auto reserve = [&](size_t n) { const size_t o = off; off += sr_align(n); return o; };
     const size_t o_flags = reserve(64 * sizeof(int));
@@ -727,6 +728,8 @@ int tmd_slabrun_create(tmd_slabrun **out, int32_t world, int32_t rank, int64_t n
     a.gid = s.gid_w;
     a.halo = s.halo;
     a.work = sr->work;
+    // measured at eight ranks (profiles/r02x_ab_g8.txt): claiming rows dynamically costs 1 % instead of saving the tail
+    a.dynamic_rows = nl_env_int("TMD_SR_DYNAMIC", 0) != 0;
     {
         double lmax = fmax(box->length[0], fmax(box->length[1], box->length[2]));
         const double rf = reach + lmax * (1.0 / 1048576.0);
@@ -856,7 +859,9 @@ static int sr_traverse(tmd_slabrun *sr, int last, cudaStream_t st, int fused = 0
                        const cudaGraphConditionalHandle *cond = nullptr) {
     NlArgs a = sr->a;
     const int g = (int)(sr->step & 1), p = sr->p;
-    if (fused) {
+    static const int fuse_barrier = nl_env_int("TMD_SR_FUSED_BARRIER", 1);
+    const bool in_kernel = fused && fuse_barrier && !sr->langevin;
+    if (in_kernel) {
         a.bar = sr->step_bar;
         a.bar_gate_out = g ^ 1;
         a.bar_has_cond = cond != nullptr;
@@ -888,6 +893,7 @@ static int sr_traverse(tmd_slabrun *sr, int last, cudaStream_t st, int fused = 0
     ::tmd::count_launch();
     if (a.ntypes == 1 || a.uniform_table) nl_force_kernel<3, true, 4, true, true, 5, 2><<<sr->fblocks, kNlThreads, 0, st>>>(a);
     else nl_force_kernel<3, false, 4, true, true, 5, 2><<<sr->fblocks, kNlThreads, 0, st>>>(a);
+    if (fused && !in_kernel) sr_launch_barrier(sr, 3, 3, nullptr, st, cond);
     TMD_CUDA(cudaGetLastError());
     return TMD_OK;
 }
