@@ -237,6 +237,12 @@ int tmd_slabrun_step(tmd_slabrun *sr, int32_t last, tmd_stream_t stream);
 /* start + steps - 1 full steps + one closing step; use_graph: pairs of steps replayed from a CUDA graph whose
  * rebuild launches sit in conditional IF nodes (a step without a rebuild is two kernels)             */
 int tmd_slabrun_run(tmd_slabrun *sr, int32_t steps, int32_t use_graph, int64_t *graph_launches, tmd_stream_t stream);
+/* one piece of a step (tests: several emulated ranks on one GPU, all signal halves of a barrier before any wait half) */
+enum tmd_slabrun_phase_id {
+    TMD_SR_MIGRATE = 0, TMD_SR_B0_SIGNAL = 1, TMD_SR_B0_WAIT = 2, TMD_SR_COLLECT = 3, TMD_SR_B1_SIGNAL = 4,
+    TMD_SR_B1_WAIT = 5, TMD_SR_BUILD = 6, TMD_SR_B2_SIGNAL = 7, TMD_SR_B2_WAIT = 8, TMD_SR_TRAVERSE = 9,
+    TMD_SR_B3_SIGNAL = 10, TMD_SR_B3_WAIT = 11, TMD_SR_PRE = 12, TMD_SR_ADVANCE = 13
+};
 int tmd_slabrun_phase(tmd_slabrun *sr, int32_t phase, int32_t last, tmd_stream_t stream);
 int tmd_slabrun_export(tmd_slabrun *sr, double *pos, double *vel, double *force, double *vw, tmd_stream_t stream);
 int tmd_slabrun_status(tmd_slabrun *sr, int32_t *err, int64_t *n_own, int64_t *builds, int32_t *layers);

@@ -445,3 +445,15 @@ def test_langevin_run_refuses_to_shard_a_force_field_the_fused_kernel_does_not_c
     integ = LangevinInertia(timestep=0.002, gamma=0.3, beta=1.0 / 0.07, rgen=PhiloxNormal(key=1))
     with pytest.raises(NotImplementedError):
         integ.run(system, 3, first=8, n_global=16)
+
+
+def test_slab_run_phase_ids_match_the_header():
+    """parallel.SR_PHASES drives tmd_slabrun_phase by number: the numbers are the header's enum."""
+    from turtlemd_b200.parallel import SR_ERRORS, SR_PHASES, _sr_error_text
+
+    text = (REPO / "include" / "turtlemd_b200.h").read_text()
+    body = re.search(r"enum tmd_slabrun_phase_id \{(.*?)\};", text, flags=re.S).group(1)
+    header = {name[len("TMD_SR_"):]: int(value) for name, value in re.findall(r"(TMD_SR_[A-Z0-9_]+)\s*=\s*(\d+)", body)}
+    assert header == SR_PHASES
+    assert _sr_error_text(0) == "ok" and "barrier" in _sr_error_text(1) and len(SR_ERRORS) == 7
+    assert ";" in _sr_error_text(1 | 4)

@@ -550,12 +550,6 @@ using namespace tmd;
 
 extern "C" {
 
-enum {
-    TMD_SR_MIGRATE = 0, TMD_SR_B0_SIGNAL = 1, TMD_SR_B0_WAIT = 2, TMD_SR_COLLECT = 3, TMD_SR_B1_SIGNAL = 4,
-    TMD_SR_B1_WAIT = 5, TMD_SR_BUILD = 6, TMD_SR_B2_SIGNAL = 7, TMD_SR_B2_WAIT = 8, TMD_SR_TRAVERSE = 9,
-    TMD_SR_B3_SIGNAL = 10, TMD_SR_B3_WAIT = 11, TMD_SR_PRE = 12, TMD_SR_ADVANCE = 13
-};
-
 int tmd_slabrun_destroy(tmd_slabrun *sr) {
     if (!sr) return TMD_OK;
     if (sr->exec) cudaGraphExecDestroy(sr->exec);
