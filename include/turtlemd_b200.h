@@ -330,6 +330,15 @@ int tmd_langevin_inertia_constants(double dt, double gamma, double beta, tmd_lan
  * stream (key, offset = position of the first step's first normal) addressed by GLOBAL atom index; call before the
  * first tmd_slabrun_start                                                                          */
 int tmd_slabrun_set_langevin(tmd_slabrun *sr, const tmd_langevin_consts *consts, uint64_t key, uint64_t offset);
+/* `steps` x LangevinInertia.integration_step (integrators.py:265-282) over LennardJonesCut without leaving the device: the
+ * resident run of tmd_nlist_run_vv with the Langevin updates as ONE pass per step over the slot-ordered state (closing update
+ * of a step + opening update of the next); noise = rng->key / rng->offset (position of the first step's first normal),
+ * addressed by atom index; force() and potential() of a step come from one traversal (same numbers).  Bit-identical to
+ * `steps` x (tmd_langevin_inertia_pre, tmd_lj_nlist, tmd_langevin_inertia_post).                                        */
+int tmd_nlist_run_langevin(tmd_nlist *nl, double *pos, double *vel, double *force, const double *imass,
+                           const int32_t *tidx, int64_t n, const tmd_box *box, const double *table, int32_t ntypes,
+                           const tmd_langevin_consts *consts, const tmd_rng *rng, int32_t steps, double *vw,
+                           tmd_stream_t stream);
 
 /* LangevinInertia (integrators.py:265-282), part 1 (before force()):
  *   (n0, n1) = z[offset + (first+i)*2*dim + 2k + {0,1}]

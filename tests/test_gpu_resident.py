@@ -161,3 +161,53 @@ def test_fused_run_energy_conservation_at_benchmark_size():
     e0, e1 = res[True][2], res[True][3]
     assert abs(e1 - e0) < 2e-4 * abs(e0), (e0, e1)
     assert res[True][4]["builds"] >= 2
+
+
+# ---- LangevinInertia: the resident run (tmd_nlist_run_langevin) -------------------------------------------------
+
+
+def _run_both_langevin(pos, size, vel, params, chunks, dt=0.004, **kw):
+    import turtlemd_b200.integrators as integrators
+    from turtlemd_b200.philox import PhiloxNormal
+
+    out = {}
+    for fused in (False, True):
+        integrators.RESIDENT_RUNS = integrators.RESIDENT_LANGEVIN = fused
+        try:
+            system, pot = _system(pos, size, vel, params, **kw)
+            system.potential_and_force()
+            integ = integrators.LangevinInertia(timestep=dt, gamma=0.7, beta=1.0 / 2.0, rgen=PhiloxNormal(key=23))
+            for k in chunks:
+                integ.run(system, k)
+            p = system.particles
+            out[fused] = (p.pos.copy(), p.vel.copy(), p.force.copy(), p.v_pot, p.virial.copy(), pot.nlist_stats(),
+                          integ.rgen.position)
+        finally:
+            integrators.RESIDENT_RUNS, integrators.RESIDENT_LANGEVIN = True, False
+    return out[False], out[True]
+
+
+def test_resident_langevin_run_is_bit_identical_to_the_step_by_step_path():
+    """integrators.py:265-282 over lennardjones.py:226-273: one pass per step over slot-ordered state vs the
+    element-wise kernels on atom-ordered arrays.  Same lists, same roundings, noise addressed by atom index: bit-identical,
+    through several rebuilds and a second run that starts from the state the first one left."""
+    pos, size = _fluid(12)
+    vel = np.random.default_rng(5).standard_normal(pos.shape) * 1.4
+    a, b = _run_both_langevin(pos, size, vel, SINGLE, [21, 14])
+    _assert_identical(a, b)
+    assert a[6] == b[6] == 35 * 2 * len(pos) * 3  # the stream moved on by 2 n dim normals per step
+    assert b[5]["builds"] >= 3
+
+
+def test_resident_langevin_run_two_types_masses_two_dimensions():
+    pos, size = _fluid(12)
+    rng = np.random.default_rng(8)
+    vel = rng.standard_normal(pos.shape)
+    ptype = (np.arange(len(pos)) % 4 == 0).astype(int)
+    mass = 1.0 + 0.25 * (np.arange(len(pos)) % 3)
+    a, b = _run_both_langevin(pos, size, vel, TWO, [17], ptype=ptype, mass=mass)
+    _assert_identical(a, b)
+    pos2, size2 = _fluid(48, dim=2)
+    vel2 = rng.standard_normal(pos2.shape)
+    a2, b2 = _run_both_langevin(pos2, size2, vel2, SINGLE, [15])
+    _assert_identical(a2, b2)

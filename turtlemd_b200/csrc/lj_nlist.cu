@@ -1092,6 +1092,50 @@ __global__ void __launch_bounds__(256) md_pre_kernel(int64_t n, double *__restri
     if (!(r <= half_skin2)) *flag = 1;
 }
 
+// LangevinInertia on slot-ordered state (resident run, tmd_nlist_run_langevin; integrators.py:265-282).  mode bit 0: the
+// closing update v = v' + b2 F of the step whose forces were just computed (:281); bit 1: the opening update of the next
+// step (:270-279) with the noise of a coordinate addressed by its ATOM index (draws q_base + 2 (atom dim + k) and + 1, as the
+// reference consumes them and as inertia_pre_kernel does), the records of the next traversal and the displacement test.
+template <int DIM>
+__global__ void __launch_bounds__(256) md_langevin_kernel(int64_t n, const int *__restrict__ order, double *__restrict__ xu,
+                                                          double *__restrict__ vs, const double *__restrict__ fs,
+                                                          const double *__restrict__ imass_s,
+                                                          const double *__restrict__ image_s,
+                                                          const double4 *__restrict__ xb, double4 *__restrict__ xs,
+                                                          tmd_langevin_consts c, uint64_t key, uint64_t q_base, int mode,
+                                                          double half_skin2, int *flag) {
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    const double im = imass_s[slot];
+    const InertiaPerParticle p = inertia_constants(c, im);
+    const int64_t atom = order[slot];
+    const double4 b = xb[slot];
+    double rec[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        const double f = fs[slot * DIM + k];
+        double v = vs[slot * DIM + k];
+        double x = xu[slot * DIM + k];
+        if (mode & 1) v = __dadd_rn(v, __dmul_rn(__dmul_rn(c.b2f, im), f));  // exactly inertia_post_kernel
+        if (mode & 2) {
+            double n0, n1;
+            two_normals(key, q_base + 2ull * (uint64_t)(atom * DIM + k), true, n0, n1);
+            const double xr = __dmul_rn(p.l00, n0);  // norm @ cho.T  (integrators.py:315)
+            const double vr = __dadd_rn(__dmul_rn(p.l10, n0), __dmul_rn(p.l11, n1));
+            inertia_pre_update(x, v, f, xr, vr, c, p);
+            xu[slot * DIM + k] = x;
+        }
+        vs[slot * DIM + k] = v;
+        rec[k] = __dsub_rn(x, image_s[slot * 3 + k]);
+    }
+    if (!(mode & 2)) return;
+    xs[slot] = make_double4(rec[0], rec[1], rec[2], b.w);
+    double r = (rec[0] - b.x) * (rec[0] - b.x);
+    if (DIM > 1) r = fma(rec[1] - b.y, rec[1] - b.y, r);
+    if (DIM > 2) r = fma(rec[2] - b.z, rec[2] - b.z, r);
+    if (!(r <= half_skin2)) *flag = 1;
+}
+
 // after an ungated build outside a traversal: what the traversal's block 0 does with the rebuild flag
 __global__ void md_built_kernel(int *nlflags) {
     if (nlflags[0]) {
@@ -1548,6 +1592,21 @@ int tmd_lj_nlist(tmd_nlist *nl, const double *pos, const int32_t *tidx, int64_t 
 // same handle, so the trajectory is bit-identical to K x (tmd_vv_kick_drift, tmd_lj_nlist, tmd_vv_kick).
 }  // extern "C"
 
+// slot-ordered state of a resident run (second record buffer; xu, vs, fs, fx, image_s: 3 doubles per slot, imass_s: 1)
+static int md_reserve_state(tmd_nlist *nl, cudaStream_t s) {
+    if (nl->cap_md >= nl->cap_n) return TMD_OK;
+    TMD_CUDA(cudaStreamSynchronize(s));
+    cudaFree(nl->xs2);
+    cudaFree(nl->md);
+    nl->xs2 = nullptr;
+    nl->md = nullptr;
+    nl->cap_md = 0;
+    TMD_CUDA(cudaMalloc(&nl->xs2, (size_t)nl->cap_n * sizeof(double4)));
+    TMD_CUDA(cudaMalloc(&nl->md, (size_t)nl->cap_n * 16 * sizeof(double)));
+    nl->cap_md = nl->cap_n;
+    return TMD_OK;
+}
+
 template <int DIM>
 static int md_run_vv(tmd_nlist *nl, NlArgs &a, bool same, double *pos, double *vel, double *force,
                      const double *imass, int64_t n, int steps, cudaStream_t s) {
@@ -1633,17 +1692,7 @@ int tmd_nlist_run_vv(tmd_nlist *nl, double *pos, double *vel, double *force, con
     TMD_CHECK(nl_prepare(nl, n, box, table, ntypes, 0, n, 0, s, a, same, ntypes > 1 ? tidx : nullptr));
     a.pos = pos;
     a.tidx = tidx;
-    if (nl->cap_md < nl->cap_n) {
-        TMD_CUDA(cudaStreamSynchronize(s));
-        cudaFree(nl->xs2);
-        cudaFree(nl->md);
-        nl->xs2 = nullptr;
-        nl->md = nullptr;
-        nl->cap_md = 0;
-        TMD_CUDA(cudaMalloc(&nl->xs2, (size_t)nl->cap_n * sizeof(double4)));
-        TMD_CUDA(cudaMalloc(&nl->md, (size_t)nl->cap_n * 16 * sizeof(double)));
-        nl->cap_md = nl->cap_n;
-    }
+    TMD_CHECK(md_reserve_state(nl, s));
     const size_t stride = (size_t)nl->cap_md * 3;
     a.xu = nl->md;
     a.vs = nl->md + stride;
@@ -1659,6 +1708,103 @@ int tmd_nlist_run_vv(tmd_nlist *nl, double *pos, double *vel, double *force, con
     if (dim == 1) return md_run_vv<1>(nl, a, same, pos, vel, force, imass, n, steps, s);
     if (dim == 2) return md_run_vv<2>(nl, a, same, pos, vel, force, imass, n, steps, s);
     return md_run_vv<3>(nl, a, same, pos, vel, force, imass, n, steps, s);
+}
+
+}  // extern "C"
+
+// K steps of LangevinInertia (integrators.py:265-282) over a LennardJonesCut force field, resident like md_run_vv: slot-ordered
+// state, per step [gated rebuild] + a traversal that leaves the forces by slot (EPI = 3: no integration inside) + ONE pass over
+// the state (closing update of the step + opening update of the next).  The list, its build positions and the rebuild rule are
+// those of tmd_lj_nlist; the noise is addressed by atom index: bit-identical to the step-by-step path.
+template <int DIM>
+static int md_run_langevin(tmd_nlist *nl, NlArgs &a, bool same, double *pos, double *vel, double *force, const double *imass,
+                           int64_t n, int steps, const tmd_langevin_consts &c, uint64_t key, uint64_t offset, cudaStream_t s) {
+    double4 *rec[2] = {nl->xs, nl->xs2};
+    int *gates = nl->flags + 8;
+    const int nb = (int)((n + 255) / 256);
+    const int fblocks = nl_force_blocks(n, DIM);
+    const uint64_t stride = 2ull * (uint64_t)n * DIM;  // normals one step consumes
+    TMD_CHECK(arena_get(SLOT_PARTIAL_VW, (size_t)fblocks * 10 * sizeof(double), (void **)&a.partial_vw));
+    double *xu = a.xu, *vs = a.vs, *fs = a.fs;
+    double *imass_s = const_cast<double *>(a.imass_s), *image_s = const_cast<double *>(a.image_s);
+    if (!same) {
+        a.gate = nl->flags;
+        a.xs = rec[0];
+        TMD_CHECK(nl_launch_build<DIM>(nl, a, s));
+        ::tmd::count_launch(), md_built_kernel<<<1, 1, 0, s>>>(nl->flags);
+    }
+    TMD_CUDA(cudaMemsetAsync(gates, 0, 2 * sizeof(int), s));
+    ::tmd::count_launch(), md_import_kernel<DIM><<<nb, 256, 0, s>>>(a.order, n, pos, vel, force, imass, a.image, xu, vs, fs,
+                                                                   imass_s, image_s, nullptr);
+    int p = 0;
+    ::tmd::count_launch(), md_langevin_kernel<DIM><<<nb, 256, 0, s>>>(n, a.order, xu, vs, fs, imass_s, image_s, a.xb, rec[p], c, key,
+                                                                     offset, 2, a.half_skin2, gates + 0);
+    for (int step = 0; step < steps; ++step) {
+        const int g = step & 1;
+        const bool last = step == steps - 1;
+        a.gate = gates + g;
+        a.xs = rec[p];
+        a.md_rebuild = 1;  // the two build kernels also carry the state from the old slots to the new ones
+        a.pos_w = pos;
+        a.vel_w = vel;
+        a.imass = imass;
+        TMD_CHECK(nl_launch_build<DIM>(nl, a, s));
+        a.md_rebuild = 0;
+        a.flag_clear = gates + g;
+        a.epi_last = last ? 1 : 0;
+        a.force = fs;
+        ::tmd::count_launch();
+        if (a.ntypes == 1 || a.uniform_table) nl_force_kernel<DIM, true, 4, true, true, 5, 3><<<fblocks, kNlThreads, 0, s>>>(a);
+        else nl_force_kernel<DIM, false, 4, true, true, 5, 3><<<fblocks, kNlThreads, 0, s>>>(a);
+        ::tmd::count_launch(), md_langevin_kernel<DIM><<<nb, 256, 0, s>>>(n, a.order, xu, vs, fs, imass_s, image_s, a.xb, rec[p ^ 1], c,
+                                                                         key, offset + (uint64_t)(step + 1) * stride,
+                                                                         last ? 1 : 3, a.half_skin2, gates + (g ^ 1));
+        if (!last) p ^= 1;
+    }
+    ::tmd::count_launch(), md_export_kernel<DIM><<<nb, 256, 0, s>>>(a.order, n, xu, vs, fs, pos, vel, force, nullptr);
+    TMD_CUDA(cudaGetLastError());
+    return TMD_OK;
+}
+
+extern "C" {
+
+int tmd_nlist_run_langevin(tmd_nlist *nl, double *pos, double *vel, double *force, const double *imass,
+                           const int32_t *tidx, int64_t n, const tmd_box *box, const double *table, int32_t ntypes,
+                           const tmd_langevin_consts *consts, const tmd_rng *rng, int32_t steps, double *vw,
+                           tmd_stream_t stream) {
+    TMD_REQUIRE(nl != nullptr, "nl is NULL");
+    TMD_REQUIRE(box && box->dim >= 1 && box->dim <= 3, "box->dim must be 1..3");
+    TMD_REQUIRE(n >= 2 && steps >= 1, "needs n >= 2 and steps >= 1");
+    TMD_REQUIRE(pos && vel && force && imass && vw && consts && rng, "NULL argument");
+    TMD_REQUIRE(rng->step_counter == nullptr, "the resident run takes the stream position in rng->offset");
+    TMD_REQUIRE(ntypes == 1 || tidx, "tidx is required when ntypes > 1");
+    TMD_REQUIRE(nl->xs_ext == nullptr, "this handle is bound to a slab (tmd_nlist_bind_records)");
+    TMD_CHECK(require_device());
+    cudaStream_t s = as_stream(stream);
+    const int dim = box->dim;
+    NlArgs a;
+    bool same = false;
+    TMD_CHECK(nl_prepare(nl, n, box, table, ntypes, 0, n, 0, s, a, same, ntypes > 1 ? tidx : nullptr));
+    a.pos = pos;
+    a.tidx = tidx;
+    TMD_CHECK(md_reserve_state(nl, s));
+    const size_t stride = (size_t)nl->cap_md * 3;
+    a.xu = nl->md;
+    a.vs = nl->md + stride;
+    a.fs = nl->md + 2 * stride;
+    a.fx = nullptr;
+    a.image_s = nl->md + 4 * stride;
+    a.imass_s = nl->md + 5 * stride;
+    a.flags = TMD_WANT_V | TMD_WANT_F | TMD_WANT_W;  // force() and potential() at the same positions: one traversal
+    a.vw = vw;
+    a.row_mode = 1;  // forces by slot
+    a.row_cell_lo = 0;
+    a.row_cell_hi = a.grid.ncells;  // EPI = 3 takes its rows from the cell table: all slots
+    a.work = nl->flags + 10;
+    a.dynamic_rows = 0;
+    if (dim == 1) return md_run_langevin<1>(nl, a, same, pos, vel, force, imass, n, steps, *consts, rng->key, rng->offset, s);
+    if (dim == 2) return md_run_langevin<2>(nl, a, same, pos, vel, force, imass, n, steps, *consts, rng->key, rng->offset, s);
+    return md_run_langevin<3>(nl, a, same, pos, vel, force, imass, n, steps, *consts, rng->key, rng->offset, s);
 }
 
 // ---- slab path: rows are cell-order slots, state lives in slot order ------------------------------

@@ -399,6 +399,8 @@ class LangevinInertia(MDIntegrator):
                     "LangevinInertia.run(first=, n_global=) shards DoubleWell-only replica ensembles driven by the "
                     "counter-based PhiloxNormal stream; for other force fields use parallel.AtomDecomposition")
             if steps > 1 and _is_device_stream(self.rgen):
+                if self._run_resident(system, steps):
+                    return None
                 return self._run_general(system, steps)
             for _ in range(steps):
                 self.integration_step(system)
@@ -454,6 +456,41 @@ def _langevin_run_general(self, system, steps: int):
 
 
 LangevinInertia._run_general = _langevin_run_general
+
+
+def _langevin_run_resident(self, system, steps: int) -> bool:
+    """The resident path (``tmd_nlist_run_langevin``): slot-ordered state, per step one traversal that leaves the forces by
+    slot and ONE pass over the state; taken when the force field is one ``LennardJonesCut`` on its neighbour-list path.
+    Bit-identical to the step-by-step path (same lists, same roundings, noise addressed by atom index)."""
+    pots = system.potentials
+    if len(pots) != 1 or not hasattr(pots[0], "_resident_args") or not (RESIDENT_RUNS and RESIDENT_LANGEVIN):
+        return False
+    _device.require_cuda()
+    res = pots[0]._resident_args(system)
+    if res is None:
+        return False
+    handle, tidx, n, box_abi, table, ntyp = res
+    part, n, dim, pos, vel, force, imass = _arrays(system)
+    vw = part._vw_buffer()
+    rng = _lib.Rng(self.rgen.key, self.rgen.position)
+    _lib.call("tmd_nlist_run_langevin", handle, _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
+              _device.dptr(imass), _device.dptr(tidx) if tidx is not None else None, n, C.byref(box_abi),
+              _lib.hptr(table), ntyp, C.byref(self._consts), C.byref(rng), int(steps), _device.dptr(vw),
+              _device.stream_ptr())
+    self.rgen.advance(2 * n * dim * steps)
+    part._pos.written_on_device()
+    part._vel.written_on_device()
+    part._force.written_on_device(shape=part._pos.shape)
+    part._vw_fresh.update(("v_pot", "virial"))
+    return True
+
+
+# Measured on B200 at N = 1M (profiles/r02ab_launches_langevin.txt): the slot-ordered pass draws its six normals per atom
+# from three Philox blocks (93 us) where the element-wise kernels share every block between two coordinates, and that
+# outweighs the gather / check pass it saves: 0.489 ms per step against 0.470 for the step-by-step path.  Off by default;
+# the multi-GPU slab run (parallel.SlabRun) uses the same pass, where it is 12 us of a 124 us step.
+RESIDENT_LANGEVIN = False
+LangevinInertia._run_resident = _langevin_run_resident
 
 
 def multivariate_normal(rgen: Generator, mean: np.ndarray, cho: np.ndarray, dim: int) -> np.ndarray:
