@@ -30,6 +30,17 @@ __device__ __forceinline__ void four_normals(uint64_t key, uint64_t q0, double (
     normal_pair_from_raw(b.w[2], b.w[3], z[2], z[3]);
 }
 
+// normals q0 .. q0 + 5 of the stream, q0 even (the six draws of one particle in three dimensions): they lie in TWO
+// consecutive Philox blocks -- words (0,1), (2,3) of the first and (0,1) of the second when q0 is a multiple of four,
+// words (2,3) of the first and (0,1), (2,3) of the second otherwise -- instead of the three blocks three pair draws cost
+__device__ __forceinline__ void six_normals(uint64_t key, uint64_t q0, double (&z)[6]) {
+    const Philox4 a = philox4x64_10(q0 >> 2, key), b = philox4x64_10((q0 >> 2) + 1, key);
+    const bool low = (q0 & 2ull) == 0;
+    normal_pair_from_raw(low ? a.w[0] : a.w[2], low ? a.w[1] : a.w[3], z[0], z[1]);
+    normal_pair_from_raw(low ? a.w[2] : b.w[0], low ? a.w[3] : b.w[1], z[2], z[3]);
+    normal_pair_from_raw(low ? b.w[0] : b.w[2], low ? b.w[1] : b.w[3], z[4], z[5]);
+}
+
 struct InertiaPerParticle {
     double a2, b1, b2, l00, l10, l11;
 };

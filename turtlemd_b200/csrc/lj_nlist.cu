@@ -1111,6 +1111,11 @@ __global__ void __launch_bounds__(256) md_langevin_kernel(int64_t n, const int *
     const int64_t atom = order[slot];
     const double4 b = xb[slot];
     double rec[3] = {0.0, 0.0, 0.0};
+    // three dimensions, even stream position: the six normals of this atom from two Philox blocks
+    double z6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const uint64_t q0 = q_base + 2ull * (uint64_t)(atom * DIM);
+    const bool six = DIM == 3 && (mode & 2) && (q0 & 1ull) == 0;
+    if (six) six_normals(key, q0, z6);
 #pragma unroll
     for (int k = 0; k < DIM; ++k) {
         const double f = fs[slot * DIM + k];
@@ -1119,7 +1124,8 @@ __global__ void __launch_bounds__(256) md_langevin_kernel(int64_t n, const int *
         if (mode & 1) v = __dadd_rn(v, __dmul_rn(__dmul_rn(c.b2f, im), f));  // exactly inertia_post_kernel
         if (mode & 2) {
             double n0, n1;
-            two_normals(key, q_base + 2ull * (uint64_t)(atom * DIM + k), true, n0, n1);
+            if (six) { n0 = z6[2 * k]; n1 = z6[2 * k + 1]; }
+            else two_normals(key, q_base + 2ull * (uint64_t)(atom * DIM + k), true, n0, n1);
             const double xr = __dmul_rn(p.l00, n0);  // norm @ cho.T  (integrators.py:315)
             const double vr = __dadd_rn(__dmul_rn(p.l10, n0), __dmul_rn(p.l11, n1));
             inertia_pre_update(x, v, f, xr, vr, c, p);

@@ -413,6 +413,10 @@ __global__ void __launch_bounds__(256) sr_langevin_kernel(const SrArgs s, double
     const int64_t atom = s.gid_s[slot];
     const double4 b = s.xb[slot];
     double r[3];
+    double z6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // even stream position: the six normals of this atom from two Philox blocks
+    const uint64_t q0 = q_base + 2ull * (uint64_t)(atom * 3);
+    const bool six = (mode & 2) && (q0 & 1ull) == 0;
+    if (six) six_normals(key, q0, z6);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const double f = s.fs[(int64_t)slot * 3 + k];
@@ -421,7 +425,8 @@ __global__ void __launch_bounds__(256) sr_langevin_kernel(const SrArgs s, double
         if (mode & 1) v = __dadd_rn(v, __dmul_rn(__dmul_rn(c.b2f, im), f));  // exactly inertia_post_kernel
         if (mode & 2) {
             double n0, n1;
-            two_normals(key, q_base + 2ull * (uint64_t)(atom * 3 + k), true, n0, n1);
+            if (six) { n0 = z6[2 * k]; n1 = z6[2 * k + 1]; }
+            else two_normals(key, q_base + 2ull * (uint64_t)(atom * 3 + k), true, n0, n1);
             const double xr = __dmul_rn(p.l00, n0);  // norm @ cho.T  (integrators.py:315)
             const double vr = __dadd_rn(__dmul_rn(p.l10, n0), __dmul_rn(p.l11, n1));
             inertia_pre_update(x, v, f, xr, vr, c, p);
