@@ -244,6 +244,7 @@ enum tmd_slabrun_phase_id {
     TMD_SR_B3_SIGNAL = 10, TMD_SR_B3_WAIT = 11, TMD_SR_PRE = 12, TMD_SR_ADVANCE = 13
 };
 int tmd_slabrun_phase(tmd_slabrun *sr, int32_t phase, int32_t last, tmd_stream_t stream);
+/* own atoms -> their entries of the atom-ordered arrays (pos, vel, force all NULL: only vw[10], this rank's (V, W) share) */
 int tmd_slabrun_export(tmd_slabrun *sr, double *pos, double *vel, double *force, double *vw, tmd_stream_t stream);
 int tmd_slabrun_status(tmd_slabrun *sr, int32_t *err, int64_t *n_own, int64_t *builds, int32_t *layers);
 

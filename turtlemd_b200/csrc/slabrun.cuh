@@ -1089,10 +1089,11 @@ int tmd_slabrun_run(tmd_slabrun *sr, int32_t steps, int32_t use_graph, int64_t *
 /* own atoms -> their entries of the atom-ordered arrays (n_global x 3; other entries untouched); vw[10] = this
  * rank's share of (V, W) from the last traversal */
 int tmd_slabrun_export(tmd_slabrun *sr, double *pos, double *vel, double *force, double *vw, tmd_stream_t stream) {
-    TMD_REQUIRE(sr && sr->loaded && pos && vel && force, "NULL argument");
+    TMD_REQUIRE(sr && sr->loaded, "load the system first");
+    TMD_REQUIRE((pos && vel && force) || (!pos && !vel && !force && vw), "give pos, vel and force together, or vw alone");
     cudaStream_t st = as_stream(stream);
     const int ob = (int)((sr->s.cap_own + 255) / 256);
-    ::tmd::count_launch(), sr_export_kernel<<<ob, 256, 0, st>>>(sr->s, pos, vel, force);
+    if (pos) ::tmd::count_launch(), sr_export_kernel<<<ob, 256, 0, st>>>(sr->s, pos, vel, force);
     if (vw) TMD_CUDA(cudaMemcpyAsync(vw, sr->vw, 10 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     TMD_CUDA(cudaGetLastError());
     return TMD_OK;

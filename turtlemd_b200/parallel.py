@@ -790,6 +790,11 @@ class _SlabRunRank:
                   _device.dptr(self._vw), _device.stream_ptr())
         return pos, vel, force, self._vw
 
+    def observables(self):
+        """This rank's share of (V, W) from the last traversal, as the device buffer vw[10]."""
+        _lib.call("tmd_slabrun_export", self.handle, None, None, None, _device.dptr(self._vw), _device.stream_ptr())
+        return self._vw
+
     def status(self) -> dict:
         err, n_own, builds = C.c_int32(), C.c_int64(), C.c_int64()
         layers = (C.c_int32 * 2)()
@@ -872,7 +877,7 @@ class SlabRun:
     def reduce_observables(self):
         import torch.distributed as dist
 
-        vw = self.r._vw.clone()
+        vw = self.r.observables().clone()
         dist.all_reduce(vw, group=self.group)
         host = vw.cpu().numpy()
         return float(host[0]), host[1:].reshape(3, 3).copy()
