@@ -321,6 +321,27 @@ def bench_lj(args, cfg, rank, world, extras=True):
     elif resident:
         sec = timed(lambda: stepper.run(args.steps), 1, world)
         parallelism += f", SlabRun.run({args.steps})"
+        # safety net: a slab run that did not complete cleanly on EVERY rank (a barrier timed out, a capacity was
+        # exceeded) is void -- say so and measure the atom decomposition instead of printing a wrong number
+        bad = torch.tensor([stepper.status()["err"]], device="cuda", dtype=torch.int32)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()) != 0:
+            failed_status = stepper.status()
+            stepper.release()
+            system, integ, pot = make()
+            stepper = AtomDecomposition(system, integ)
+            stepper.prepare()
+            graphed = stepper.capture()
+            resident, step = False, stepper.step
+            for _ in range(args.warmup):
+                step()
+            launches0 = _lib.launch_count()
+            sec = timed(step, args.steps, world)
+            parallelism = (f"atom-decomposition x{world}, NCCL all-gather of positions (the resident slab run FAILED on "
+                           f"this box: {failed_status['error']})")
     else:
         sec = timed(step, args.steps, world)
     launches = _lib.launch_count() - launches0

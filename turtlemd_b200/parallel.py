@@ -833,23 +833,42 @@ class SlabRun:
     def prepare(self) -> None:
         import torch.distributed as dist
 
-        handle = (C.c_ubyte * 64)()
-        _lib.call("tmd_ipc_get_handle", C.c_void_p(self.r.window), handle)
+        torch = _device.torch()
+        failure = None
+        try:
+            handle = (C.c_ubyte * 64)()
+            _lib.call("tmd_ipc_get_handle", C.c_void_p(self.r.window), handle)
+            blob = bytes(handle)
+        except Exception as exc:  # noqa: BLE001 - reported to every rank below
+            failure, blob = exc, b""
         everyone = [None] * self.world
-        dist.all_gather_object(everyone, bytes(handle), group=self.group)
-        windows = []
-        for rank, blob in enumerate(everyone):
-            if rank == self.rank:
-                windows.append(self.r.window)
-                continue
-            ptr = C.c_void_p()
-            _lib.call("tmd_ipc_open_handle", (C.c_ubyte * 64).from_buffer_copy(blob), C.byref(ptr))
-            self._peers.append(ptr)
-            windows.append(ptr.value)
-        self.r.connect(windows)
-        self.r.load()
-        _device.synchronize()
-        dist.barrier(group=self.group)  # every rank's lists exist before anybody's halo stores arrive
+        dist.all_gather_object(everyone, blob, group=self.group)
+        if failure is None and all(everyone):
+            try:
+                windows = []
+                for rank, peer in enumerate(everyone):
+                    if rank == self.rank:
+                        windows.append(self.r.window)
+                        continue
+                    ptr = C.c_void_p()
+                    _lib.call("tmd_ipc_open_handle", (C.c_ubyte * 64).from_buffer_copy(peer), C.byref(ptr))
+                    self._peers.append(ptr)
+                    windows.append(ptr.value)
+                self.r.connect(windows)
+                self.r.load()
+                _device.synchronize()
+            except Exception as exc:  # noqa: BLE001
+                failure = exc
+        elif failure is None:
+            failure = RuntimeError("a peer could not export its window")
+        # one verdict for all ranks (a rank that went on alone would wait for the others forever): after this
+        # all-reduce every rank's lists exist, or every rank raises
+        ok = torch.tensor([0 if failure is not None else 1], device="cuda", dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            raise NotImplementedError(
+                f"rank {self.rank}: the resident slab run could not be set up (peer memory over CUDA IPC is required): "
+                f"{failure if failure is not None else 'a peer failed'}")
 
     def capture(self) -> bool:
         """Ask :meth:`run` to replay pairs of steps from the library's step graph (recorded at the first run: two
