@@ -97,6 +97,29 @@ def test_emulated_slab_ranks_langevin_inertia(world):
     assert all(s["builds"] >= 1 for s in status), status
 
 
+def test_four_emulated_slab_ranks_two_types_langevin():
+    """N = 23 328 (L = 30.8: eight cell layers along z, two per rank): four ranks, two particle types with different
+    Lennard-Jones parameters and three masses under LangevinInertia -- every rank has a different neighbour above and below."""
+    status = _compare(_make(18, TWO, temperature=1.2, masses=True), 4, [24], langevin=True)
+    assert all(s["layers_per_rank"] == 2 and s["layers"] == 8 for s in status), status
+    assert all(s["builds"] >= 1 for s in status)
+
+
+def test_slab_run_status_and_error_text():
+    from turtlemd_b200.integrators import VelocityVerlet
+    from turtlemd_b200.parallel import SlabRunEmulation, _sr_error_text
+
+    emu = SlabRunEmulation([_make(12, SINGLE, temperature=0.5)()] * 2, VelocityVerlet(0.004))
+    try:
+        emu.run(3)
+        st = emu.status()
+        assert [s["err"] for s in st] == [0, 0] and all(s["error"] == "ok" for s in st)
+        assert sum(s["n_own"] for s in st) == emu.n
+    finally:
+        emu.release()
+    assert "migrant inbox full" in _sr_error_text(4) and "capacity" in _sr_error_text(16)
+
+
 def test_slab_run_refuses_too_many_ranks():
     """Two layers per rank are the minimum (own and ghost layers must not coincide)."""
     from turtlemd_b200.integrators import VelocityVerlet
