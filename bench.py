@@ -436,7 +436,7 @@ def bench_lj(args, cfg, rank, world, extras=True):
     }
     if cfg["method"] == "nlist":
         out["config"]["nlist"] = dict(pot.nlist_stats(), skin=pot.skin)
-        if type(integ).__name__ == "VelocityVerlet" and not cfg.get("dimer"):
+        if type(integ).__name__ == "VelocityVerlet":
             # the kernel that dominates the timed step is the FUSED traversal (forces + kick + kick + drift epilogue):
             # its own launches, timed live with CUDA events on the launching stream over another args.steps steps
             pot.time_traversals(True)

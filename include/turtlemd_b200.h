@@ -177,6 +177,20 @@ int tmd_nlist_run_vv(tmd_nlist *nl, double *pos, double *vel, double *force, con
 /* Measurement hook for bench.py's roofline: while on, tmd_nlist_run_vv brackets every traversal launch with
  * CUDA events on its stream, waits for the run at the end (so: never inside a timed region) and accumulates
  * the kernel time; tmd_nlist_timing returns the sum in milliseconds and the number of launches in it. */
+/* ... with a DoubleWellPair (potentials/well.py:230-286) as the system's second potential: the few atoms of the bonded
+ * types (at most 128; idx0 / idx1 as for tmd_dwpair) are evaluated by one small kernel per step from the slot-ordered
+ * state and their forces are added in the traversal's epilogue -- System.potential_and_force's sum (system/system.py:58-76),
+ * bit-identical to the step-by-step path.                                                                              */
+typedef struct tmd_dwpair_term {
+    const int32_t *idx0;
+    int32_t n0;
+    const int32_t *idx1;
+    int32_t n1, same_type;
+    double rwidth, width2, height;
+} tmd_dwpair_term;
+int tmd_nlist_run_vv_dwpair(tmd_nlist *nl, double *pos, double *vel, double *force, const double *imass,
+                            const int32_t *tidx, int64_t n, const tmd_box *box, const double *table, int32_t ntypes,
+                            double dt, int32_t steps, const tmd_dwpair_term *term, double *vw, tmd_stream_t stream);
 int tmd_nlist_set_timing(tmd_nlist *nl, int32_t on);
 int tmd_nlist_timing(tmd_nlist *nl, double *traversal_ms, int64_t *traversals);
 

@@ -211,3 +211,77 @@ def test_resident_langevin_run_two_types_masses_two_dimensions():
     vel2 = rng.standard_normal(pos2.shape)
     a2, b2 = _run_both_langevin(pos2, size2, vel2, SINGLE, [15])
     _assert_identical(a2, b2)
+
+
+# ---- a DoubleWellPair as the second potential of the fused run (tmd_nlist_run_vv_dwpair) -----------------------------
+
+
+def _dimer_system(pos, size, vel, ptype, types, skin=0.3):
+    from turtlemd_b200.potentials import DoubleWellPair, LennardJonesCut
+    from turtlemd_b200.system import Box, Particles, System
+
+    one = {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}
+    lj = LennardJonesCut(dim=pos.shape[1], shift=True, method="nlist", skin=skin)
+    lj.set_parameters({0: dict(one), 1: dict(one), 2: dict(one)})
+    bond = DoubleWellPair(types=types, dim=pos.shape[1])
+    bond.set_parameters({"rzero": 2.0 ** (1.0 / 6.0), "height": 6.0, "width": 0.25})
+    part = Particles.from_arrays(pos, vel=vel, ptype=ptype)
+    return System(Box(low=size[:, 0], high=size[:, 1]), part, [lj, bond]), lj
+
+
+@pytest.mark.parametrize("types", [(1, 1), (1, 2)])
+def test_fused_run_with_a_bonded_pair_is_bit_identical_to_single_steps(types):
+    """BASELINE.json configs[4] in small: LennardJonesCut + DoubleWellPair (well.py:230-286) under VelocityVerlet.  The fused
+    run evaluates the bonded atoms from the slot-ordered state and adds their forces in the traversal's epilogue; forces,
+    energy and virial are System.potential_and_force's sums (system.py:58-76), bit for bit, through list rebuilds."""
+    import turtlemd_b200.integrators as integrators
+
+    pos, size = _fluid(12)
+    rng = np.random.default_rng(21)
+    vel = rng.standard_normal(pos.shape) * 1.3
+    ptype = np.zeros(len(pos), dtype=int)
+    first = len(pos) // 2
+    near = np.argsort(np.sum((pos - pos[first]) ** 2, axis=1))[1:4]
+    ptype[first] = 1
+    ptype[near[0]] = types[1]
+    if types[0] != types[1]:
+        ptype[near[1]] = 1  # two atoms of the first type, one of the second: two bonded pairs
+    out = {}
+    for fused in (False, True):
+        integrators.RESIDENT_RUNS = fused
+        try:
+            system, lj = _dimer_system(pos, size, vel, ptype, types)
+            system.potential_and_force()
+            integ = integrators.VelocityVerlet(0.004)
+            for k in (19, 12):
+                integ.run(system, k)
+            p = system.particles
+            out[fused] = (p.pos.copy(), p.vel.copy(), p.force.copy(), p.v_pot, p.virial.copy(), lj.nlist_stats())
+        finally:
+            integrators.RESIDENT_RUNS = True
+    _assert_identical(out[False], out[True])
+    assert out[True][5]["builds"] >= 2
+
+
+def test_fused_run_with_a_bonded_pair_follows_the_reference_trajectory():
+    """traj_vv_dimer_864.npz (the reference's own run) through the fused path."""
+    g = load_golden("traj_vv_dimer_864.npz")
+    from turtlemd_b200.integrators import VelocityVerlet
+    from turtlemd_b200.potentials import DoubleWellPair, LennardJonesCut
+    from turtlemd_b200.system import Box, Particles, System
+
+    one = {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}
+    lj = LennardJonesCut(dim=3, shift=True, method="nlist")
+    lj.set_parameters({0: dict(one), 1: dict(one)})
+    bond = DoubleWellPair(types=(1, 1))
+    bond.set_parameters({"rzero": 2.0 ** (1.0 / 6.0), "height": 6.0, "width": 0.25})
+    part = Particles.from_arrays(g["pos0"], vel=g["vel0"], mass=g["mass"], ptype=g["ptype"])
+    system = System(Box(low=g["low"], high=g["high"]), part, [lj, bond])
+    system.potential_and_force()
+    integ = VelocityVerlet(float(g["dt"]))
+    integ.run(system, int(g["frames"][-1]))
+    p = system.particles
+    assert rel_norm(p.pos, g["pos"][-1]) < 1e-8 and rel_norm(p.vel, g["vel"][-1]) < 1e-8
+    assert rel_norm(p.force, g["force"][-1]) < 1e-8
+    assert abs(p.v_pot - g["v_pot"][-1]) <= 1e-8 * abs(g["v_pot"][-1])
+    assert rel_norm(p.virial, g["virial"][-1]) < 1e-8

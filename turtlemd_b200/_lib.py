@@ -66,6 +66,13 @@ class LangevinConsts(C.Structure):
         "one_minus_e2", "one_minus_e_sq")]
 
 
+class DwPairTerm(C.Structure):
+    """``tmd_dwpair_term``: a DoubleWellPair as the second potential of a resident run."""
+
+    _fields_ = [("idx0", C.c_void_p), ("n0", C.c_int32), ("idx1", C.c_void_p), ("n1", C.c_int32),
+                ("same_type", C.c_int32), ("rwidth", C.c_double), ("width2", C.c_double), ("height", C.c_double)]
+
+
 class NlistBuffers(C.Structure):
     """``tmd_nlist_buffers``: device pointers of a neighbour-list handle (slab path)."""
 
@@ -112,6 +119,7 @@ PROTOTYPES = {
     "tmd_nlist_stats": [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I32)],
     "tmd_lj_nlist": [_P, _P, _P, _I64, _BOX, _P, _I32, _U32, _I64, _I64, _P, _P, _P],
     "tmd_nlist_run_vv": [_P, _P, _P, _P, _P, _P, _I64, _BOX, _P, _I32, _D, _I32, _P, _P],
+    "tmd_nlist_run_vv_dwpair": [_P, _P, _P, _P, _P, _P, _I64, _BOX, _P, _I32, _D, _I32, C.POINTER(DwPairTerm), _P, _P],
     "tmd_nlist_set_timing": [_P, _I32],
     "tmd_nlist_timing": [_P, C.POINTER(_D), C.POINTER(_I64)],
     "tmd_nlist_bind_records": [_P, _P],

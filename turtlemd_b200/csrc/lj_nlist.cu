@@ -171,6 +171,7 @@ struct tmd_nlist {
     double4 *xs2;         // second record buffer (the epilogue of a step writes the records of the next)
     double *md;           // xu, vs, fs, fx, image_s (3 doubles per slot each), imass_s (1)
     int64_t cap_md;
+    void *dw_scratch;     // resident runs with a DoubleWellPair term: prev_slot[128] ints, then partials[10] doubles
     // measurement (tmd_nlist_set_timing): CUDA events around every traversal launch of a resident run
     int timing;
     double traversal_ms;
@@ -1150,6 +1151,95 @@ __global__ void md_built_kernel(int *nlflags) {
     }
 }
 
+// DoubleWellPair (well.py:230-286) as the SECOND potential of a resident run: the few atoms of the active types, one
+// thread each in ONE block, read their positions from the slot-ordered state, and leave their forces in fx (slot order),
+// which the traversal's epilogue adds to the Lennard-Jones force -- System.potential_and_force's sum (system.py:58-76).
+// The arithmetic is dwpair_kernel's (wells.cu), term for term: same roundings, same order of partners -> the same bits.
+// prev_slot remembers where this thread wrote last (slots change at every rebuild): those entries are cleared first.
+struct MdDwPair {
+    const int32_t *idx0, *idx1;  // atoms of types[0] / types[1] (ascending)
+    int n0, n1, same_type;
+    double rwidth, width2, height;
+    double len[3], ilen[3], half[3];
+    int per[3];
+    int *prev_slot;              // [n0 (+ n1)], -1 = nothing written yet
+    double *partials;            // [10]: V and W of the pairs, every pair seen from both ends (reduced with scale 0.5)
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(128) md_dwpair_kernel(const MdDwPair w, const int *__restrict__ slot_of,
+                                                        const double *__restrict__ xu, double *__restrict__ fx,
+                                                        uint32_t flags) {
+    __shared__ double smem[10 * 4];
+    double acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = 0.0;
+    const int nown = w.same_type ? w.n0 : w.n0 + w.n1;
+    const int t = threadIdx.x;
+    if (t < nown) {
+        const int ps = w.prev_slot[t];
+        if (ps >= 0) {
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) fx[(int64_t)ps * DIM + k] = 0.0;
+        }
+    }
+    __syncthreads();
+    if (t < nown) {
+        const bool in0 = t < w.n0;
+        const int me = in0 ? w.idx0[t] : w.idx1[t - w.n0];
+        const int32_t *other = w.same_type ? w.idx0 : (in0 ? w.idx1 : w.idx0);
+        const int nother = w.same_type ? w.n0 : (in0 ? w.n1 : w.n0);
+        const int myslot = slot_of[me];
+        double xi[3] = {0.0, 0.0, 0.0}, fi[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) xi[k] = xu[(int64_t)myslot * DIM + k];
+        const double height4 = __dmul_rn(4.0, w.height);  // well.py:212
+        for (int p = 0; p < nother; ++p) {
+            const int you = other[p];
+            if (you == me) continue;
+            const bool first = me < you;  // the reference visits the pair as (i, j) with i < j (particles.py:129-132)
+            const int yourslot = slot_of[you];
+            double d[3] = {0.0, 0.0, 0.0};
+            double rsq = 0.0;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                const double xj = xu[(int64_t)yourslot * DIM + k];
+                double dk = first ? __dsub_rn(xi[k], xj) : __dsub_rn(xj, xi[k]);
+                // Box.pbc_dist: strict '>' half box, stored reciprocal (box.py:376-378)
+                if (w.per[k] && fabs(dk) > w.half[k])
+                    dk = __dsub_rn(dk, __dmul_rn(rint(__dmul_rn(dk, w.ilen[k])), w.len[k]));
+                d[k] = dk;
+            }
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) rsq = (k == 0) ? __dmul_rn(d[k], d[k]) : __dadd_rn(rsq, __dmul_rn(d[k], d[k]));
+            const double delr = __dsqrt_rn(rsq);
+            const double diff = __dsub_rn(delr, w.rwidth);
+            const double q = __ddiv_rn(__dmul_rn(diff, diff), w.width2);
+            if (flags & TMD_WANT_V) {  // height*(1 - diff^2/width2)^2  (well.py:250-260)
+                const double om = __dsub_rn(1.0, q);
+                acc[0] += __dmul_rn(w.height, __dmul_rn(om, om));
+            }
+            // height4*(1 - diff^2/width2)*(diff/width2) * delta/delr  (well.py:279-282)
+            const double mag = __dmul_rn(__dmul_rn(height4, __dsub_rn(1.0, q)), __ddiv_rn(diff, w.width2));
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                const double fk = __ddiv_rn(__dmul_rn(mag, d[k]), delr);
+                fi[k] += first ? fk : -fk;
+#pragma unroll
+                for (int m = 0; m < DIM; ++m) acc[1 + k * 3 + m] += __dmul_rn(fk, d[m]);  // np.outer (well.py:285)
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) fx[(int64_t)myslot * DIM + k] = fi[k];  // (dwpair_kernel: 0 + fi[k])
+        w.prev_slot[t] = myslot;
+    }
+    block_sum<10, 128>(acc, smem);  // (as dwpair_kernel's only block when there are at most 128 active atoms)
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) w.partials[k] = acc[k];
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 
 static void nl_release(tmd_nlist *nl) {
@@ -1166,6 +1256,8 @@ static void nl_release(tmd_nlist *nl) {
     cudaFree(nl->image);
     cudaFree(nl->xs2);
     cudaFree(nl->md);
+    cudaFree(nl->dw_scratch);
+    nl->dw_scratch = nullptr;
     nl->xs2 = nullptr;
     nl->md = nullptr;
     nl->cap_md = 0;
@@ -1615,7 +1707,7 @@ static int md_reserve_state(tmd_nlist *nl, cudaStream_t s) {
 
 template <int DIM>
 static int md_run_vv(tmd_nlist *nl, NlArgs &a, bool same, double *pos, double *vel, double *force,
-                     const double *imass, int64_t n, int steps, cudaStream_t s) {
+                     const double *imass, int64_t n, int steps, cudaStream_t s, const MdDwPair *bond = nullptr) {
     double4 *rec[2] = {nl->xs, nl->xs2};
     int *gates = nl->flags + 8;
     const int nb = (int)((n + 255) / 256);
@@ -1633,6 +1725,10 @@ static int md_run_vv(tmd_nlist *nl, NlArgs &a, bool same, double *pos, double *v
     TMD_CUDA(cudaMemsetAsync(gates, 0, 2 * sizeof(int), s));
     ::tmd::count_launch(), md_import_kernel<DIM><<<nb, 256, 0, s>>>(a.order, n, pos, vel, force, imass, a.image, xu, vs, fs,
                                                                    imass_s, image_s, nullptr);
+    if (bond) {  // forces of the second potential: zero except at the slots of the active atoms
+        TMD_CUDA(cudaMemsetAsync(const_cast<double *>(a.fx), 0, (size_t)n * DIM * sizeof(double), s));
+        TMD_CUDA(cudaMemsetAsync(bond->prev_slot, 0xFF, 128 * sizeof(int), s));  // -1: nothing written yet
+    }
     int p = 0;
     ::tmd::count_launch(), md_pre_kernel<DIM><<<nb, 256, 0, s>>>(n, xu, vs, fs, imass_s, image_s, a.xb, rec[p], a.dt,
                                                                 a.half_dt, a.half_skin2, gates + 0);
@@ -1653,6 +1749,9 @@ static int md_run_vv(tmd_nlist *nl, NlArgs &a, bool same, double *pos, double *v
         a.imass = imass;
         TMD_CHECK(nl_launch_build<DIM>(nl, a, s));
         a.md_rebuild = 0;
+        if (bond)  // the DoubleWellPair forces at the positions this traversal evaluates (after the rebuild: current slots)
+            ::tmd::count_launch(), md_dwpair_kernel<DIM><<<1, 128, 0, s>>>(*bond, a.slot_of, xu, const_cast<double *>(a.fx),
+                                                                          TMD_WANT_F | (last ? (TMD_WANT_V | TMD_WANT_W) : 0u));
         // ---- forces + closing kick (+ opening kick and drift of the next step) ----
         a.xs_next = rec[p ^ 1];
         a.flag_clear = gates + g;
@@ -1663,6 +1762,8 @@ static int md_run_vv(tmd_nlist *nl, NlArgs &a, bool same, double *pos, double *v
         if (nl->timing) TMD_CUDA(cudaEventRecord(events[2 * step + 1], s));
         if (!last) p ^= 1;
     }
+    if (bond)  // System sums the potentials in order (system.py:58-76): Lennard-Jones wrote (V, W), the bond adds its share
+        TMD_CHECK(launch_reduce_vw(bond->partials, 1, 0.5, TMD_WANT_V | TMD_WANT_W | TMD_ACCUMULATE, a.vw, s));
     ::tmd::count_launch(), md_export_kernel<DIM><<<nb, 256, 0, s>>>(a.order, n, xu, vs, fs, pos, vel, force, nullptr);
     TMD_CUDA(cudaGetLastError());
     if (nl->timing) {  // measurement runs only: waits for the run
@@ -1680,9 +1781,9 @@ static int md_run_vv(tmd_nlist *nl, NlArgs &a, bool same, double *pos, double *v
 
 extern "C" {
 
-int tmd_nlist_run_vv(tmd_nlist *nl, double *pos, double *vel, double *force, const double *imass,
-                     const int32_t *tidx, int64_t n, const tmd_box *box, const double *table, int32_t ntypes,
-                     double dt, int32_t steps, double *vw, tmd_stream_t stream) {
+static int run_vv_impl(tmd_nlist *nl, double *pos, double *vel, double *force, const double *imass,
+                       const int32_t *tidx, int64_t n, const tmd_box *box, const double *table, int32_t ntypes,
+                       double dt, int32_t steps, const tmd_dwpair_term *term, double *vw, tmd_stream_t stream) {
     TMD_REQUIRE(nl != nullptr, "nl is NULL");
     TMD_REQUIRE(box && box->dim >= 1 && box->dim <= 3, "box->dim must be 1..3");
     TMD_REQUIRE(n >= 2 && steps >= 1, "needs n >= 2 and steps >= 1");
@@ -1703,7 +1804,33 @@ int tmd_nlist_run_vv(tmd_nlist *nl, double *pos, double *vel, double *force, con
     a.xu = nl->md;
     a.vs = nl->md + stride;
     a.fs = nl->md + 2 * stride;
-    a.fx = nullptr;  // (nl->md + 3 * stride is reserved for the forces of other potentials)
+    a.fx = nullptr;
+    MdDwPair bond, *bp = nullptr;
+    if (term) {  // a DoubleWellPair on top of the Lennard-Jones potential: its forces arrive through fx
+        const int nown = term->same_type ? term->n0 : term->n0 + term->n1;
+        TMD_REQUIRE(term->n0 >= 0 && term->n1 >= 0 && nown <= 128, "the resident run takes at most 128 atoms of the bonded types");
+        TMD_REQUIRE(nown == 0 || term->idx0 || term->n0 == 0, "idx0 is NULL");
+        if (!nl->dw_scratch) TMD_CUDA(cudaMalloc(&nl->dw_scratch, 128 * sizeof(int) + 16 * sizeof(double)));
+        bond.idx0 = term->idx0;
+        bond.idx1 = term->idx1;
+        bond.n0 = term->n0;
+        bond.n1 = term->n1;
+        bond.same_type = term->same_type;
+        bond.rwidth = term->rwidth;
+        bond.width2 = term->width2;
+        bond.height = term->height;
+        for (int k = 0; k < 3; ++k) {
+            const bool on = k < dim && box->periodic[k];
+            bond.per[k] = on ? 1 : 0;
+            bond.len[k] = on ? box->length[k] : 0.0;
+            bond.ilen[k] = on ? box->ilength[k] : 0.0;
+            bond.half[k] = on ? 0.5 * box->length[k] : 0.0;
+        }
+        bond.prev_slot = reinterpret_cast<int *>(nl->dw_scratch);
+        bond.partials = reinterpret_cast<double *>(reinterpret_cast<char *>(nl->dw_scratch) + 128 * sizeof(int));
+        bp = &bond;
+        a.fx = nl->md + 3 * stride;
+    }
     a.image_s = nl->md + 4 * stride;
     a.imass_s = nl->md + 5 * stride;
     a.dt = dt;
@@ -1711,9 +1838,22 @@ int tmd_nlist_run_vv(tmd_nlist *nl, double *pos, double *vel, double *force, con
     a.flags = TMD_WANT_V | TMD_WANT_F | TMD_WANT_W;
     a.force = nullptr;
     a.vw = vw;
-    if (dim == 1) return md_run_vv<1>(nl, a, same, pos, vel, force, imass, n, steps, s);
-    if (dim == 2) return md_run_vv<2>(nl, a, same, pos, vel, force, imass, n, steps, s);
-    return md_run_vv<3>(nl, a, same, pos, vel, force, imass, n, steps, s);
+    if (dim == 1) return md_run_vv<1>(nl, a, same, pos, vel, force, imass, n, steps, s, bp);
+    if (dim == 2) return md_run_vv<2>(nl, a, same, pos, vel, force, imass, n, steps, s, bp);
+    return md_run_vv<3>(nl, a, same, pos, vel, force, imass, n, steps, s, bp);
+}
+
+int tmd_nlist_run_vv(tmd_nlist *nl, double *pos, double *vel, double *force, const double *imass,
+                     const int32_t *tidx, int64_t n, const tmd_box *box, const double *table, int32_t ntypes,
+                     double dt, int32_t steps, double *vw, tmd_stream_t stream) {
+    return run_vv_impl(nl, pos, vel, force, imass, tidx, n, box, table, ntypes, dt, steps, nullptr, vw, stream);
+}
+
+int tmd_nlist_run_vv_dwpair(tmd_nlist *nl, double *pos, double *vel, double *force, const double *imass,
+                            const int32_t *tidx, int64_t n, const tmd_box *box, const double *table, int32_t ntypes,
+                            double dt, int32_t steps, const tmd_dwpair_term *term, double *vw, tmd_stream_t stream) {
+    TMD_REQUIRE(term != nullptr, "term is NULL");
+    return run_vv_impl(nl, pos, vel, force, imass, tidx, n, box, table, ntypes, dt, steps, term, vw, stream);
 }
 
 }  // extern "C"

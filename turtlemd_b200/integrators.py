@@ -27,7 +27,7 @@ from numpy.random import Generator
 
 from . import _device, _lib
 from .philox import PhiloxNormal
-from .potentials.well import DoubleWell
+from .potentials.well import DoubleWell, DoubleWellPair
 
 LOGGER = logging.getLogger(__name__)
 LOGGER.addHandler(logging.NullHandler())
@@ -147,7 +147,12 @@ def _vv_run_resident(self, system, steps: int) -> bool:
     Taken when the force field is one ``LennardJonesCut`` on its neighbour-list path; bit-identical to the
     step-by-step path (same lists, same roundings).  Returns False when the system does not qualify."""
     pots = system.potentials
-    if len(pots) != 1 or not hasattr(pots[0], "_resident_args") or not RESIDENT_RUNS:
+    if not RESIDENT_RUNS or not pots or not hasattr(pots[0], "_resident_args"):
+        return False
+    bond = None
+    if len(pots) == 2 and isinstance(pots[1], DoubleWellPair):
+        bond = pots[1]  # System sums the potentials in order: Lennard-Jones, then the pair double well
+    elif len(pots) != 1:
         return False
     _device.require_cuda()
     res = pots[0]._resident_args(system)
@@ -156,9 +161,21 @@ def _vv_run_resident(self, system, steps: int) -> bool:
     handle, tidx, n, box_abi, table, ntyp = res
     part, n, dim, pos, vel, force, imass = _arrays(system)
     vw = part._vw_buffer()
-    _lib.call("tmd_nlist_run_vv", handle, _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
-              _device.dptr(imass), _device.dptr(tidx) if tidx is not None else None, n, C.byref(box_abi),
-              _lib.hptr(table), ntyp, float(self.timestep), int(steps), _device.dptr(vw), _device.stream_ptr())
+    args = (handle, _device.dptr(pos), _device.dptr(vel), _device.dptr(force), _device.dptr(imass),
+            _device.dptr(tidx) if tidx is not None else None, n, C.byref(box_abi), _lib.hptr(table), ntyp,
+            float(self.timestep), int(steps))
+    if bond is not None:
+        idx0, idx1, dev0, dev1 = bond._active(part)
+        same = bond.types[0] == bond.types[1]
+        if (len(idx0) if same else len(idx0) + len(idx1)) > 128:
+            return False  # the resident run evaluates the bonded atoms in one block
+        rwidth, width2, height = bond._scalars()
+        term = _lib.DwPairTerm(dev0.data_ptr() if dev0 is not None else None, len(idx0),
+                               dev1.data_ptr() if dev1 is not None else None, len(idx1), 1 if same else 0,
+                               rwidth, width2, height)
+        _lib.call("tmd_nlist_run_vv_dwpair", *args, C.byref(term), _device.dptr(vw), _device.stream_ptr())
+    else:
+        _lib.call("tmd_nlist_run_vv", *args, _device.dptr(vw), _device.stream_ptr())
     part._pos.written_on_device()
     part._vel.written_on_device()
     part._force.written_on_device(shape=part._pos.shape)
