@@ -266,7 +266,8 @@ def bench_lj(args, cfg, rank, world, extras=True):
     if world > 1 or os.environ.get("TMD_BENCH_DECOMP") in ("slab1", "atoms1"):
         from turtlemd_b200.parallel import AtomDecomposition, SlabDecomposition, SlabRun
 
-        simple = cfg["method"] == "nlist" and not cfg.get("dimer")  # one LennardJonesCut, VelocityVerlet or LangevinInertia
+        # one LennardJonesCut under VelocityVerlet or LangevinInertia, or LennardJonesCut + DoubleWellPair under VelocityVerlet
+        simple = cfg["method"] == "nlist" and not (cfg.get("dimer") and cfg.get("integrator") == "langevin")
         decomp = os.environ.get("TMD_BENCH_DECOMP", "slabrun" if simple and world > 1 else "atoms")
         if decomp == "slabrun" and simple and world > 1:
             try:
@@ -282,7 +283,7 @@ def bench_lj(args, cfg, rank, world, extras=True):
             except NotImplementedError:
                 stepper = None  # fewer than two cell layers per rank: replicate positions instead
                 system, integ, pot = make()
-        if decomp in ("slab", "slab1") and simple:
+        if decomp in ("slab", "slab1") and simple and not cfg.get("dimer"):
             try:
                 stepper = SlabDecomposition(system, integ)
                 stepper.prepare()

@@ -246,6 +246,11 @@ int tmd_slabrun_connect(tmd_slabrun *sr, void *const *windows);
 /* replicated DEVICE arrays of all n_global atoms (force valid for pos) -> slabs, ghosts, lists   */
 int tmd_slabrun_load(tmd_slabrun *sr, const double *pos, const double *vel, const double *force, const double *imass,
                      const int32_t *tidx, tmd_stream_t stream);
+/* a DoubleWellPair as the system's second potential (VelocityVerlet): HOST arrays of the global indices of the atoms of
+ * types[0] / types[1] (ascending, at most 128 in all); their positions are replicated through the windows, every rank
+ * evaluates the pairs of the bonded atoms it owns.  Call before tmd_slabrun_load.                     */
+int tmd_slabrun_set_dwpair(tmd_slabrun *sr, const int32_t *gid0, int32_t n0, const int32_t *gid1, int32_t n1,
+                           int32_t same_type, double rwidth, double width2, double height, const tmd_box *box);
 int tmd_slabrun_start(tmd_slabrun *sr, tmd_stream_t stream);
 int tmd_slabrun_step(tmd_slabrun *sr, int32_t last, tmd_stream_t stream);
 /* start + steps - 1 full steps + one closing step; use_graph: pairs of steps replayed from a CUDA graph whose

@@ -1222,7 +1222,7 @@ def test_slab_decomposition_refuses_thin_slabs():
                                                 ("atoms", "graph", "vv"), ("atoms", "graph", "langevin"),
                                                 ("atoms", "", "langevin"), ("atoms", "graph", "dimer"),
                                                 ("slabrun", "", "vv"), ("slabrun", "graph", "vv"),
-                                                ("slabrun", "graph", "langevin")])
+                                                ("slabrun", "graph", "langevin"), ("slabrun", "graph", "dimer")])
 def test_two_real_ranks_match_single_gpu(kind, graph, physics):
     """Two processes, two GPUs, NCCL: tests/multi_gpu_check.py compares the decomposed trajectory with
     the single-GPU one.  Skipped on a one-GPU box (the emulated-rank tests above cover the logic)."""

@@ -105,6 +105,59 @@ def test_four_emulated_slab_ranks_two_types_langevin():
     assert all(s["builds"] >= 1 for s in status)
 
 
+@pytest.mark.parametrize("world,types", [(2, (1, 1)), (3, (1, 2))])
+def test_emulated_slab_ranks_with_a_bonded_pair(world, types):
+    """BASELINE.json configs[4] in small on slabs: LennardJonesCut + DoubleWellPair (well.py:230-286) under VelocityVerlet.
+    The bonded atoms sit next to a slab boundary (the middle of the box is one for two ranks), so they are owned by
+    different ranks or migrate during the run; their positions travel through the replicated table."""
+    from turtlemd_b200.integrators import VelocityVerlet
+    from turtlemd_b200.parallel import SlabRunEmulation
+    from turtlemd_b200.potentials import DoubleWellPair, LennardJonesCut
+    from turtlemd_b200.system import Box, Particles, System
+    from turtlemd_b200.tools import generate_lattice
+
+    pos, size = generate_lattice("fcc", [12] * 3, density=0.8)
+    rng = np.random.default_rng(31)
+    pos = pos + 0.05 * (2.0 * rng.random(pos.shape) - 1.0)
+    vel = rng.standard_normal(pos.shape) * 1.4
+    vel -= vel.mean(axis=0)
+    length = size[:, 1] - size[:, 0]
+    centre = np.argmin(np.sum((pos - 0.5 * length) ** 2, axis=1))  # an atom at the middle of the box
+    near = np.argsort(np.sum((pos - pos[centre]) ** 2, axis=1))[1:4]
+    ptype = np.zeros(len(pos), dtype=int)
+    ptype[centre] = 1
+    ptype[near[0]] = types[1]
+    if types[0] != types[1]:
+        ptype[near[1]] = 1
+    one = {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}
+
+    def build():
+        lj = LennardJonesCut(dim=3, shift=True, method="nlist")
+        lj.set_parameters({0: dict(one), 1: dict(one), 2: dict(one)})
+        bond = DoubleWellPair(types=types, dim=3)
+        bond.set_parameters({"rzero": 2.0 ** (1.0 / 6.0), "height": 6.0, "width": 0.25})
+        system = System(Box(low=size[:, 0], high=size[:, 1]), Particles.from_arrays(pos, vel=vel, ptype=ptype), [lj, bond])
+        system.potential_and_force()
+        return system
+
+    ref = build()
+    integ = VelocityVerlet(0.004)
+    emu = SlabRunEmulation([build()] * world, VelocityVerlet(0.004))
+    try:
+        for k in (23, 14):
+            integ.run(ref, k)
+            emu.run(k)
+        x, v, f, v_pot, virial = emu.gather_state()
+        status = emu.status()
+    finally:
+        emu.release()
+    q = ref.particles
+    assert rel_norm(x, q.pos) < 1e-11 and rel_norm(v, q.vel) < 1e-9 and rel_norm(f, q.force) < 1e-9
+    assert abs(v_pot - q.v_pot) <= 1e-10 * abs(q.v_pot)
+    assert rel_norm(virial, q.virial) < 1e-9
+    assert all(s["builds"] >= 1 for s in status)
+
+
 def test_slab_run_status_and_error_text():
     from turtlemd_b200.integrators import VelocityVerlet
     from turtlemd_b200.parallel import SlabRunEmulation, _sr_error_text

@@ -137,6 +137,7 @@ PROTOTYPES = {
     "tmd_slabrun_load": [_P, _P, _P, _P, _P, _P, _P],
     "tmd_slabrun_set_langevin": [_P, _LC, _U64, _U64],
     "tmd_nlist_run_langevin": [_P, _P, _P, _P, _P, _P, _I64, _BOX, _P, _I32, _LC, _RNG, _I32, _P, _P],
+    "tmd_slabrun_set_dwpair": [_P, _P, _I32, _P, _I32, _I32, _D, _D, _D, _BOX],
     "tmd_slabrun_start": [_P, _P],
     "tmd_slabrun_step": [_P, _I32, _P],
     "tmd_slabrun_run": [_P, _I32, _I32, C.POINTER(_I64), _P],

@@ -30,6 +30,7 @@ namespace tmd {
 
 constexpr int kSrMaxWorld = 16;
 constexpr int kSrMigDoubles = 8;  // x y z vx vy vz 1/m (global index, type)
+constexpr int kSrMaxBonded = 128;
 
 enum SrErr {
     SR_OK = 0,
@@ -51,6 +52,8 @@ struct SrWin {  // pointers into ONE rank's window (the only memory other ranks 
     int *ghost_count;             // [2]
     int *info;                    // [4]: slot where my ghost layer below / above starts, their populations
     int *err;
+    double *active[2];            // [kSrMaxBonded][3]: unwrapped positions of the atoms of a DoubleWellPair's types, written
+                                  // by their owners into EVERY rank's table, double-buffered like the records
 };
 
 struct SrCounters {  // device words of a rank (private)
@@ -89,6 +92,10 @@ struct SrArgs {
     const double4 *xb;
     const double *image;
     int with_force;
+    double *fx;            // NULL, or slot-ordered forces of the second potential (zeroed at every rebuild)
+    int bond_n;            // atoms of a DoubleWellPair's types (0 = none)
+    const int *bond_gid;
+    int *bond_slot;
 };
 
 // ---- initial distribution from the replicated arrays (every rank holds the whole system at the start) ----
@@ -270,7 +277,112 @@ __global__ void __launch_bounds__(256) sr_state_kernel(const SrArgs s) {
         if (s.with_force) s.fs[(int64_t)slot * 3 + c] = s.force_w[atom * 3 + c];
     }
     s.imass_s[slot] = s.imass_w[atom];
-    s.gid_s[slot] = s.gid_w[atom];
+    const int g = s.gid_w[atom];
+    s.gid_s[slot] = g;
+    if (s.fx) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s.fx[(int64_t)slot * 3 + c] = 0.0;
+        for (int k = 0; k < s.bond_n; ++k)
+            if (s.bond_gid[k] == g) s.bond_slot[k] = slot;  // (an atom of both lists of a two-type bond cannot exist)
+    }
+}
+
+// ---- a DoubleWellPair (well.py:230-286) as the system's second potential: a handful of atoms, no cut-off ----
+// Their unwrapped positions are replicated: the owner of a bonded atom stores it into every rank's table after each position
+// update (before the step barrier); every rank then evaluates the pairs of the bonded atoms it OWNS into a slot-ordered
+// force array that the traversal's epilogue adds (System.potential_and_force's sum, system.py:58-76).  Arithmetic and
+// partner order are dwpair_kernel's (wells.cu).
+struct SrBond {
+    int n0, n1, same_type, nown;
+    double rwidth, width2, height;
+    double len[3], ilen[3], half[3];
+    int per[3];
+    const int *gid;    // [nown]: global indices of the atoms of types[0], then of types[1] (each ascending)
+    int *my_slot;      // [nown]: the own slot of that atom, -1 when another rank owns it (set at every rebuild)
+    double *partials;  // [10]: this rank's share of the pairs' V and W (every pair seen from both ends)
+};
+
+__global__ void sr_bond_reset_kernel(const SrBond b, const int *gate) {
+    if (gate && *gate == 0) return;
+    if (threadIdx.x < b.nown) b.my_slot[threadIdx.x] = -1;
+}
+
+struct SrTables {
+    double *tab[kSrMaxWorld];
+};
+
+// owners -> every rank's table of the given parity
+__global__ void sr_bond_push_kernel(const SrBond b, const double *__restrict__ xu, SrTables t, int world) {
+    const int k = threadIdx.x;
+    if (k >= b.nown) return;
+    const int slot = b.my_slot[k];
+    if (slot < 0) return;
+    const double x = xu[(int64_t)slot * 3 + 0], y = xu[(int64_t)slot * 3 + 1], z = xu[(int64_t)slot * 3 + 2];
+    for (int r = 0; r < world; ++r) {
+        t.tab[r][k * 3 + 0] = x;
+        t.tab[r][k * 3 + 1] = y;
+        t.tab[r][k * 3 + 2] = z;
+    }
+}
+
+__global__ void __launch_bounds__(128) sr_bond_force_kernel(const SrBond b, const double *__restrict__ table,
+                                                            double *__restrict__ fx, uint32_t flags) {
+    __shared__ double smem[10 * 4];
+    double acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = 0.0;
+    const int t = threadIdx.x;
+    const int slot = t < b.nown ? b.my_slot[t] : -1;
+    if (slot >= 0) {
+        const bool in0 = t < b.n0;
+        const int me = b.gid[t];
+        const int obase = b.same_type ? 0 : (in0 ? b.n0 : 0);
+        const int nother = b.same_type ? b.n0 : (in0 ? b.n1 : b.n0);
+        double xi[3], fi[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) xi[k] = table[t * 3 + k];
+        const double height4 = __dmul_rn(4.0, b.height);  // well.py:212
+        for (int p = 0; p < nother; ++p) {
+            const int q = obase + p;
+            const int you = b.gid[q];
+            if (you == me) continue;
+            const bool first = me < you;  // the reference visits the pair as (i, j) with i < j (particles.py:129-132)
+            double d[3];
+            double rsq = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double xj = table[q * 3 + k];
+                double dk = first ? __dsub_rn(xi[k], xj) : __dsub_rn(xj, xi[k]);
+                if (b.per[k] && fabs(dk) > b.half[k])  // Box.pbc_dist: strict '>' half box, stored reciprocal (box.py:376-378)
+                    dk = __dsub_rn(dk, __dmul_rn(rint(__dmul_rn(dk, b.ilen[k])), b.len[k]));
+                d[k] = dk;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rsq = (k == 0) ? __dmul_rn(d[k], d[k]) : __dadd_rn(rsq, __dmul_rn(d[k], d[k]));
+            const double delr = __dsqrt_rn(rsq);
+            const double diff = __dsub_rn(delr, b.rwidth);
+            const double qq = __ddiv_rn(__dmul_rn(diff, diff), b.width2);
+            if (flags & TMD_WANT_V) {
+                const double om = __dsub_rn(1.0, qq);
+                acc[0] += __dmul_rn(b.height, __dmul_rn(om, om));
+            }
+            const double mag = __dmul_rn(__dmul_rn(height4, __dsub_rn(1.0, qq)), __ddiv_rn(diff, b.width2));
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double fk = __ddiv_rn(__dmul_rn(mag, d[k]), delr);
+                fi[k] += first ? fk : -fk;
+#pragma unroll
+                for (int m = 0; m < 3; ++m) acc[1 + k * 3 + m] += __dmul_rn(fk, d[m]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) fx[(int64_t)slot * 3 + k] = fi[k];
+    }
+    block_sum<10, 128>(acc, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) b.partials[k] = acc[k];
+    }
 }
 
 // ---- barrier across the ranks + the few words that travel with it ----
@@ -480,6 +592,12 @@ struct tmd_slabrun {
     int *flags;           // nlflags[16] | dyn[4] | gates[2] | local_flag[2] | halo[8]
     int *gates, *local_flag, *work;
     tmd::NlStepBarrier *step_bar;  // device copy: the traversal's last block runs the step barrier on real ranks
+    // a DoubleWellPair as second potential (tmd_slabrun_set_dwpair)
+    int bonded;
+    tmd::SrBond bond;
+    double *fx;
+    double *active_self[2];
+    tmd::SrTables active_all[2];
     // LangevinInertia instead of VelocityVerlet (tmd_slabrun_set_langevin)
     int langevin;
     tmd_langevin_consts lconsts;
@@ -515,6 +633,7 @@ static SrWin sr_window_layout(void *base, int world, int64_t cap_loc, int64_t ca
     w.ghost_count = reinterpret_cast<int *>(take(2 * sizeof(int)));
     w.info = reinterpret_cast<int *>(take(4 * sizeof(int)));
     w.err = reinterpret_cast<int *>(take(sizeof(int)));
+    for (int k = 0; k < 2; ++k) w.active[k] = reinterpret_cast<double *>(take((size_t)kSrMaxBonded * 3 * sizeof(double)));
     if (bytes) *bytes = off;
     return w;
 }
@@ -644,6 +763,8 @@ int tmd_slabrun_create(tmd_slabrun **out, int32_t world, int32_t rank, int64_t n
     const size_t o_epoch = reserve(sizeof(unsigned long long));
     const size_t o_stepbar = reserve(sizeof(NlStepBarrier));
     const size_t o_noise = reserve(sizeof(unsigned long long));
+    const size_t o_fx = reserve((size_t)L * 3 * sizeof(double));
+    const size_t o_bond = reserve((size_t)kSrMaxBonded * 2 * sizeof(int) + 16 * sizeof(double));
     const size_t o_ints = reserve((2 * ncells1 + chunks + 5 * (size_t)L) * sizeof(int));
     const size_t o_wrapped = reserve((size_t)L * sizeof(double4));
     const size_t o_xb = reserve((size_t)L * sizeof(double4));
@@ -672,6 +793,10 @@ int tmd_slabrun_create(tmd_slabrun **out, int32_t world, int32_t rank, int64_t n
     sr->step_bar = reinterpret_cast<NlStepBarrier *>(base + o_stepbar);
     sr->noise_steps = reinterpret_cast<unsigned long long *>(base + o_noise);
     sr->noise_stride = 2ull * (uint64_t)n_global * 3ull;
+    sr->fx = reinterpret_cast<double *>(base + o_fx);
+    sr->bond.gid = reinterpret_cast<int *>(base + o_bond);
+    sr->bond.my_slot = reinterpret_cast<int *>(base + o_bond) + kSrMaxBonded;
+    sr->bond.partials = reinterpret_cast<double *>(base + o_bond + (size_t)kSrMaxBonded * 2 * sizeof(int));
     s.dyn = sr->flags + 16;
     s.halo = sr->flags + 24;
     s.cnt = reinterpret_cast<SrCounters *>(base + o_cnt);
@@ -797,6 +922,11 @@ int tmd_slabrun_connect(tmd_slabrun *sr, void *const *windows) {
         sr->rec_below[k] = s.below.rec[k];
         sr->rec_above[k] = s.above.rec[k];
     }
+    for (int k = 0; k < 2; ++k) {
+        sr->active_self[k] = s.self.active[k];
+        for (int r = 0; r < w; ++r)
+            sr->active_all[k].tab[r] = sr_window_layout(windows[r], w, s.cap_loc, s.cap_mig, s.cap_ghost, nullptr).active[k];
+    }
     NlStepBarrier nb;
     memset(&nb, 0, sizeof(nb));
     nb.world = w;
@@ -826,6 +956,13 @@ static int sr_build(tmd_slabrun *sr, const int *gate, int with_force, cudaStream
     ::tmd::count_launch();
     TMD_CUDA(cudaLaunchCooperativeKernel((const void *)nl_bin_kernel<3>, dim3(sr->bin_blocks), dim3(kBinThreads), args, 0, st));
     ::tmd::count_launch(), nl_list_kernel<3><<<sr->list_blocks, kNlThreads, 0, st>>>(a);
+    if (sr->bonded) {
+        s.fx = sr->fx;
+        s.bond_n = sr->bond.nown;
+        s.bond_gid = sr->bond.gid;
+        s.bond_slot = sr->bond.my_slot;
+        ::tmd::count_launch(), sr_bond_reset_kernel<<<1, kSrMaxBonded, 0, st>>>(sr->bond, gate);
+    }
     ::tmd::count_launch(), sr_state_kernel<<<ob, 256, 0, st>>>(s);
     TMD_CUDA(cudaGetLastError());
     return TMD_OK;
@@ -859,7 +996,7 @@ static int sr_traverse(tmd_slabrun *sr, int last, cudaStream_t st, int fused = 0
     NlArgs a = sr->a;
     const int g = (int)(sr->step & 1), p = sr->p;
     static const int fuse_barrier = nl_env_int("TMD_SR_FUSED_BARRIER", 1);
-    const bool in_kernel = fused && fuse_barrier && !sr->langevin;
+    const bool in_kernel = fused && fuse_barrier && !sr->langevin && !sr->bonded;
     if (in_kernel) {
         a.bar = sr->step_bar;
         a.bar_gate_out = g ^ 1;
@@ -889,9 +1026,20 @@ static int sr_traverse(tmd_slabrun *sr, int last, cudaStream_t st, int fused = 0
         TMD_CUDA(cudaGetLastError());
         return TMD_OK;
     }
+    if (sr->bonded) {  // the bond's forces at the positions this traversal evaluates: table of parity p -> fx
+        a.fx = sr->fx;
+        ::tmd::count_launch(), sr_bond_force_kernel<<<1, kSrMaxBonded, 0, st>>>(sr->bond, sr->active_self[p], sr->fx,
+                                                                               TMD_WANT_F | (last ? (TMD_WANT_V | TMD_WANT_W) : 0u));
+    }
     ::tmd::count_launch();
     if (a.ntypes == 1 || a.uniform_table) nl_force_kernel<3, true, 4, true, true, 5, 2><<<sr->fblocks, kNlThreads, 0, st>>>(a);
     else nl_force_kernel<3, false, 4, true, true, 5, 2><<<sr->fblocks, kNlThreads, 0, st>>>(a);
+    if (sr->bonded) {
+        if (last)  // System sums the potentials in order: Lennard-Jones wrote this rank's (V, W) share, the bond adds its own
+            TMD_CHECK(launch_reduce_vw(sr->bond.partials, 1, 0.5, TMD_WANT_V | TMD_WANT_W | TMD_ACCUMULATE, sr->vw, st));
+        else  // the new positions of the bonded atoms this rank owns go to every rank's table of the next parity
+            ::tmd::count_launch(), sr_bond_push_kernel<<<1, kSrMaxBonded, 0, st>>>(sr->bond, sr->s.xu, sr->active_all[p ^ 1], sr->world);
+    }
     if (fused && !in_kernel) sr_launch_barrier(sr, 3, 3, nullptr, st, cond);
     TMD_CUDA(cudaGetLastError());
     return TMD_OK;
@@ -934,6 +1082,8 @@ int tmd_slabrun_phase(tmd_slabrun *sr, int32_t phase, int32_t last, tmd_stream_t
             else
                 ::tmd::count_launch(), sr_pre_kernel<<<ob, 256, 0, st>>>(s, sr->rec_self[0], sr->rec_below[0], sr->rec_above[0],
                                                                        sr->dt, sr->dt * 0.5, sr->a.half_skin2, sr->local_flag);
+            if (sr->bonded)
+                ::tmd::count_launch(), sr_bond_push_kernel<<<1, kSrMaxBonded, 0, st>>>(sr->bond, sr->s.xu, sr->active_all[0], sr->world);
             sr->step = -1;
             break;
         }
@@ -958,6 +1108,41 @@ int tmd_slabrun_set_langevin(tmd_slabrun *sr, const tmd_langevin_consts *consts,
     sr->noise_key = key;
     sr->noise_offset = offset;
     TMD_CUDA(cudaMemset(sr->noise_steps, 0, sizeof(unsigned long long)));
+    return TMD_OK;
+}
+
+/* A DoubleWellPair (potentials/well.py:230-286) as the system's second potential (VelocityVerlet runs): gid0 / gid1 = HOST
+ * arrays of the global indices of the atoms of types[0] / types[1], ascending (tmd_dwpair's idx0 / idx1); at most 128 atoms
+ * in all.  Call before tmd_slabrun_load. */
+int tmd_slabrun_set_dwpair(tmd_slabrun *sr, const int32_t *gid0, int32_t n0, const int32_t *gid1, int32_t n1,
+                           int32_t same_type, double rwidth, double width2, double height, const tmd_box *box) {
+    TMD_REQUIRE(sr && box && box->dim == 3, "NULL argument or not a three-dimensional box");
+    TMD_REQUIRE(!sr->loaded && !sr->langevin, "set the bond before tmd_slabrun_load; VelocityVerlet runs only");
+    const int nown = same_type ? n0 : n0 + n1;
+    TMD_REQUIRE(n0 >= 0 && n1 >= 0 && nown >= 1 && nown <= kSrMaxBonded, "between 1 and 128 atoms of the bonded types");
+    TMD_REQUIRE(gid0 || n0 == 0, "gid0 is NULL");
+    TMD_REQUIRE(same_type || gid1 || n1 == 0, "gid1 is NULL");
+    SrBond &b = sr->bond;
+    b.n0 = n0;
+    b.n1 = same_type ? 0 : n1;
+    b.same_type = same_type ? 1 : 0;
+    b.nown = nown;
+    b.rwidth = rwidth;
+    b.width2 = width2;
+    b.height = height;
+    for (int k = 0; k < 3; ++k) {
+        const bool on = box->periodic[k];
+        b.per[k] = on ? 1 : 0;
+        b.len[k] = on ? box->length[k] : 0.0;
+        b.ilen[k] = on ? box->ilength[k] : 0.0;
+        b.half[k] = on ? 0.5 * box->length[k] : 0.0;
+    }
+    int host[kSrMaxBonded];
+    for (int k = 0; k < n0; ++k) host[k] = gid0[k];
+    for (int k = 0; k < b.n1; ++k) host[n0 + k] = gid1[k];
+    TMD_CUDA(cudaMemcpy(const_cast<int *>(b.gid), host, (size_t)nown * sizeof(int), cudaMemcpyHostToDevice));
+    TMD_CUDA(cudaMemset(b.my_slot, 0xFF, kSrMaxBonded * sizeof(int)));
+    sr->bonded = 1;
     return TMD_OK;
 }
 

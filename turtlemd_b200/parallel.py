@@ -739,8 +739,13 @@ class _SlabRunRank:
         if isinstance(integrator, LangevinInertia) and not _is_device_stream(integrator.rgen):
             raise NotImplementedError("sharded Langevin dynamics needs the counter-based PhiloxNormal stream")
         pots = system.potentials
-        if len(pots) != 1 or not isinstance(pots[0], LennardJonesCut):
-            raise NotImplementedError("the resident slab run steps systems with a single LennardJonesCut potential")
+        bond = None
+        if len(pots) == 2 and isinstance(pots[0], LennardJonesCut) and isinstance(pots[1], DoubleWellPair) \
+                and isinstance(integrator, VelocityVerlet):
+            bond = pots[1]  # System sums the potentials in order: Lennard-Jones, then the pair double well
+        elif len(pots) != 1 or not isinstance(pots[0], LennardJonesCut):
+            raise NotImplementedError("the resident slab run steps one LennardJonesCut potential, optionally followed by a "
+                                      "DoubleWellPair under VelocityVerlet")
         _device.require_cuda()
         self.system, self.integrator, self.pot = system, integrator, pots[0]
         self.world, self.rank = world, rank
@@ -761,6 +766,16 @@ class _SlabRunRank:
         _lib.call("tmd_slabrun_window", self.handle, C.byref(ptr), C.byref(size))
         self.window, self.window_bytes = ptr.value, size.value
         self._vw = _device.zeros(10)
+        if bond is not None:
+            idx0, idx1, _, _ = bond._active(part)
+            same = bond.types[0] == bond.types[1]
+            if (len(idx0) if same else len(idx0) + len(idx1)) > 128 or len(idx0) == 0:
+                self.destroy()
+                raise NotImplementedError("the resident slab run takes between 1 and 128 atoms of the bonded types")
+            g0 = np.ascontiguousarray(idx0, dtype=np.int32)
+            g1 = np.ascontiguousarray(idx1, dtype=np.int32)
+            _lib.call("tmd_slabrun_set_dwpair", self.handle, _lib.hptr(g0), len(g0), _lib.hptr(g1) if len(g1) else None,
+                      len(g1), 1 if same else 0, *bond._scalars(), C.byref(box))
         self.draws_per_step = 0
         if isinstance(integrator, LangevinInertia):
             integrator.initiate_parameters(system)
