@@ -11,13 +11,18 @@
 // contiguous block of records, and "my slot s of layer z" lives at "base of that layer there + (s - base
 // here)" on the neighbour.
 //
-// One step on a rank (everything stream-ordered; launches that belong to a rebuild return at once unless the
-// step's gate word is set -- the same on every rank, see barrier):
+// One step on a rank (everything stream-ordered; launches that belong to a rebuild run only when the step's gate word is
+// set -- the same on every rank, see barrier; inside the step graph they sit in a conditional IF node):
 //     [migrate -> barrier -> collect + ghost send -> barrier -> bin -> lists -> state -> barrier]   (rebuild)
 //     traversal whose epilogue does kick + kick + drift, writes the records of the next step and STORES the
 //         records of the two boundary layers straight into the neighbours' buffers (peer memory over NVLink)
 //     barrier: every rank writes (epoch, "one of my atoms moved more than skin / 2") into every rank's
-//         mailbox and waits until all ranks of this epoch are there; the OR of the flags is the next gate.
+//         mailbox and waits until all ranks of this epoch are there; the OR of the flags is the next gate.  On real
+//         ranks the traversal block that finishes last runs it (one launch per step); emulated ranks and the
+//         rebuild phases use sr_barrier_kernel.
+// Variants: LangevinInertia (traversal leaves forces by slot, sr_langevin_kernel integrates and pushes the halo,
+// barrier kernel); a DoubleWellPair as second potential (bonded atoms' positions replicated through the windows,
+// sr_bond_force_kernel before and sr_bond_push_kernel after the traversal, barrier kernel).
 // The barrier is a spin on memory the peers write: the ranks must run on different GPUs (or, for tests, one
 // after the other on one GPU with the signal and wait halves launched separately: tmd_slabrun_phase).  Every
 // wait is bounded (~2 s), then the run is marked failed instead of hanging the box.
