@@ -743,7 +743,11 @@ int tmd_slabrun_create(tmd_slabrun **out, int32_t world, int32_t rank, int64_t n
     s.cap_own = (int64_t)(mean_layer * per * 1.25) + 2048;
     s.cap_loc = s.cap_own + 2 * s.cap_ghost;
     s.cap_mig = (int64_t)(mean_layer * 0.25) + 1024;
-    TMD_REQUIRE(s.cap_loc < (1ll << 27), "too many atoms per rank");
+    if (s.cap_loc >= (1ll << 27)) {
+        delete sr;
+        set_error("tmd_slabrun: too many atoms per rank");
+        return TMD_ERR_UNSUPPORTED;
+    }
 
     // ---- the window: what the other ranks write ----
     sr_window_layout(nullptr, world, s.cap_loc, s.cap_mig, s.cap_ghost, &sr->window_bytes);
