@@ -9,7 +9,7 @@ import socket
 import numpy as np
 import pytest
 
-from turtlemd_b200.parallel import ShardPlan, halo_ranges, replica_shard
+from turtlemd_b200.parallel import ShardPlan, halo_ranges, replica_shard, slab_layer_plan
 
 
 def test_shard_plan_covers_everything_once():
@@ -158,3 +158,57 @@ def test_two_rank_halo_exchange(n, halo):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(r[1] and r[2] == 1 for r in results), results
+
+
+# ---- resident slab run: layer plan and the all-ranks verdict ------------------------------------------------------
+
+
+def test_slab_layer_plan_invariants():
+    """Every layer is owned exactly once, ghost layers are the periodic neighbours of a slab and never own layers, the
+    two ghost layers of a rank differ; the benchmark systems: 38 layers -> 32 on eight ranks, 36 on four, 38 on two."""
+    for layers, world in ((38, 8), (38, 4), (38, 2), (24, 8), (14, 2), (6, 3), (7, 2), (4, 2)):
+        plan = slab_layer_plan(layers, world)
+        nz = (layers // world) * world
+        owned = np.zeros(nz, dtype=int)
+        for z0, z1, below, above in plan:
+            assert z1 - z0 == nz // world >= 2
+            owned[z0:z1] += 1
+            assert below == (z0 - 1) % nz and above == z1 % nz
+            assert below != above and not (z0 <= below < z1) and not (z0 <= above < z1)
+        assert np.all(owned == 1)
+    assert [p[1] - p[0] for p in slab_layer_plan(38, 8)] == [4] * 8
+    assert slab_layer_plan(38, 4)[-1][:2] == (27, 36) and slab_layer_plan(38, 2)[1] == (19, 38, 18, 0)
+    for layers, world in ((15, 8), (3, 2), (38, 1)):
+        with pytest.raises(NotImplementedError):
+            slab_layer_plan(layers, world)
+
+
+def _verdict_worker(rank, world, port, queue):
+    import torch.distributed as dist
+
+    from turtlemd_b200.parallel import all_ranks_agree
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        everyone_fine = all_ranks_agree(True)
+        one_failed = all_ranks_agree(rank != 1)  # rank 1 could not map a peer's window: nobody may go on
+        queue.put((rank, everyone_fine, one_failed))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_verdict_is_the_same_everywhere():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_verdict_worker, args=(r, 2, port, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [queue.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] is True and r[2] is False for r in results), results

@@ -726,6 +726,31 @@ SR_ERRORS = {1: "a peer did not arrive at a barrier", 2: "an atom left its slab 
              32: "own + ghost capacity exceeded", 64: "a ghost layer does not match its owner's layer"}
 
 
+def slab_layer_plan(layers: int, world: int) -> list[tuple[int, int, int, int]]:
+    """Cell layers per rank of a resident slab run: ``(z0, z1, below, above)`` for every rank -- own layers ``[z0, z1)``,
+    the two ghost layers.  ``layers`` (cells of edge rcut + skin that fit along z) is rounded down to a multiple of
+    ``world`` (thicker cells instead of uneven slabs); two layers per rank are the minimum, so that own and ghost layers
+    never coincide.  The rule of ``sr_make_grid`` (csrc/slabrun.cuh), as pure host logic."""
+    if world < 2:
+        raise NotImplementedError("a slab run needs at least two ranks")
+    nz = (layers // world) * world
+    if nz < 2 * world or nz < 3:
+        raise NotImplementedError(f"{layers} cell layers along z are too few for {world} ranks (two per rank are needed)")
+    per = nz // world
+    return [(r * per, (r + 1) * per, (r * per - 1) % nz, ((r + 1) * per) % nz) for r in range(world)]
+
+
+def all_ranks_agree(ok: bool, group=None, device=None) -> bool:
+    """True on every rank only if ``ok`` is true on every rank (an all-reduce of one word): the verdict after a step
+    that may fail on one rank only -- a rank that went on alone would wait for its peers forever."""
+    import torch
+    import torch.distributed as dist
+
+    word = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(word, op=dist.ReduceOp.MIN, group=group)
+    return bool(word.item())
+
+
 def _sr_error_text(bits: int) -> str:
     return "; ".join(text for bit, text in SR_ERRORS.items() if bits & bit) or "ok"
 
@@ -759,6 +784,9 @@ class _SlabRunRank:
         types, table, tidx = self.pot._tables(part)
         self._table = np.ascontiguousarray(table, dtype=np.float64)
         self._tidx = part._static_device(f"lj_tidx_{id(self.pot)}", tidx, np.int32) if len(types) > 1 else None
+        # the same verdict on every rank before anything is allocated: enough cell layers along z for this many ranks?
+        reach = math.sqrt(float(np.nanmax(self._table[5]))) + float(self.pot.skin)
+        self.layer_plan = slab_layer_plan(min(1024, int(float(box.length[2]) / (reach * (1.0 + 1e-6)))), world)
         self.handle = C.c_void_p()
         _lib.call("tmd_slabrun_create", C.byref(self.handle), world, rank, self.n, C.byref(box), _lib.hptr(self._table),
                   len(types), float(self.pot.skin), float(integrator.timestep))
@@ -878,9 +906,7 @@ class SlabRun:
             failure = RuntimeError("a peer could not export its window")
         # one verdict for all ranks (a rank that went on alone would wait for the others forever): after this
         # all-reduce every rank's lists exist, or every rank raises
-        ok = torch.tensor([0 if failure is not None else 1], device="cuda", dtype=torch.int32)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
-        if int(ok.item()) == 0:
+        if not all_ranks_agree(failure is None, self.group, device="cuda"):
             raise NotImplementedError(
                 f"rank {self.rank}: the resident slab run could not be set up (peer memory over CUDA IPC is required): "
                 f"{failure if failure is not None else 'a peer failed'}")
