@@ -85,6 +85,27 @@ def test_langevin_ensemble_matches_the_reference_default_rng_in_distribution():
     assert abs(np.std(x) - np.std(g["pos"])) < 0.03 * np.std(g["pos"])
 
 
+def test_stock_langevin_script_retraces_the_reference_under_the_same_seed():
+    """``LangevinInertia(timestep, gamma, beta, seed=7)`` exactly as a TurtleMD script writes it: the default generator is
+    the reference's ``default_rng(seed)`` (integrators.py:216), drawn on the host in the reference's order (:284-315), and
+    the kernels do the rest.  20 000 particles x 500 steps against the reference's own run (fixture of
+    tests/golden/make_golden_r2.py): the same trajectory, not merely the same distribution."""
+    from turtlemd_b200.integrators import LangevinInertia
+    from turtlemd_b200.potentials import DoubleWell
+    from turtlemd_b200.system import Box, Particles, System
+
+    g = load_golden("langevin_dist_default_rng.npz")
+    n, steps = int(g["n"]), int(g["steps"])
+    system = System(Box(periodic=[False]), Particles.from_arrays(np.full((n, 1), float(g["x0"]))),
+                    [DoubleWell(a=float(g["a"]), b=float(g["b"]), c=float(g["c"]))])
+    system.potential_and_force()
+    integ = LangevinInertia(timestep=float(g["dt"]), gamma=float(g["gamma"]), beta=float(g["beta"]), seed=int(g["seed"]))
+    for _ in range(steps):
+        integ(system)
+    assert rel_norm(system.particles.pos, g["pos"]) < 1e-9
+    assert rel_norm(system.particles.vel, g["vel"]) < 1e-9
+
+
 def test_langevin_replicas_reach_equipartition():
     """<v^2> = 1/(beta m) once the ensemble has equilibrated (t = 20 = 6 / gamma): 100 000 replicas, three
     standard errors (sqrt(2/n) <v^2> for a Gaussian) plus 0.5 % for the finite time step."""

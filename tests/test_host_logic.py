@@ -339,8 +339,11 @@ def test_integrator_constructors():
     assert vv.half_timestep == 0.002 and vv.dynamics == "NVE" and isinstance(vv, MDIntegrator)
     ver = Verlet(0.5)
     assert ver.timestep_squared == 0.25 and ver.half_idt == 1.0 and ver.previous_pos is None
-    default = LangevinInertia(timestep=0.002, gamma=0.3, beta=1.0, seed=5)
-    assert isinstance(default.rgen, PhiloxNormal) and default.rgen.key == 5
+    default = LangevinInertia(timestep=0.002, gamma=0.3, beta=1.0, seed=5)  # the reference's default (integrators.py:216)
+    assert isinstance(default.rgen, np.random.Generator)
+    assert default.rgen.normal() == np.random.default_rng(5).normal()
+    fast = LangevinInertia(timestep=0.002, gamma=0.3, beta=1.0, rgen=PhiloxNormal(key=5))
+    assert isinstance(fast.rgen, PhiloxNormal) and fast.rgen.key == 5
 
 
 # ---- driver loop ---------------------------------------------------------------------------------------
@@ -457,3 +460,25 @@ def test_slab_run_phase_ids_match_the_header():
     assert header == SR_PHASES
     assert _sr_error_text(0) == "ok" and "barrier" in _sr_error_text(1) and len(SR_ERRORS) == 7
     assert ";" in _sr_error_text(1 | 4)
+
+
+def test_vectorised_host_draw_equals_the_per_particle_draws():
+    """LangevinInertia.draw_random_numbers: one (n, dim, 2) call on a NumPy Generator + a batched product against the
+    reference's loop of per-particle multivariate_normal calls (integrators.py:284-315): the same stream position afterwards
+    and the same numbers (to the last bit or two: the 2 x 2 products may be contracted differently)."""
+    import turtlemd_b200.integrators as integrators
+
+    part = Particles.from_arrays(np.zeros((50, 3)), mass=1.0 + 0.5 * (np.arange(50) % 3))
+    system = System(Box(high=[10, 10, 10]), part)
+    fast = LangevinInertia(timestep=0.002, gamma=0.3, beta=2.0, seed=11)
+    pos_f, vel_f = fast.draw_random_numbers(system)
+    slow = LangevinInertia(timestep=0.002, gamma=0.3, beta=2.0, seed=11)
+    original = integrators.multivariate_normal
+    integrators.multivariate_normal = lambda rgen, mean, cho, dim: original(rgen, mean, cho, dim)  # not the original object
+    try:
+        pos_s, vel_s = slow.draw_random_numbers(system)
+    finally:
+        integrators.multivariate_normal = original
+    assert pos_f.shape == pos_s.shape == (50, 3)
+    assert np.allclose(pos_f, pos_s, rtol=1e-15, atol=0.0) and np.allclose(vel_f, vel_s, rtol=1e-14, atol=1e-18)
+    assert fast.rgen.normal() == slow.rgen.normal()  # both streams stand at the same position

@@ -6,15 +6,17 @@ is copied to the host unless the caller reads ``particles.pos`` etc.
 
 Random numbers (``LangevinOverdamped``, ``LangevinInertia``):
 
-* ``rgen`` is a :class:`turtlemd_b200.philox.PhiloxNormal` (or ``rgen=None`` for
-  ``LangevinInertia``, which then uses key = ``seed``): the normals are generated
+* ``rgen`` is a :class:`turtlemd_b200.philox.PhiloxNormal`: the normals are generated
   inside the kernel from the counter-based stream; the twin object is advanced
-  by the number of draws the reference would have made.
+  by the number of draws the reference would have made.  This is the fast path
+  (and the only one that shards over GPUs); ask for it explicitly.
 * any other object with ``.normal(loc, scale, size)`` (``numpy`` generators, the
   reference tests' ``FakeRandomGenerator``): the draws are made on the host
   exactly like the reference makes them (same calls, same order, through the
   module-level ``multivariate_normal`` looked up at call time), uploaded, and
-  the same kernels consume them.
+  the same kernels consume them.  ``LangevinInertia(rgen=None, seed=s)`` is the
+  reference's default, ``numpy.random.default_rng(s)`` (integrators.py:216): a stock
+  script retraces the reference's trajectory under the same seed.
 """
 from __future__ import annotations
 
@@ -295,9 +297,9 @@ class LangevinInertia(MDIntegrator):
     def __init__(self, timestep: float, gamma: float, beta: float, rgen: Generator | None = None, seed: int = 0):
         super().__init__(timestep=timestep, description="Langevin overdamped integrator", dynamics="stochastic")
         self.gamma = gamma
-        # reference: default_rng(seed) (PCG64 + ziggurat, a sequential stream).  Here the default
-        # is the counter-based stream with key = seed: same distribution, different numbers.
-        self.rgen = PhiloxNormal(key=seed) if rgen is None else rgen
+        # the reference's default (integrators.py:216): PCG64 + ziggurat, drawn on the host in the reference's order, so
+        # that a stock script retraces the reference under the same seed; pass rgen=PhiloxNormal(key) for in-kernel noise
+        self.rgen = np.random.default_rng(seed) if rgen is None else rgen
         self.beta = beta
         self._initiate = True
         self.param = LangevinParameter()
@@ -358,6 +360,16 @@ class LangevinInertia(MDIntegrator):
         import sys
 
         draw = sys.modules[__name__].multivariate_normal  # looked up at call time: tests monkeypatch it
+        if draw is multivariate_normal and isinstance(self.rgen, Generator):
+            # The reference makes one rgen.normal(0, 1, 2 dim) call per particle, in particle order; for a NumPy
+            # Generator that is the same stream as ONE call of shape (n, dim, 2) (probed), and
+            # mean + norm @ cho.T per particle is the batched product below: no Python loop over a million particles.
+            n = shape[0]
+            norm = self.rgen.normal(loc=0.0, scale=1.0, size=(n, dim, 2))
+            cho = np.asarray(self.param.cho, dtype=float).reshape(n, 2, 2)
+            mean = np.asarray(self.param.mean, dtype=float).reshape(n, 1, 2)
+            randxv = mean + np.matmul(norm, np.transpose(cho, (0, 2, 1)))
+            return np.ascontiguousarray(randxv[:, :, 0]), np.ascontiguousarray(randxv[:, :, 1])
         for i, (meani, choi) in enumerate(zip(self.param.mean, self.param.cho)):
             randxv = draw(self.rgen, meani, choi, dim)
             pos_rand[i] = randxv[:, 0]
