@@ -18,10 +18,7 @@ import torch
 import torch.distributed as dist
 
 import bench
-from turtlemd_b200.integrators import VelocityVerlet
 from turtlemd_b200.parallel import AtomDecomposition, SlabDecomposition, SlabRun
-from turtlemd_b200.potentials import LennardJonesCut
-from turtlemd_b200.system import Box, Particles, System
 
 
 def main():
