@@ -9,6 +9,7 @@ container, where /root/reference is mounted; the GPU box only reads the .npz fil
                               run (tmd_nlist_run_vv) directly against the reference.
   traj_vv_dimer_864.npz       config #5 in miniature on the neighbour-list path: LJ (rc = 2.5, two types with
                               identical parameters) + DoubleWellPair on two bonded atoms, 10 steps.
+  traj_langevin_inertia_lj_108_default_rng.npz  a stock LangevinInertia(seed=3) script over a 108-atom LJ fluid, 10 steps.
   langevin_dist_default_rng.npz  x, v of 20000 independent 1-D DoubleWell particles after 500 LangevinInertia steps
                               under the reference's OWN default generator (default_rng(seed), PCG64 + ziggurat):
                               the sample the "matching in distribution" gate compares the in-kernel Philox
@@ -93,8 +94,27 @@ def langevin_dist():
          n=n, steps=steps, dt=0.002, gamma=0.3, beta=1.0 / 0.07, seed=7, a=1.0, b=2.0, c=0.0, x0=-1.0)
 
 
+def langevin_lj_default_rng():
+    """config #4 in miniature exactly as a stock script writes it: LangevinInertia(timestep, gamma, beta, seed=3) -- the
+    reference's own default generator -- over a 108-atom LJ fluid, 10 bare integrator calls."""
+    from make_golden import generate_maxwell_velocities, run_traj
+
+    pos, size = lj_fluid([3] * 3, seed=71)
+    part = bulk_particles(pos)
+    generate_maxwell_velocities(part, rgen=np.random.default_rng(9), temperature=0.8)
+    pot = LennardJonesCut(dim=3, shift=True)
+    pot.set_parameters({0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}})
+    box = Box(low=size[:, 0], high=size[:, 1])
+    system = System(box=box, particles=part, potentials=[pot])
+    system.potential_and_force()
+    integ = LangevinInertia(timestep=0.005, gamma=0.3, beta=1.0 / 0.8, seed=3)
+    run_traj("traj_langevin_inertia_lj_108_default_rng.npz", system, integ, 10, first_eval=False,
+             extra=dict(low=box.low, high=box.high, dt=0.005, gamma=0.3, beta=1.0 / 0.8, seed=3))
+
+
 CASES = {"traj_vv_lj_864_hot.npz": vv_lj_864_hot, "traj_vv_dimer_864.npz": vv_dimer_864,
-         "langevin_dist_default_rng.npz": langevin_dist}
+         "langevin_dist_default_rng.npz": langevin_dist,
+         "traj_langevin_inertia_lj_108_default_rng.npz": langevin_lj_default_rng}
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(CASES)):

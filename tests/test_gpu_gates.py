@@ -106,6 +106,31 @@ def test_stock_langevin_script_retraces_the_reference_under_the_same_seed():
     assert rel_norm(system.particles.vel, g["vel"]) < 1e-9
 
 
+def test_stock_langevin_script_on_an_lj_fluid_retraces_the_reference():
+    """BASELINE.json configs[3] in miniature as a stock script writes it: ``LangevinInertia(0.005, 0.3, 1 / 0.8, seed=3)`` over
+    a 108-atom LennardJonesCut fluid, every frame of the reference's own 10-step run (positions, velocities, forces, virial,
+    potential energy) to the 10-step tolerance of the north star."""
+    from turtlemd_b200.integrators import LangevinInertia
+    from turtlemd_b200.potentials import LennardJonesCut
+    from turtlemd_b200.system import Box, Particles, System
+
+    g = load_golden("traj_langevin_inertia_lj_108_default_rng.npz")
+    pot = LennardJonesCut(dim=3, shift=True)
+    pot.set_parameters({0: dict(ONE)})
+    part = Particles.from_arrays(g["pos0"], vel=g["vel0"], mass=g["mass"], ptype=g["ptype"])
+    system = System(Box(low=g["low"], high=g["high"]), part, [pot])
+    system.potential_and_force()
+    integ = LangevinInertia(timestep=float(g["dt"]), gamma=float(g["gamma"]), beta=float(g["beta"]), seed=int(g["seed"]))
+    for frame in range(11):
+        p = system.particles
+        assert rel_norm(p.pos, g["pos"][frame]) < TRAJ_TOL, frame
+        assert rel_norm(p.vel, g["vel"][frame]) < TRAJ_TOL, frame
+        assert rel_norm(p.force, g["force"][frame]) < TRAJ_TOL, frame
+        assert rel_norm(p.virial, g["virial"][frame]) < TRAJ_TOL, frame
+        assert abs(p.v_pot - g["v_pot"][frame]) <= TRAJ_TOL * abs(g["v_pot"][frame]), frame
+        integ(system)
+
+
 def test_langevin_replicas_reach_equipartition():
     """<v^2> = 1/(beta m) once the ensemble has equilibrated (t = 20 = 6 / gamma): 100 000 replicas, three
     standard errors (sqrt(2/n) <v^2> for a Gaussian) plus 0.5 % for the finite time step."""

@@ -263,6 +263,19 @@ def test_langevin_inertia_lj_trajectory():
         stepper.step(st, ff)
 
 
+def test_langevin_inertia_lj_trajectory_under_the_reference_default_generator():
+    """The reference's own default, default_rng(seed) (integrators.py:216), fed to the oracle's stepper: the fixture the
+    reference wrote with a stock LangevinInertia(seed=3) script (tests/golden/make_golden_r2.py)."""
+    g = load_golden("traj_langevin_inertia_lj_108_default_rng.npz")
+    ff = _ff_lj(g)
+    st = to.State(g["pos0"], g["vel0"], g["mass"])
+    to._eval_all(ff, st)
+    stepper = to.InertiaStepper(float(g["dt"]), float(g["gamma"]), float(g["beta"]), np.random.default_rng(int(g["seed"])))
+    for frame in range(11):
+        _check_traj(st, g, frame)
+        stepper.step(st, ff)
+
+
 def test_langevin_constants():
     g = load_golden("langevin_constants.npz")
     for tag in "abc":
