@@ -375,6 +375,19 @@ int tmd_langevin_inertia_pre(double *pos, double *vel, const double *force, cons
 int tmd_langevin_inertia_post_pre(double *pos, double *vel, const double *force, const double *imass,
                                   int64_t n, int32_t dim, const tmd_langevin_consts *consts,
                                   const tmd_rng *rng, int64_t first, tmd_stream_t stream);
+/* The same two updates fed with STANDARD normals that are already on the device (tmd_npstream_normals below: the
+ * reference's own numpy.random.Generator stream, integrators.py:156-160 and :312): overdamped element e takes
+ * normals[e]; inertia element e takes normals[2e] and normals[2e+1] (multivariate_normal's reshape) and
+ * chol[3i .. 3i+2] = (l00, l10, l11) of particle i, the reference's np.linalg.cholesky (integrators.py:261);
+ * x-noise = l00 z0, v-noise = fma(l11, z1, l10 z0), the rounding of NumPy's norm @ cho.T.  post != 0: the previous
+ * step's closing update v = v' + b2 F is applied first (what tmd_langevin_inertia_post_pre does).        */
+int tmd_langevin_overdamped_normals(double *pos, double *vel, const double *force, const double *imass,
+                                    int64_t n, int32_t dim, double dt, double gamma, double beta,
+                                    const double *normals, tmd_stream_t stream);
+int tmd_langevin_inertia_pre_normals(double *pos, double *vel, const double *force, const double *imass,
+                                     int64_t n, int32_t dim, const tmd_langevin_consts *consts,
+                                     const double *normals, const double *chol, int32_t post,
+                                     tmd_stream_t stream);
 /* ... part 2 (after force()): v = v' + b2_i * F                                                  */
 int tmd_langevin_inertia_post(double *vel, const double *force, const double *imass,
                               int64_t n, int32_t dim, const tmd_langevin_consts *consts,
@@ -397,6 +410,29 @@ int tmd_philox_normal_fill(double *out, int64_t count, const tmd_rng *rng, tmd_s
 /* same numbers computed on the HOST by the same source (no device needed) */
 int tmd_host_philox_normal_fill(double *out, int64_t count, uint64_t key, uint64_t offset);
 int tmd_host_philox_raw_fill(uint64_t *out, int64_t count, uint64_t key, uint64_t offset);
+
+/* ------------------------------------------------------------------ NumPy's normal stream on the device
+ * numpy.random.Generator(PCG64).standard_normal(count) -- what the reference's rgen.normal(...) consumes
+ * (turtlemd/integrators.py:156-160, :312; default_rng(seed) at :216; system/particles.py:260) -- generated ON THE
+ * DEVICE, bit for bit: PCG64 (jump-ahead per chunk of 32 words) + NumPy's 256-layer ziggurat + glibc's log1p
+ * restated for the tail (csrc/npy_normal.h, csrc/npy_normal.cu).  The generator state lives on the device; a
+ * stock script keeps its trajectory without a host draw or an upload per step.
+ *   seed:    state_inc = {state hi, state lo, inc hi, inc lo} of bit_generator.state (PCG64);
+ *   normals: out[count] (device) <- the next `count` standard normals; enqueues five kernels, reads nothing back;
+ *   state:   waits for the stream, returns the generator state {hi, lo}, the 64-bit words consumed since the
+ *            seed and (tests) the chunks walked off the canonical chain; TMD_ERR_INVALID if a call's word
+ *            window was too short (never observed: > 100 sigma) -- the normals of that call are then not valid;
+ *   libm_variant: which glibc log1p build this process runs (1: FMA build, 0: baseline, -1: neither -- then
+ *            create() refuses and callers draw on the host).                                              */
+int tmd_npstream_libm_variant(void);
+int tmd_npstream_create(void **handle);
+int tmd_npstream_destroy(void *handle);
+int tmd_npstream_seed(void *handle, const uint64_t *state_inc, tmd_stream_t stream);
+int tmd_npstream_normals(void *handle, double *out, int64_t count, tmd_stream_t stream);
+int tmd_npstream_state(void *handle, uint64_t *state, uint64_t *words_consumed, uint64_t *rewalks,
+                       tmd_stream_t stream);
+/* the same stream on the HOST by the same source (no device needed); state_inc is advanced in place */
+int tmd_host_npstream_normals(uint64_t *state_inc, double *out, int64_t count, uint64_t *words_consumed);
 
 /* ---------------------------------------------------------------- slab (slot-ordered) integrators */
 /* The same updates on slot-ordered state (see the slab path above); rows = slots

@@ -155,6 +155,15 @@ PROTOTYPES = {
     "tmd_langevin_inertia_pre": [_P, _P, _P, _P, _I64, _I32, _LC, _RNG, _I64, _P, _P, _P],
     "tmd_langevin_inertia_post_pre": [_P, _P, _P, _P, _I64, _I32, _LC, _RNG, _I64, _P],
     "tmd_langevin_inertia_post": [_P, _P, _P, _I64, _I32, _LC, _P],
+    "tmd_langevin_overdamped_normals": [_P, _P, _P, _P, _I64, _I32, _D, _D, _D, _P, _P],
+    "tmd_langevin_inertia_pre_normals": [_P, _P, _P, _P, _I64, _I32, _LC, _P, _P, _I32, _P],
+    "tmd_npstream_libm_variant": [],
+    "tmd_npstream_create": [C.POINTER(_P)],
+    "tmd_npstream_destroy": [_P],
+    "tmd_npstream_seed": [_P, _P, _P],
+    "tmd_npstream_normals": [_P, _P, _I64, _P],
+    "tmd_npstream_state": [_P, _P, C.POINTER(_U64), C.POINTER(_U64), _P],
+    "tmd_host_npstream_normals": [_P, _P, _I64, C.POINTER(_U64)],
     "tmd_langevin_inertia_doublewell": [_P, _P, _P, _P, _I64, _I32, _D, _D, _D, _LC, _RNG, _I64, _I64, _I32, _P, _P],
     "tmd_counter_add": [_P, _U64, _P],
     "tmd_philox_normal_fill": [_P, _I64, _RNG, _P],
@@ -175,7 +184,7 @@ PROTOTYPES = {
     "tmd_bench_dfma": [_I32, C.POINTER(_D), C.POINTER(_D)],
     "tmd_bench_copy": [C.c_size_t, _I32, C.POINTER(_D), C.POINTER(_D)],
 }
-_NON_STATUS = {"tmd_abi_version": C.c_int, "tmd_last_error": C.c_char_p, "tmd_status_string": C.c_char_p}
+_NON_STATUS = {"tmd_npstream_libm_variant": C.c_int, "tmd_abi_version": C.c_int, "tmd_last_error": C.c_char_p, "tmd_status_string": C.c_char_p}
 
 _lib = None
 

@@ -148,7 +148,9 @@ __global__ void __launch_bounds__(256) verlet_kernel(double *__restrict__ pos, d
 
 // ---- noise ------------------------------------------------------------------------------------------
 // ---- Langevin, overdamped ------------------------------------------------------------------------
-template <int DIM, bool VEC, bool HOSTNOISE>
+// NOISE: 0 = the in-kernel Philox stream, 1 = noise drawn by the caller (already scaled), 2 = STANDARD normals of the
+// caller (tmd_npstream_normals: NumPy's own stream generated on the device), scaled here like the Philox ones
+template <int DIM, bool VEC, int NOISE>
 __global__ void __launch_bounds__(256) overdamped_kernel(double *__restrict__ pos, double *__restrict__ vel,
                                                          const double *__restrict__ force,
                                                          const double *__restrict__ imass, int64_t total,
@@ -159,11 +161,17 @@ __global__ void __launch_bounds__(256) overdamped_kernel(double *__restrict__ po
     const D2 im = ld_imass<DIM>(imass, e, two);
     D2 x = ld2<VEC>(pos, e, two);
     D2 xi;
-    if (HOSTNOISE) {
+    if (NOISE == 1) {
         xi = ld2<VEC>(noise, e, two);
     } else {
         double z0, z1;
-        two_normals(key, q_base + (uint64_t)e, two, z0, z1);
+        if (NOISE == 2) {  // rgen.normal(loc=0, scale=sigma, size=vel.shape): element e takes normal e
+            const D2 z = ld2<VEC>(noise, e, two);
+            z0 = z.a;
+            z1 = z.b;
+        } else {
+            two_normals(key, q_base + (uint64_t)e, two, z0, z1);
+        }
         // sigma = sqrt(2*dt*imass/(beta*gamma))  (integrators.py:145-147)
         const double bg = __dmul_rn(beta, gamma), tdt = __dmul_rn(2.0, dt);
         xi.a = __dmul_rn(__dsqrt_rn(__ddiv_rn(__dmul_rn(tdt, im.a), bg)), z0);
@@ -179,7 +187,11 @@ __global__ void __launch_bounds__(256) overdamped_kernel(double *__restrict__ po
 // ---- Langevin with inertia ----------------------------------------------------------------------
 // POST: the closing velocity update of the previous step, v = v' + b2 F (integrators.py:281), is applied
 // first -- the same F as this step's opening update uses -- so a run of steps needs one pass per step.
-template <int DIM, bool VEC, bool HOSTNOISE, bool POST = false>
+// NOISE as above; with NOISE == 2, noise_pos holds the standard normals (element e takes normals 2e and 2e + 1, the
+// reshape of multivariate_normal, integrators.py:312-313) and noise_vel the reference's own Cholesky factors, (l00, l10,
+// l11) per particle (np.linalg.cholesky, integrators.py:261).  norm @ cho.T is evaluated the way NumPy's matmul rounds it
+// (dgemm accumulates the second product with a fused multiply-add): x-noise = l00 z0, v-noise = fma(l11, z1, l10 z0).
+template <int DIM, bool VEC, int NOISE, bool POST = false>
 __global__ void __launch_bounds__(256) inertia_pre_kernel(double *__restrict__ pos, double *__restrict__ vel,
                                                           const double *__restrict__ force,
                                                           const double *__restrict__ imass, int64_t total,
@@ -201,9 +213,22 @@ __global__ void __launch_bounds__(256) inertia_pre_kernel(double *__restrict__ p
     const InertiaPerParticle pa = inertia_constants(c, im.a);
     const InertiaPerParticle pb = (im.b == im.a) ? pa : inertia_constants(c, im.b);
     D2 xr, vr;
-    if (HOSTNOISE) {
+    if (NOISE == 1) {
         xr = ld2<VEC>(noise_pos, e, two);
         vr = ld2<VEC>(noise_vel, e, two);
+    } else if (NOISE == 2) {
+        const D2 za = ld2<VEC>(noise_pos, 2 * e, true);
+        const double *__restrict__ ca = noise_vel + 3 * (e / DIM);
+        xr.a = __dmul_rn(ca[0], za.a);
+        vr.a = __fma_rn(ca[2], za.b, __dmul_rn(ca[1], za.a));
+        if (two) {
+            const D2 zb = ld2<VEC>(noise_pos, 2 * e + 2, true);
+            const double *__restrict__ cb = noise_vel + 3 * ((e + 1) / DIM);
+            xr.b = __dmul_rn(cb[0], zb.a);
+            vr.b = __fma_rn(cb[2], zb.b, __dmul_rn(cb[1], zb.a));
+        } else {
+            xr.b = vr.b = 0.0;
+        }
     } else {
         // element e consumes normals q_base + 2e (position) and + 2e + 1 (velocity):
         // multivariate_normal reshapes its 2*dim draws to (dim, 2)  (integrators.py:312-313)
@@ -539,6 +564,52 @@ int tmd_langevin_inertia_post_pre(double *pos, double *vel, const double *force,
     else if (dim == 2) { if (vec) TMD_IPP(2, true); else TMD_IPP(2, false); }
     else { if (vec) TMD_IPP(3, true); else TMD_IPP(3, false); }
 #undef TMD_IPP
+    TMD_CUDA(cudaGetLastError());
+    return TMD_OK;
+}
+
+int tmd_langevin_overdamped_normals(double *pos, double *vel, const double *force, const double *imass, int64_t n,
+                                    int32_t dim, double dt, double gamma, double beta, const double *normals,
+                                    tmd_stream_t stream) {
+    TMD_REQUIRE(dim >= 1 && dim <= 3 && n >= 0, "dim must be 1..3 and n >= 0");
+    TMD_REQUIRE(normals != nullptr, "normals is NULL");
+    TMD_CHECK(require_device());
+    const int64_t total = n * dim;
+    if (total == 0) return TMD_OK;
+    const bool vec = aligned16(pos) && aligned16(vel) && aligned16(force) && aligned16(normals);
+    const Launch l = ew_launch(total);
+    cudaStream_t s = as_stream(stream);
+#define TMD_ODN(D, V) \
+    ::tmd::count_launch(), overdamped_kernel<D, V, 2><<<l.blocks, l.threads, 0, s>>>(pos, vel, force, imass, total, dt, gamma, beta, 0, 0, normals)
+    if (dim == 1) { if (vec) TMD_ODN(1, true); else TMD_ODN(1, false); }
+    else if (dim == 2) { if (vec) TMD_ODN(2, true); else TMD_ODN(2, false); }
+    else { if (vec) TMD_ODN(3, true); else TMD_ODN(3, false); }
+#undef TMD_ODN
+    TMD_CUDA(cudaGetLastError());
+    return TMD_OK;
+}
+
+int tmd_langevin_inertia_pre_normals(double *pos, double *vel, const double *force, const double *imass, int64_t n,
+                                     int32_t dim, const tmd_langevin_consts *consts, const double *normals,
+                                     const double *chol, int32_t post, tmd_stream_t stream) {
+    TMD_REQUIRE(dim >= 1 && dim <= 3 && n >= 0, "dim must be 1..3 and n >= 0");
+    TMD_REQUIRE(consts != nullptr && normals != nullptr && chol != nullptr, "consts / normals / chol is NULL");
+    TMD_CHECK(require_device());
+    const int64_t total = n * dim;
+    if (total == 0) return TMD_OK;
+    const bool vec = aligned16(pos) && aligned16(vel) && aligned16(force) && aligned16(normals);
+    const Launch l = ew_launch(total);
+    cudaStream_t s = as_stream(stream);
+#define TMD_IPN(D, V, P) \
+    ::tmd::count_launch(), inertia_pre_kernel<D, V, 2, P><<<l.blocks, l.threads, 0, s>>>(pos, vel, force, imass, total, *consts, 0, 0, normals, chol, nullptr, 0)
+#define TMD_IPN_D(D)                                                            \
+    do {                                                                        \
+        if (post) { if (vec) TMD_IPN(D, true, true); else TMD_IPN(D, false, true); } \
+        else { if (vec) TMD_IPN(D, true, false); else TMD_IPN(D, false, false); }    \
+    } while (0)
+    if (dim == 1) TMD_IPN_D(1); else if (dim == 2) TMD_IPN_D(2); else TMD_IPN_D(3);
+#undef TMD_IPN_D
+#undef TMD_IPN
     TMD_CUDA(cudaGetLastError());
     return TMD_OK;
 }

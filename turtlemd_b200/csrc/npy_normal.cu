@@ -1,0 +1,469 @@
+// K8: numpy.random.Generator(PCG64).standard_normal on the device, bit for bit (npy_normal.h has the restatement and
+// the reference call sites it serves: turtlemd/integrators.py:156-160, :216, :312; turtlemd/system/particles.py:260).
+//
+// The generator is sequential by definition -- normal k starts at the 64-bit word where normal k-1 stopped, and 1.2 % of
+// the normals take more than one word -- but PCG64 can jump ahead in O(log) and "which words start a normal" is a chain
+// that re-synchronises at once: if a normal is ASSUMED to start at word w, its length is a function of the words from w on
+// alone, and 98.8 % of the words are whole normals.  So:
+//   canon    one thread per chunk of 32 words jumps to its chunk and walks it as if a normal started at word 0: a 32-bit
+//            mask of the words where normals start on that (canonical) chain and the exit offset, i.e. how many words of
+//            the next chunk its last normal eats;
+//   super    chunks are grouped 256 to a super-chunk; thread (s, e) follows super-chunk s from entry offset e = 0..31
+//            through the canonical records -- a chain that enters a chunk at a word the canonical chain also starts at IS
+//            the canonical chain from there on: count = popc(mask >> e); otherwise (about one chunk in 10^4) that chunk
+//            is re-walked from e -- and leaves (normals produced, exit offset) in a 32-entry table per super-chunk;
+//   chain    one thread runs the super-chunk tables from entry 0 (the stream position): entry offset and number of normals
+//            before every super-chunk;
+//   resolve  one thread per super-chunk repeats its walk from the true entry: entry offset and output index per chunk;
+//   emit     one thread per chunk walks its words from the true entry and stores the normals through shared memory
+//            (coalesced); the thread that produces normal `count` - 1 leaves the generator state behind it.
+// The words are never stored: every pass regenerates them from the jump (30 instructions per word).  Nothing is read
+// back: the state lives on the device (two slots, flipped by the host per call) until tmd_npstream_state asks for it.
+// An entry offset of 32 or more (one normal eating a whole chunk: probability < 1e-45) or a window that turns out too
+// short (the window is count * 1.025 + 4096 words against a measured mean of 1.02204 per normal, > 100 sigma) raise a
+// sticky status instead of producing a wrong stream.
+#if defined(TMD_NPY_EMULATE)
+#include "cuda_emul.h"  // tests/emul: the kernels below run as host threads, one block at a time (CPU test of the passes)
+#else
+#include "common.cuh"
+#define TMD_LAUNCH(kernel, grid, block, stream) kernel<<<(grid), (block), 0, (stream)>>>
+#endif
+#include "npy_normal.h"
+
+namespace tmd {
+namespace npy {
+
+constexpr int kChunk = 32;         // words per chunk (= bits of the start mask)
+constexpr int kSuper = 256;        // chunks per super-chunk
+constexpr int kEmitThreads = 128;  // chunks per block of the emit pass
+
+__device__ const uint64_t g_ki[256] = {TMD_NPY_KI_VALUES};
+__device__ const double g_wi[256] = {TMD_NPY_WI_VALUES};
+__device__ const double g_fi[256] = {TMD_NPY_FI_VALUES};
+static const uint64_t h_ki[256] = {TMD_NPY_KI_VALUES};
+static const double h_wi[256] = {TMD_NPY_WI_VALUES};
+static const double h_fi[256] = {TMD_NPY_FI_VALUES};
+
+// device words of a stream: state of slot 0 (hi, lo), state of slot 1 (hi, lo), increment (hi, lo), words consumed since
+// the seed, status, chunks re-walked off the canonical chain (a coverage counter for the tests)
+enum { W_STATE0 = 0, W_STATE1 = 2, W_INC = 4, W_CONSUMED = 6, W_STATUS = 7, W_REWALKS = 8, W_COUNT = 9 };
+enum { ST_OK = 0, ST_WINDOW = 1, ST_ENTRY = 2 };
+
+struct Stream {
+    int device = 0;
+    int slot = 0;  // which state slot is current
+    bool seeded = false;
+    bool fused = false;
+    uint64_t *words = nullptr;
+    // scratch, grown on demand
+    int64_t cap_chunks = 0;
+    uint64_t *recs = nullptr;     // canonical record per chunk: start mask | exit << 32
+    uint32_t *entry = nullptr;    // true entry offset per chunk
+    int64_t *prefix = nullptr;    // normals before the chunk (+ one closing element)
+    uint2 *table = nullptr;       // per super-chunk and entry offset: (normals, exit offset)
+    uint2 *super_in = nullptr;    // per super-chunk: (entry offset, unused) ...
+    int64_t *super_prefix = nullptr;  // ... and normals before it
+};
+
+struct SmemTables {
+    uint64_t ki[256];
+    double wi[256], fi[256];
+};
+
+__device__ __forceinline__ void load_tables(SmemTables &t) {
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+        t.ki[k] = g_ki[k];
+        t.wi[k] = g_wi[k];
+        t.fi[k] = g_fi[k];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ Pcg64 generator_at(const uint64_t *words, int slot, uint64_t word_index) {
+    Pcg64 g;
+    const u128 state = make_u128(words[2 * slot], words[2 * slot + 1]);
+    g.inc = make_u128(words[W_INC], words[W_INC + 1]);
+    g.state = pcg_advance(state, g.inc, word_index);
+    return g;
+}
+
+// Walk one chunk from word `entry`: the start mask of the chain, how many normals start in the chunk and how far the
+// last one reaches into the next chunk.  EMIT stores the normals (out[0 .. count-1]); `stop_at` >= 0 makes the walk
+// report the number of words consumed up to and including its normal number `stop_at` (0-based) in `words_at_stop`.
+template <bool EMIT>
+__device__ __forceinline__ void walk_chunk(Pcg64 g, const ZigTables &t, uint32_t entry, uint32_t &mask, uint32_t &count,
+                                           uint32_t &exit_offset, double *out, int64_t stop_at, uint32_t &words_at_stop) {
+    uint32_t pos = entry;
+    mask = 0;
+    count = 0;
+    while (pos < (uint32_t)kChunk) {
+        mask |= 1u << pos;
+        uint32_t used = 0;
+        const double z = standard_normal(g, t, used);
+        pos += used;
+        if (EMIT) {
+            out[count] = z;
+            if ((int64_t)count == stop_at) words_at_stop = pos;
+        }
+        ++count;
+    }
+    exit_offset = pos - (uint32_t)kChunk;
+}
+
+__global__ void __launch_bounds__(128) np_canon_kernel(const uint64_t *words, int slot, bool fused,
+                                                       uint64_t *__restrict__ recs, int64_t n_chunks) {
+    __shared__ SmemTables tab;
+    load_tables(tab);
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const ZigTables t = {tab.ki, tab.wi, tab.fi, fused};
+    uint32_t mask, count, exit_offset, unused = 0;
+    walk_chunk<false>(generator_at(words, slot, (uint64_t)c * kChunk), t, 0u, mask, count, exit_offset, nullptr, -1,
+                      unused);
+    recs[c] = (uint64_t)mask | ((uint64_t)exit_offset << 32);
+}
+
+// one chunk of a chain that enters it at word `e`: adds the normals it produces, leaves the entry offset of the next chunk
+__device__ __forceinline__ void follow_chunk(const uint64_t *words, int slot, bool fused, uint64_t rec,
+                                             int64_t chunk, uint32_t &e, int64_t &produced, uint64_t *status) {
+    if (e >= (uint32_t)kChunk) {  // a normal longer than a chunk: flagged, the stream is not used
+        status[0] = ST_ENTRY;
+        e = kChunk - 1;
+    }
+    const uint32_t mask = (uint32_t)rec;
+    if ((mask >> e) & 1u) {  // on the canonical chain from here on (always so for e == 0)
+        produced += __popc(mask >> e);
+        e = (uint32_t)(rec >> 32);
+    } else {
+        const ZigTables t = {g_ki, g_wi, g_fi, fused};
+        uint32_t m2, count, exit_offset, unused = 0;
+        atomicAdd(reinterpret_cast<unsigned long long *>(status + (W_REWALKS - W_STATUS)), 1ull);
+        walk_chunk<false>(generator_at(words, slot, (uint64_t)chunk * kChunk + e), t, e, m2, count, exit_offset, nullptr,
+                          -1, unused);
+        produced += count;
+        e = exit_offset;
+    }
+}
+
+__global__ void __launch_bounds__(128) np_super_kernel(uint64_t *words, int slot, bool fused,
+                                                       const uint64_t *__restrict__ recs, uint2 *__restrict__ table,
+                                                       int64_t n_supers) {
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_supers * kChunk) return;
+    const int64_t s = id / kChunk;
+    uint32_t e = (uint32_t)(id % kChunk);
+    int64_t produced = 0;
+    const int64_t c0 = s * kSuper;
+    for (int64_t c = c0; c < c0 + kSuper; ++c) follow_chunk(words, slot, fused, recs[c], c, e, produced, words + W_STATUS);
+    table[id] = make_uint2((uint32_t)produced, e);
+}
+
+__global__ void np_chain_kernel(uint64_t *words, const uint2 *__restrict__ table,
+                                uint2 *__restrict__ super_in, int64_t *__restrict__ super_prefix, int64_t n_supers,
+                                int64_t count) {
+    // rows of 32 entries staged through shared memory 32 super-chunks at a time; thread 0 runs the chain
+    __shared__ uint2 rows[32 * kChunk];
+    __shared__ uint32_t e_sh;
+    __shared__ int64_t p_sh;
+    if (threadIdx.x == 0) {
+        e_sh = 0;
+        p_sh = 0;
+    }
+    for (int64_t base = 0; base < n_supers; base += 32) {
+        const int64_t here = (n_supers - base < 32) ? n_supers - base : 32;
+        __syncthreads();
+        for (int64_t k = threadIdx.x; k < here * kChunk; k += blockDim.x) rows[k] = table[base * kChunk + k];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t e = e_sh;
+            int64_t p = p_sh;
+            for (int64_t s = 0; s < here; ++s) {
+                super_in[base + s] = make_uint2(e, 0u);
+                super_prefix[base + s] = p;
+                if (e >= (uint32_t)kChunk) {
+                    words[W_STATUS] = ST_ENTRY;
+                    e = kChunk - 1;
+                }
+                const uint2 row = rows[s * kChunk + e];
+                p += row.x;
+                e = row.y;
+            }
+            e_sh = e;
+            p_sh = p;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        super_prefix[n_supers] = p_sh;
+        if (p_sh < count && words[W_STATUS] == ST_OK) words[W_STATUS] = ST_WINDOW;
+    }
+}
+
+__global__ void __launch_bounds__(128) np_resolve_kernel(uint64_t *words, int slot, bool fused,
+                                                         const uint64_t *__restrict__ recs,
+                                                         const uint2 *__restrict__ super_in,
+                                                         const int64_t *__restrict__ super_prefix,
+                                                         uint32_t *__restrict__ entry, int64_t *__restrict__ prefix,
+                                                         int64_t n_supers) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_supers) return;
+    uint32_t e = super_in[s].x;
+    int64_t produced = super_prefix[s];
+    const int64_t c0 = s * kSuper;
+    for (int64_t c = c0; c < c0 + kSuper; ++c) {
+        entry[c] = e;
+        prefix[c] = produced;
+        follow_chunk(words, slot, fused, recs[c], c, e, produced, words + W_STATUS);
+    }
+    if (s == n_supers - 1) prefix[n_supers * kSuper] = produced;
+}
+
+__global__ void __launch_bounds__(kEmitThreads) np_emit_kernel(uint64_t *words, int slot, bool fused,
+                                                               const uint32_t *__restrict__ entry,
+                                                               const int64_t *__restrict__ prefix,
+                                                               double *__restrict__ out, int64_t count,
+                                                               int64_t n_chunks) {
+    __shared__ SmemTables tab;
+    __shared__ double stage[kEmitThreads * kChunk];
+    const int64_t c_first = (int64_t)blockIdx.x * kEmitThreads;
+    const int64_t p_first = prefix[c_first];
+    if (p_first >= count) return;  // the whole block lies behind the last normal asked for
+    load_tables(tab);
+    const int64_t c_end = (c_first + kEmitThreads < n_chunks) ? c_first + kEmitThreads : n_chunks;
+    const int64_t p_end = prefix[c_end];
+    const int64_t c = c_first + threadIdx.x;
+    if (c < n_chunks) {
+        const int64_t p = prefix[c];
+        if (p < count) {
+            const ZigTables t = {tab.ki, tab.wi, tab.fi, fused};
+            const uint32_t e = min(entry[c], (uint32_t)(kChunk - 1));
+            uint32_t mask, produced, exit_offset, words_at_stop = 0;
+            const int64_t stop_at = count - 1 - p;  // index, within this chunk, of the last normal asked for
+            walk_chunk<true>(generator_at(words, slot, (uint64_t)c * kChunk + e), t, e, mask, produced, exit_offset,
+                             stage + (p - p_first), stop_at, words_at_stop);
+            if (stop_at < (int64_t)produced && words[W_STATUS] == ST_OK) {
+                // this thread made the last normal of the call: the stream continues right behind it
+                const uint64_t consumed = (uint64_t)c * kChunk + words_at_stop;
+                const u128 inc = make_u128(words[W_INC], words[W_INC + 1]);
+                const u128 next = pcg_advance(make_u128(words[2 * slot], words[2 * slot + 1]), inc, consumed);
+                words[2 * (slot ^ 1)] = (uint64_t)(next >> 64);
+                words[2 * (slot ^ 1) + 1] = (uint64_t)next;
+                words[W_CONSUMED] += consumed;
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t n_here = ((p_end < count) ? p_end : count) - p_first;
+    for (int64_t k = threadIdx.x; k < n_here; k += kEmitThreads) out[p_first + k] = stage[k];
+}
+
+__global__ void np_seed_kernel(uint64_t *words, int slot, uint64_t s_hi, uint64_t s_lo, uint64_t i_hi,
+                               uint64_t i_lo) {
+    words[2 * slot] = s_hi;
+    words[2 * slot + 1] = s_lo;
+    words[W_INC] = i_hi;
+    words[W_INC + 1] = i_lo;
+    words[W_CONSUMED] = 0;
+    words[W_STATUS] = ST_OK;
+    words[W_REWALKS] = 0;
+}
+
+static int64_t window_chunks(int64_t count) {
+    const int64_t words = count + count / 40 + 4096;
+    const int64_t per_super = (int64_t)kChunk * kSuper;
+    return ((words + per_super - 1) / per_super) * kSuper;
+}
+
+static void release_scratch(Stream *h) {
+    cudaFree(h->recs);
+    cudaFree(h->entry);
+    cudaFree(h->prefix);
+    cudaFree(h->table);
+    cudaFree(h->super_in);
+    cudaFree(h->super_prefix);
+    h->recs = nullptr;
+    h->entry = nullptr;
+    h->prefix = nullptr;
+    h->table = nullptr;
+    h->super_in = nullptr;
+    h->super_prefix = nullptr;
+    h->cap_chunks = 0;
+}
+
+static int reserve(Stream *h, int64_t n_chunks, cudaStream_t stream) {
+    if (n_chunks <= h->cap_chunks) return TMD_OK;
+    TMD_CUDA(cudaStreamSynchronize(stream));  // launches of earlier calls may still read the old scratch
+    release_scratch(h);
+    const int64_t want = n_chunks + n_chunks / 4;
+    const int64_t chunks = ((want + kSuper - 1) / kSuper) * kSuper, supers = chunks / kSuper;
+    cudaError_t err = cudaMalloc(&h->recs, sizeof(uint64_t) * chunks);
+    if (err == cudaSuccess) err = cudaMalloc(&h->entry, sizeof(uint32_t) * chunks);
+    if (err == cudaSuccess) err = cudaMalloc(&h->prefix, sizeof(int64_t) * (chunks + 1));
+    if (err == cudaSuccess) err = cudaMalloc(&h->table, sizeof(uint2) * supers * kChunk);
+    if (err == cudaSuccess) err = cudaMalloc(&h->super_in, sizeof(uint2) * supers);
+    if (err == cudaSuccess) err = cudaMalloc(&h->super_prefix, sizeof(int64_t) * (supers + 1));
+    if (err != cudaSuccess) {
+        release_scratch(h);
+        return cuda_fail(err, "cudaMalloc (numpy stream scratch)", __FILE__, __LINE__);
+    }
+    h->cap_chunks = chunks;
+    return TMD_OK;
+}
+
+// which log1p NumPy's process runs: libm's own answers on twelve arguments where the two builds differ in the last bit
+// (found by running both restatements over 4e6 uniform arguments); 1 = the FMA build, 0 = the baseline build, -1 = neither
+static int libm_variant() {
+    static int cached = -2;
+    if (cached != -2) return cached;
+    static const uint64_t probes[12] = {
+        0xBFEFAB720963D8A9ull, 0xBFE500819F0ED9A2ull, 0xBFDA8EAF9AD6259Aull, 0xBFD636AAA46F6AF6ull,
+        0xBFD439B24026C5DAull, 0xBFD357C889E5D6A0ull, 0xBFD25E83648AA84Eull, 0xBFD17C24F95A1932ull,
+        0xBFCFC8D3ABE09D28ull, 0xBFCB4FD4CAD991ECull, 0xBFC6B0614FC5DEB0ull, 0xBFA511FAD4170590ull};
+    bool plain_ok = true, fused_ok = true;
+    for (uint64_t bits : probes) {
+        volatile double x = u64_as_double(bits);
+        const uint64_t ref = double_as_u64(log1p((double)x));
+        if (double_as_u64(log1p_glibc(x, false)) != ref) plain_ok = false;
+        if (double_as_u64(log1p_glibc(x, true)) != ref) fused_ok = false;
+    }
+    cached = fused_ok ? 1 : (plain_ok ? 0 : -1);
+    return cached;
+}
+
+}  // namespace npy
+}  // namespace tmd
+
+using namespace tmd;
+using namespace tmd::npy;
+
+extern "C" {
+
+int tmd_npstream_libm_variant(void) { return libm_variant(); }
+
+int tmd_npstream_create(void **handle) {
+    TMD_REQUIRE(handle != nullptr, "handle is NULL");
+    TMD_CHECK(require_device());
+    const int variant = libm_variant();
+    if (variant < 0) {
+        set_error("tmd_npstream_create: this libm's log1p is neither of the two glibc builds restated in npy_normal.h; "
+                  "the device stream could not match NumPy's tail draws");
+        return TMD_ERR_INVALID;
+    }
+    Stream *h = new Stream();
+    h->fused = variant == 1;
+    TMD_CUDA(cudaGetDevice(&h->device));
+    cudaError_t err = cudaMalloc(&h->words, sizeof(uint64_t) * W_COUNT);
+    if (err != cudaSuccess) {
+        delete h;
+        return cuda_fail(err, "cudaMalloc (numpy stream state)", __FILE__, __LINE__);
+    }
+    *handle = h;
+    return TMD_OK;
+}
+
+int tmd_npstream_destroy(void *handle) {
+    Stream *h = static_cast<Stream *>(handle);
+    if (!h) return TMD_OK;
+    cudaDeviceSynchronize();
+    release_scratch(h);
+    cudaFree(h->words);
+    delete h;
+    return TMD_OK;
+}
+
+int tmd_npstream_seed(void *handle, const uint64_t *state_inc, tmd_stream_t stream) {
+    Stream *h = static_cast<Stream *>(handle);
+    TMD_REQUIRE(h != nullptr && state_inc != nullptr, "handle / state is NULL");
+    TMD_REQUIRE((state_inc[3] & 1ull) == 1ull, "the PCG64 increment must be odd");
+    count_launch();
+    TMD_LAUNCH(np_seed_kernel, 1, 1, as_stream(stream))(h->words, h->slot, state_inc[0], state_inc[1], state_inc[2],
+                                                   state_inc[3]);
+    TMD_CUDA(cudaGetLastError());
+    h->seeded = true;
+    return TMD_OK;
+}
+
+int tmd_npstream_normals(void *handle, double *out, int64_t count, tmd_stream_t stream) {
+    Stream *h = static_cast<Stream *>(handle);
+    TMD_REQUIRE(h != nullptr && h->seeded, "stream is NULL or was never seeded");
+    TMD_REQUIRE(count >= 0 && (count == 0 || out != nullptr), "count must be >= 0 and out non-NULL");
+    cudaStream_t s = as_stream(stream);
+    const int64_t kMaxPerCall = (int64_t)1 << 24;  // bounds the scratch and the serial chain pass
+    for (int64_t done = 0; done < count;) {
+        const int64_t now = (count - done < kMaxPerCall) ? count - done : kMaxPerCall;
+        const int64_t n_chunks = window_chunks(now), n_supers = n_chunks / kSuper;
+        TMD_CHECK(reserve(h, n_chunks, s));
+        count_launch();
+        TMD_LAUNCH(np_canon_kernel, (unsigned)((n_chunks + 127) / 128), 128, s)(h->words, h->slot, h->fused, h->recs, n_chunks);
+        count_launch();
+        TMD_LAUNCH(np_super_kernel, (unsigned)((n_supers * kChunk + 127) / 128), 128, s)(h->words, h->slot, h->fused, h->recs,
+                                                                                 h->table, n_supers);
+        count_launch();
+        TMD_LAUNCH(np_chain_kernel, 1, 256, s)(h->words, h->table, h->super_in, h->super_prefix, n_supers, now);
+        count_launch();
+        TMD_LAUNCH(np_resolve_kernel, (unsigned)((n_supers + 127) / 128), 128, s)(h->words, h->slot, h->fused, h->recs,
+                                                                           h->super_in, h->super_prefix, h->entry,
+                                                                           h->prefix, n_supers);
+        count_launch();
+        TMD_LAUNCH(np_emit_kernel, (unsigned)((n_chunks + kEmitThreads - 1) / kEmitThreads), kEmitThreads, s)(
+            h->words, h->slot, h->fused, h->entry, h->prefix, out + done, now, n_chunks);
+        TMD_CUDA(cudaGetLastError());
+        h->slot ^= 1;
+        done += now;
+    }
+    return TMD_OK;
+}
+
+int tmd_npstream_state(void *handle, uint64_t *state, uint64_t *words_consumed, uint64_t *rewalks,
+                       tmd_stream_t stream) {
+    Stream *h = static_cast<Stream *>(handle);
+    TMD_REQUIRE(h != nullptr && h->seeded, "stream is NULL or was never seeded");
+    uint64_t host[W_COUNT];
+    TMD_CUDA(cudaMemcpyAsync(host, h->words, sizeof(host), cudaMemcpyDeviceToHost, as_stream(stream)));
+    TMD_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    if (host[W_STATUS] != ST_OK) {
+        set_error("tmd_npstream: %s", host[W_STATUS] == ST_WINDOW
+                                           ? "the word window of a call was too short for the normals asked for"
+                                           : "a single normal consumed more than a chunk of 32 words");
+        return TMD_ERR_INVALID;
+    }
+    if (state) {
+        state[0] = host[2 * h->slot];
+        state[1] = host[2 * h->slot + 1];
+    }
+    if (words_consumed) *words_consumed = host[W_CONSUMED];
+    if (rewalks) *rewalks = host[W_REWALKS];
+    return TMD_OK;
+}
+
+int tmd_host_npstream_normals(uint64_t *state_inc, double *out, int64_t count, uint64_t *words_consumed) {
+    TMD_REQUIRE(state_inc != nullptr && count >= 0 && (count == 0 || out != nullptr), "bad arguments");
+    const int variant = libm_variant();
+    TMD_REQUIRE(variant >= 0, "this libm's log1p is not one of the glibc builds restated in npy_normal.h");
+    Pcg64 g = {make_u128(state_inc[0], state_inc[1]), make_u128(state_inc[2], state_inc[3])};
+    const ZigTables t = {h_ki, h_wi, h_fi, variant == 1};
+    uint64_t total = 0;
+    for (int64_t k = 0; k < count; ++k) {
+        uint32_t used = 0;
+        out[k] = standard_normal(g, t, used);
+        total += used;
+    }
+    state_inc[0] = (uint64_t)(g.state >> 64);
+    state_inc[1] = (uint64_t)g.state;
+    if (words_consumed) *words_consumed = total;
+    return TMD_OK;
+}
+
+#if defined(TMD_NPY_EMULATE)
+// test hooks of the host emulation build only (tests/test_npy_normal.py)
+void emul_log1p(const double *x, double *y, int64_t n, int32_t fused) {
+    for (int64_t k = 0; k < n; ++k) y[k] = log1p_glibc(x[k], fused != 0);
+}
+void emul_pcg_advance(uint64_t *state_inc, uint64_t delta) {
+    const u128 s = pcg_advance(make_u128(state_inc[0], state_inc[1]), make_u128(state_inc[2], state_inc[3]), delta);
+    state_inc[0] = (uint64_t)(s >> 64);
+    state_inc[1] = (uint64_t)s;
+}
+#endif
+
+}  // extern "C"

@@ -10,13 +10,17 @@ Random numbers (``LangevinOverdamped``, ``LangevinInertia``):
   inside the kernel from the counter-based stream; the twin object is advanced
   by the number of draws the reference would have made.  This is the fast path
   (and the only one that shards over GPUs); ask for it explicitly.
-* any other object with ``.normal(loc, scale, size)`` (``numpy`` generators, the
-  reference tests' ``FakeRandomGenerator``): the draws are made on the host
-  exactly like the reference makes them (same calls, same order, through the
-  module-level ``multivariate_normal`` looked up at call time), uploaded, and
-  the same kernels consume them.  ``LangevinInertia(rgen=None, seed=s)`` is the
-  reference's default, ``numpy.random.default_rng(s)`` (integrators.py:216): a stock
-  script retraces the reference's trajectory under the same seed.
+* ``rgen`` is a NumPy ``Generator`` over ``PCG64`` -- ``numpy.random.default_rng(s)``, the
+  reference's default for ``LangevinInertia(rgen=None, seed=s)`` (integrators.py:216): the
+  generator is CONTINUED ON THE DEVICE (:mod:`turtlemd_b200.npstream`, ``tmd_npstream_*``): the
+  very normals ``rgen.normal`` would return, bit for bit, produced where the kernels consume them;
+  the host generator is moved to the position the device reached.  A stock script retraces the
+  reference's trajectory under the same seed without a host draw or an upload per step.
+* any other object with ``.normal(loc, scale, size)`` (other bit generators, the reference
+  tests' ``FakeRandomGenerator``, a monkeypatched ``multivariate_normal``): the draws are made on
+  the host exactly like the reference makes them (same calls, same order, through the
+  module-level ``multivariate_normal`` looked up at call time), uploaded, and the same kernels
+  consume them.
 """
 from __future__ import annotations
 
@@ -27,7 +31,7 @@ from abc import ABC, abstractmethod
 import numpy as np
 from numpy.random import Generator
 
-from . import _device, _lib
+from . import _device, _lib, npstream
 from .philox import PhiloxNormal
 from .potentials.well import DoubleWell, DoubleWellPair
 
@@ -204,6 +208,15 @@ class LangevinOverdamped(MDIntegrator):
         self.bddt = 0.0
         self.beta = beta
         self._initiate = True
+        self._np_stream = None
+
+    def _numpy_stream(self):
+        """The device continuation of ``rgen`` when it is a NumPy PCG64 generator, else None."""
+        if not npstream.usable(self.rgen):
+            return None
+        if self._np_stream is None or self._np_stream.rgen is not self.rgen:
+            self._np_stream = npstream.NumpyStream(self.rgen)
+        return self._np_stream
 
     def initiate_parameters(self, system):
         """sigma and dt/(m gamma) per particle (integrators.py:137-149); the kernel re-derives them from imass."""
@@ -214,31 +227,48 @@ class LangevinOverdamped(MDIntegrator):
             self._initiate = False
 
     def integration_step(self, system):
-        self._step(system, last=True)
+        self.run(system, 1)
 
     def run(self, system, steps: int):
         """``steps`` steps without touching the host in between.  The reference evaluates ``potential()`` after
         every step (integrators.py:163), but a later step overwrites it before anybody can look: only the last
         step's evaluation is made -- steps + 1 passes over the force field instead of 2 steps.  Same
         trajectory and same final ``force`` / ``virial`` / ``v_pot`` as ``steps`` single calls."""
-        for k in range(steps):
-            self._step(system, last=k == steps - 1)
+        if steps <= 0:
+            return
+        stream = None if _is_device_stream(self.rgen) else self._numpy_stream()
+        if stream is not None:
+            stream.begin()
+        try:
+            for k in range(steps):
+                self._step(system, last=k == steps - 1, stream=stream)
+        finally:
+            if stream is not None:
+                stream.end()
 
-    def _step(self, system, last: bool):
+    def _step(self, system, last: bool, stream=None):
         self.initiate_parameters(system)
         system.evaluate(_lib.WANT_F | _lib.WANT_W)
         part, n, dim, pos, vel, force, imass = _arrays(system)
         rng, noise = None, None
-        if _is_device_stream(self.rgen):
-            rng = _lib.Rng(self.rgen.key, self.rgen.position)
-            self.rgen.advance(n * dim)
+        if stream is not None:
+            # rgen.normal(loc=0, scale=sigma, size=vel.shape) (integrators.py:156-160) = sigma * the next n dim
+            # standard normals of the generator, which the device produces itself
+            normals = stream.normals(n * dim)
+            _lib.call("tmd_langevin_overdamped_normals", _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
+                      _device.dptr(imass), n, dim, float(self.timestep), float(self.gamma), float(self.beta),
+                      _device.dptr(normals), _device.stream_ptr())
         else:
-            rands = self.rgen.normal(loc=0.0, scale=self.sigma, size=part._vel.shape)
-            noise = _device.to_device(np.asarray(rands, dtype=np.float64))
-        _lib.call("tmd_langevin_overdamped", _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
-                  _device.dptr(imass), n, dim, float(self.timestep), float(self.gamma), float(self.beta),
-                  C.byref(rng) if rng is not None else None, 0,
-                  _device.dptr(noise) if noise is not None else None, _device.stream_ptr())
+            if _is_device_stream(self.rgen):
+                rng = _lib.Rng(self.rgen.key, self.rgen.position)
+                self.rgen.advance(n * dim)
+            else:
+                rands = self.rgen.normal(loc=0.0, scale=self.sigma, size=part._vel.shape)
+                noise = _device.to_device(np.asarray(rands, dtype=np.float64))
+            _lib.call("tmd_langevin_overdamped", _device.dptr(pos), _device.dptr(vel), _device.dptr(force),
+                      _device.dptr(imass), n, dim, float(self.timestep), float(self.gamma), float(self.beta),
+                      C.byref(rng) if rng is not None else None, 0,
+                      _device.dptr(noise) if noise is not None else None, _device.stream_ptr())
         part._pos.written_on_device()
         part._vel.written_on_device()
         if last:
@@ -304,6 +334,32 @@ class LangevinInertia(MDIntegrator):
         self._initiate = True
         self.param = LangevinParameter()
         self._consts = None
+        self._np_stream = None
+        self._chol_dev = None
+
+    def _numpy_stream(self):
+        """The device continuation of ``rgen`` when it is a NumPy PCG64 generator drawn from the way the reference
+        draws (stock ``draw_random_numbers`` and ``multivariate_normal``), else None."""
+        import sys
+
+        if (type(self).draw_random_numbers is not LangevinInertia.draw_random_numbers
+                or sys.modules[__name__].multivariate_normal is not multivariate_normal
+                or not npstream.usable(self.rgen)):
+            return None
+        if self._np_stream is None or self._np_stream.rgen is not self.rgen:
+            self._np_stream = npstream.NumpyStream(self.rgen)
+        return self._np_stream
+
+    def _cholesky_device(self):
+        """(l00, l10, l11) per particle of the reference's ``np.linalg.cholesky(cov_matrix)`` (integrators.py:261), on
+        the device; one factorisation per distinct mass."""
+        if self._chol_dev is None:
+            cov = self.param._cov
+            uniq, inverse = np.unique(cov.reshape(len(cov), 4), axis=0, return_inverse=True)
+            cho = np.linalg.cholesky(uniq.reshape(-1, 2, 2))
+            packed = np.stack([cho[:, 0, 0], cho[:, 1, 0], cho[:, 1, 1]], axis=1)[inverse.reshape(-1)]
+            self._chol_dev = _device.to_device(np.ascontiguousarray(packed, dtype=np.float64))
+        return self._chol_dev
 
     def initiate_parameters(self, system):
         """c0, a1, a2, b1, b2 and the noise covariance per particle (integrators.py:223-263)."""
@@ -347,6 +403,7 @@ class LangevinInertia(MDIntegrator):
         consts.one_minus_e2 = 1.0 - exp_gdt**2
         consts.one_minus_e_sq = (1.0 - exp_gdt) ** 2
         self._consts = consts
+        self._chol_dev = None
         self._initiate = False
 
     def draw_random_numbers(self, system):
@@ -384,6 +441,8 @@ class LangevinInertia(MDIntegrator):
         self.initiate_parameters(system)
         if self._fusable(system):
             return self.run(system, 1)
+        if not _is_device_stream(self.rgen) and self._numpy_stream() is not None:
+            return self._run_numpy_stream(system, 1)
         part, n, dim, pos, vel, force, imass = _arrays(system)
         stream = _device.stream_ptr()
         rng, npos, nvel = None, None, None
@@ -431,6 +490,8 @@ class LangevinInertia(MDIntegrator):
                 if self._run_resident(system, steps):
                     return None
                 return self._run_general(system, steps)
+            if steps > 0 and not _is_device_stream(self.rgen) and self._numpy_stream() is not None:
+                return self._run_numpy_stream(system, steps)
             for _ in range(steps):
                 self.integration_step(system)
             return
@@ -485,6 +546,42 @@ def _langevin_run_general(self, system, steps: int):
 
 
 LangevinInertia._run_general = _langevin_run_general
+
+
+def _langevin_run_numpy_stream(self, system, steps: int):
+    """``steps`` steps under the reference's own generator continued on the device (:mod:`turtlemd_b200.npstream`): per
+    step the next 2 n dim standard normals of ``rgen`` -- what the reference's n calls of ``multivariate_normal`` consume,
+    in its order (integrators.py:284-297, :312) -- are generated in HBM and one pass applies the closing update of the
+    previous step and the opening update of this one.  Same structure as :func:`_langevin_run_general`; the host
+    generator is moved to the device's position once, at the end."""
+    part, n, dim, pos, vel, force, imass = _arrays(system)
+    stream = _device.stream_ptr()
+    one_pass = system.energy_rides_with_forces()
+    ns = self._numpy_stream()
+    chol = self._cholesky_device()
+    ns.begin()
+    try:
+        for k in range(steps):
+            if k > 0:
+                system.evaluate(_lib.WANT_F | _lib.WANT_W)
+            normals = ns.normals(2 * n * dim)
+            _lib.call("tmd_langevin_inertia_pre_normals", _device.dptr(pos), _device.dptr(vel),
+                      _device.dptr(part._force.device()), _device.dptr(imass), n, dim, C.byref(self._consts),
+                      _device.dptr(normals), _device.dptr(chol), 1 if k > 0 else 0, stream)
+            part._pos.written_on_device()
+            part._vel.written_on_device()
+        part._pos.prefetch_host()
+        system.evaluate(_lib.WANT_F | _lib.WANT_W | (_lib.WANT_V if one_pass else 0))
+        _lib.call("tmd_langevin_inertia_post", _device.dptr(vel), _device.dptr(part._force.device()),
+                  _device.dptr(imass), n, dim, C.byref(self._consts), stream)
+        part._vel.written_on_device()
+        if not one_pass:
+            system.evaluate(_lib.WANT_V | _lib.V_STANDALONE)
+    finally:
+        ns.end()
+
+
+LangevinInertia._run_numpy_stream = _langevin_run_numpy_stream
 
 
 def _langevin_run_resident(self, system, steps: int) -> bool:
