@@ -23,6 +23,7 @@
 #define __host__
 #define __shared__ static
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
 #define __CUDACC_EMULATED__ 1

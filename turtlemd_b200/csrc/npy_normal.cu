@@ -8,17 +8,19 @@
 //   canon    one thread per chunk of 32 words jumps to its chunk and walks it as if a normal started at word 0: a 32-bit
 //            mask of the words where normals start on that (canonical) chain and the exit offset, i.e. how many words of
 //            the next chunk its last normal eats;
-//   super    chunks are grouped 256 to a super-chunk; thread (s, e) follows super-chunk s from entry offset e = 0..31
-//            through the canonical records -- a chain that enters a chunk at a word the canonical chain also starts at IS
-//            the canonical chain from there on: count = popc(mask >> e); otherwise (about one chunk in 10^4) that chunk
-//            is re-walked from e -- and leaves (normals produced, exit offset) in a 32-entry table per super-chunk;
-//   chain    one thread runs the super-chunk tables from entry 0 (the stream position): entry offset and number of normals
-//            before every super-chunk;
-//   resolve  one thread per super-chunk repeats its walk from the true entry: entry offset and output index per chunk;
+//   super    chunks are grouped 1024 to a super-chunk, one block each with the records in shared memory; lane e of its
+//            first warp follows the super-chunk from entry offset e = 0..31 -- a chain that enters a chunk at a word the
+//            canonical chain also starts at IS the canonical chain from there on: count = popc(mask >> e); otherwise
+//            (about one chunk in 3000) that chunk is re-walked from e -- and leaves (normals produced, exit offset) in a
+//            32-entry row per super-chunk;
+//   chain    one thread runs the rows from entry 0 (the stream position): entry offset and number of normals before
+//            every super-chunk;
+//   resolve  one block per super-chunk repeats the walk from the true entry: entry offset and output index per chunk;
 //   emit     one thread per chunk walks its words from the true entry and stores the normals through shared memory
 //            (coalesced); the thread that produces normal `count` - 1 leaves the generator state behind it.
-// The words are never stored: every pass regenerates them from the jump (30 instructions per word).  Nothing is read
-// back: the state lives on the device (two slots, flipped by the host per call) until tmd_npstream_state asks for it.
+// The words are never stored: canon and emit regenerate them from the jump (a table of the 64 maps "2^k steps ahead",
+// written with the seed, makes a jump one 128-bit multiply-add per set bit).  Nothing is read back: the state lives on
+// the device (two slots, flipped by the host per call) until tmd_npstream_state asks for it.
 // An entry offset of 32 or more (one normal eating a whole chunk: probability < 1e-45) or a window that turns out too
 // short (the window is count * 1.025 + 4096 words against a measured mean of 1.02204 per normal, > 100 sigma) raise a
 // sticky status instead of producing a wrong stream.
@@ -34,8 +36,9 @@ namespace tmd {
 namespace npy {
 
 constexpr int kChunk = 32;         // words per chunk (= bits of the start mask)
-constexpr int kSuper = 256;        // chunks per super-chunk
+constexpr int kSuper = 1024;       // chunks per super-chunk
 constexpr int kEmitThreads = 128;  // chunks per block of the emit pass
+constexpr int kChainTile = 256;    // super-chunk rows staged per tile of the chain pass
 
 __device__ const uint64_t g_ki[256] = {TMD_NPY_KI_VALUES};
 __device__ const double g_wi[256] = {TMD_NPY_WI_VALUES};
@@ -45,8 +48,10 @@ static const double h_wi[256] = {TMD_NPY_WI_VALUES};
 static const double h_fi[256] = {TMD_NPY_FI_VALUES};
 
 // device words of a stream: state of slot 0 (hi, lo), state of slot 1 (hi, lo), increment (hi, lo), words consumed since
-// the seed, status, chunks re-walked off the canonical chain (a coverage counter for the tests)
-enum { W_STATE0 = 0, W_STATE1 = 2, W_INC = 4, W_CONSUMED = 6, W_STATUS = 7, W_REWALKS = 8, W_COUNT = 9 };
+// the seed, status, chunks re-walked off the canonical chain (a coverage counter for the tests); then the jump table of
+// the generator: (multiplier, increment) of the map "2^k steps ahead", k = 0..63, four words each (written by the seed)
+enum { W_STATE0 = 0, W_STATE1 = 2, W_INC = 4, W_CONSUMED = 6, W_STATUS = 7, W_REWALKS = 8, W_JUMP = 16,
+       W_COUNT = W_JUMP + 4 * 64 };
 enum { ST_OK = 0, ST_WINDOW = 1, ST_ENTRY = 2 };
 
 struct Stream {
@@ -57,11 +62,11 @@ struct Stream {
     uint64_t *words = nullptr;
     // scratch, grown on demand
     int64_t cap_chunks = 0;
-    uint64_t *recs = nullptr;     // canonical record per chunk: start mask | exit << 32
-    uint32_t *entry = nullptr;    // true entry offset per chunk
-    int64_t *prefix = nullptr;    // normals before the chunk (+ one closing element)
-    uint2 *table = nullptr;       // per super-chunk and entry offset: (normals, exit offset)
-    uint2 *super_in = nullptr;    // per super-chunk: (entry offset, unused) ...
+    uint64_t *recs = nullptr;         // canonical record per chunk: start mask | exit << 32
+    uint32_t *entry = nullptr;        // true entry offset per chunk
+    int64_t *prefix = nullptr;        // normals before the chunk (+ one closing element)
+    uint32_t *table = nullptr;        // per super-chunk and entry offset: normals | exit offset << 16
+    uint32_t *super_in = nullptr;     // per super-chunk: true entry offset ...
     int64_t *super_prefix = nullptr;  // ... and normals before it
 };
 
@@ -79,17 +84,29 @@ __device__ __forceinline__ void load_tables(SmemTables &t) {
     __syncthreads();
 }
 
+// the state `delta` words ahead: one multiply-add of 128 bits per set bit of delta (the maps commute)
+__device__ __forceinline__ u128 jump_ahead(const uint64_t *words, u128 state, uint64_t delta) {
+    const uint64_t *jump = words + W_JUMP;
+    for (int k = 0; delta != 0; ++k, delta >>= 1) {
+        if (delta & 1ull)
+            state = state * make_u128(jump[4 * k], jump[4 * k + 1]) + make_u128(jump[4 * k + 2], jump[4 * k + 3]);
+    }
+    return state;
+}
+
 __device__ __forceinline__ Pcg64 generator_at(const uint64_t *words, int slot, uint64_t word_index) {
     Pcg64 g;
-    const u128 state = make_u128(words[2 * slot], words[2 * slot + 1]);
     g.inc = make_u128(words[W_INC], words[W_INC + 1]);
-    g.state = pcg_advance(state, g.inc, word_index);
+    g.state = jump_ahead(words, make_u128(words[2 * slot], words[2 * slot + 1]), word_index);
     return g;
 }
 
 // Walk one chunk from word `entry`: the start mask of the chain, how many normals start in the chunk and how far the
 // last one reaches into the next chunk.  EMIT stores the normals (out[0 .. count-1]); `stop_at` >= 0 makes the walk
 // report the number of words consumed up to and including its normal number `stop_at` (0-based) in `words_at_stop`.
+// The inner loop takes the words that are accepted on the spot -- all lanes of a warp in lock step -- and is left at a
+// wedge or tail word; the lanes that have one finish it together behind the loop (zig_slow is 5-10x a fast word, and
+// with one chunk per lane some lane meets one in a third of the iterations).
 template <bool EMIT>
 __device__ __forceinline__ void walk_chunk(Pcg64 g, const ZigTables &t, uint32_t entry, uint32_t &mask, uint32_t &count,
                                            uint32_t &exit_offset, double *out, int64_t stop_at, uint32_t &words_at_stop) {
@@ -97,15 +114,33 @@ __device__ __forceinline__ void walk_chunk(Pcg64 g, const ZigTables &t, uint32_t
     mask = 0;
     count = 0;
     while (pos < (uint32_t)kChunk) {
-        mask |= 1u << pos;
-        uint32_t used = 0;
-        const double z = standard_normal(g, t, used);
-        pos += used;
-        if (EMIT) {
-            out[count] = z;
-            if ((int64_t)count == stop_at) words_at_stop = pos;
+        uint64_t r = 0;
+        double x = 0.0;
+        bool pending = false;
+        while (pos < (uint32_t)kChunk) {
+            r = pcg_next(g);
+            mask |= 1u << pos;
+            ++pos;
+            if (!zig_fast(r, t, x)) {
+                pending = true;
+                break;
+            }
+            if (EMIT) {
+                out[count] = x;
+                if ((int64_t)count == stop_at) words_at_stop = pos;
+            }
+            ++count;
         }
-        ++count;
+        if (pending) {
+            uint32_t used = 0;
+            x = zig_slow(g, t, r, x, used);
+            pos += used;
+            if (EMIT) {
+                out[count] = x;
+                if ((int64_t)count == stop_at) words_at_stop = pos;
+            }
+            ++count;
+        }
     }
     exit_offset = pos - (uint32_t)kChunk;
 }
@@ -123,99 +158,112 @@ __global__ void __launch_bounds__(128) np_canon_kernel(const uint64_t *words, in
     recs[c] = (uint64_t)mask | ((uint64_t)exit_offset << 32);
 }
 
-// one chunk of a chain that enters it at word `e`: adds the normals it produces, leaves the entry offset of the next chunk
-__device__ __forceinline__ void follow_chunk(const uint64_t *words, int slot, bool fused, uint64_t rec,
-                                             int64_t chunk, uint32_t &e, int64_t &produced, uint64_t *status) {
+// a chunk entered at a word the canonical chain does not start at: walked again from there (about one chunk in 3000)
+__device__ __noinline__ void rewalk_chunk(uint64_t *words, int slot, bool fused, int64_t chunk, uint32_t &e,
+                                          uint32_t &produced) {
+    const ZigTables t = {g_ki, g_wi, g_fi, fused};
+    uint32_t mask, exit_offset, unused = 0;
+    atomicAdd(reinterpret_cast<unsigned long long *>(words + W_REWALKS), 1ull);
+    walk_chunk<false>(generator_at(words, slot, (uint64_t)chunk * kChunk + e), t, e, mask, produced, exit_offset,
+                      nullptr, -1, unused);
+    e = exit_offset;
+}
+
+// one chunk of a chain that enters it at word `e`: the normals it produces there and the entry offset of the next chunk
+__device__ __forceinline__ uint32_t follow_chunk(uint64_t *words, int slot, bool fused, uint64_t rec, int64_t chunk,
+                                                 uint32_t &e) {
     if (e >= (uint32_t)kChunk) {  // a normal longer than a chunk: flagged, the stream is not used
-        status[0] = ST_ENTRY;
+        words[W_STATUS] = ST_ENTRY;
         e = kChunk - 1;
     }
     const uint32_t mask = (uint32_t)rec;
+    uint32_t produced;
     if ((mask >> e) & 1u) {  // on the canonical chain from here on (always so for e == 0)
-        produced += __popc(mask >> e);
+        produced = (uint32_t)__popc(mask >> e);
         e = (uint32_t)(rec >> 32);
     } else {
-        const ZigTables t = {g_ki, g_wi, g_fi, fused};
-        uint32_t m2, count, exit_offset, unused = 0;
-        atomicAdd(reinterpret_cast<unsigned long long *>(status + (W_REWALKS - W_STATUS)), 1ull);
-        walk_chunk<false>(generator_at(words, slot, (uint64_t)chunk * kChunk + e), t, e, m2, count, exit_offset, nullptr,
-                          -1, unused);
-        produced += count;
-        e = exit_offset;
+        rewalk_chunk(words, slot, fused, chunk, e, produced);
     }
+    return produced;
 }
 
-__global__ void __launch_bounds__(128) np_super_kernel(uint64_t *words, int slot, bool fused,
-                                                       const uint64_t *__restrict__ recs, uint2 *__restrict__ table,
-                                                       int64_t n_supers) {
-    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= n_supers * kChunk) return;
-    const int64_t s = id / kChunk;
-    uint32_t e = (uint32_t)(id % kChunk);
-    int64_t produced = 0;
-    const int64_t c0 = s * kSuper;
-    for (int64_t c = c0; c < c0 + kSuper; ++c) follow_chunk(words, slot, fused, recs[c], c, e, produced, words + W_STATUS);
-    table[id] = make_uint2((uint32_t)produced, e);
+// one block per super-chunk: its 1024 records staged in shared memory, lane e of the first warp follows them from entry e
+__global__ void __launch_bounds__(256) np_super_kernel(uint64_t *words, int slot, bool fused,
+                                                       const uint64_t *__restrict__ recs, uint32_t *__restrict__ table) {
+    __shared__ uint64_t rec_s[kSuper];
+    const int64_t c0 = (int64_t)blockIdx.x * kSuper;
+    for (int k = threadIdx.x; k < kSuper; k += blockDim.x) rec_s[k] = recs[c0 + k];
+    __syncthreads();
+    if (threadIdx.x >= (unsigned)kChunk) return;
+    uint32_t e = threadIdx.x, produced = 0;
+    for (int k = 0; k < kSuper; ++k) produced += follow_chunk(words, slot, fused, rec_s[k], c0 + k, e);
+    if (e >= (uint32_t)kChunk) {
+        words[W_STATUS] = ST_ENTRY;
+        e = kChunk - 1;
+    }
+    table[(int64_t)blockIdx.x * kChunk + threadIdx.x] = produced | (e << 16);  // produced <= 32768
 }
 
-__global__ void np_chain_kernel(uint64_t *words, const uint2 *__restrict__ table,
-                                uint2 *__restrict__ super_in, int64_t *__restrict__ super_prefix, int64_t n_supers,
-                                int64_t count) {
-    // rows of 32 entries staged through shared memory 32 super-chunks at a time; thread 0 runs the chain
-    __shared__ uint2 rows[32 * kChunk];
-    __shared__ uint32_t e_sh;
-    __shared__ int64_t p_sh;
-    if (threadIdx.x == 0) {
-        e_sh = 0;
-        p_sh = 0;
-    }
-    for (int64_t base = 0; base < n_supers; base += 32) {
-        const int64_t here = (n_supers - base < 32) ? n_supers - base : 32;
+// one block: the rows of the super-chunks staged a tile at a time, thread 0 runs the chain from entry 0
+__global__ void __launch_bounds__(1024) np_chain_kernel(uint64_t *words, const uint32_t *__restrict__ table,
+                                                        uint32_t *__restrict__ super_in,
+                                                        int64_t *__restrict__ super_prefix, int64_t n_supers,
+                                                        int64_t count) {
+    __shared__ uint32_t rows[kChainTile * kChunk];
+    uint32_t e = 0;
+    int64_t p = 0;
+    for (int64_t base = 0; base < n_supers; base += kChainTile) {
+        const int64_t here = (n_supers - base < kChainTile) ? n_supers - base : kChainTile;
         __syncthreads();
         for (int64_t k = threadIdx.x; k < here * kChunk; k += blockDim.x) rows[k] = table[base * kChunk + k];
         __syncthreads();
         if (threadIdx.x == 0) {
-            uint32_t e = e_sh;
-            int64_t p = p_sh;
             for (int64_t s = 0; s < here; ++s) {
-                super_in[base + s] = make_uint2(e, 0u);
+                super_in[base + s] = e;
                 super_prefix[base + s] = p;
-                if (e >= (uint32_t)kChunk) {
-                    words[W_STATUS] = ST_ENTRY;
-                    e = kChunk - 1;
-                }
-                const uint2 row = rows[s * kChunk + e];
-                p += row.x;
-                e = row.y;
+                const uint32_t row = rows[s * kChunk + e];
+                p += row & 0xffffu;
+                e = row >> 16;
             }
-            e_sh = e;
-            p_sh = p;
         }
     }
-    __syncthreads();
     if (threadIdx.x == 0) {
-        super_prefix[n_supers] = p_sh;
-        if (p_sh < count && words[W_STATUS] == ST_OK) words[W_STATUS] = ST_WINDOW;
+        super_prefix[n_supers] = p;
+        if (p < count && words[W_STATUS] == ST_OK) words[W_STATUS] = ST_WINDOW;
     }
 }
 
-__global__ void __launch_bounds__(128) np_resolve_kernel(uint64_t *words, int slot, bool fused,
+// one block per super-chunk: thread 0 repeats the walk from the true entry, the block stores entry offset and output
+// index of every chunk
+__global__ void __launch_bounds__(256) np_resolve_kernel(uint64_t *words, int slot, bool fused,
                                                          const uint64_t *__restrict__ recs,
-                                                         const uint2 *__restrict__ super_in,
+                                                         const uint32_t *__restrict__ super_in,
                                                          const int64_t *__restrict__ super_prefix,
                                                          uint32_t *__restrict__ entry, int64_t *__restrict__ prefix,
                                                          int64_t n_supers) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_supers) return;
-    uint32_t e = super_in[s].x;
-    int64_t produced = super_prefix[s];
-    const int64_t c0 = s * kSuper;
-    for (int64_t c = c0; c < c0 + kSuper; ++c) {
-        entry[c] = e;
-        prefix[c] = produced;
-        follow_chunk(words, slot, fused, recs[c], c, e, produced, words + W_STATUS);
+    __shared__ uint64_t rec_s[kSuper];
+    __shared__ uint32_t rel_s[kSuper];
+    __shared__ unsigned char entry_s[kSuper];
+    __shared__ uint32_t total_s;
+    const int64_t c0 = (int64_t)blockIdx.x * kSuper;
+    for (int k = threadIdx.x; k < kSuper; k += blockDim.x) rec_s[k] = recs[c0 + k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t e = super_in[blockIdx.x], produced = 0;
+        for (int k = 0; k < kSuper; ++k) {
+            entry_s[k] = (unsigned char)(e < (uint32_t)kChunk ? e : kChunk - 1);
+            rel_s[k] = produced;
+            produced += follow_chunk(words, slot, fused, rec_s[k], c0 + k, e);
+        }
+        total_s = produced;
     }
-    if (s == n_supers - 1) prefix[n_supers * kSuper] = produced;
+    __syncthreads();
+    const int64_t p0 = super_prefix[blockIdx.x];
+    for (int k = threadIdx.x; k < kSuper; k += blockDim.x) {
+        entry[c0 + k] = entry_s[k];
+        prefix[c0 + k] = p0 + rel_s[k];
+    }
+    if (threadIdx.x == 0 && (int64_t)blockIdx.x == n_supers - 1) prefix[n_supers * kSuper] = p0 + total_s;
 }
 
 __global__ void __launch_bounds__(kEmitThreads) np_emit_kernel(uint64_t *words, int slot, bool fused,
@@ -244,8 +292,7 @@ __global__ void __launch_bounds__(kEmitThreads) np_emit_kernel(uint64_t *words, 
             if (stop_at < (int64_t)produced && words[W_STATUS] == ST_OK) {
                 // this thread made the last normal of the call: the stream continues right behind it
                 const uint64_t consumed = (uint64_t)c * kChunk + words_at_stop;
-                const u128 inc = make_u128(words[W_INC], words[W_INC + 1]);
-                const u128 next = pcg_advance(make_u128(words[2 * slot], words[2 * slot + 1]), inc, consumed);
+                const u128 next = jump_ahead(words, make_u128(words[2 * slot], words[2 * slot + 1]), consumed);
                 words[2 * (slot ^ 1)] = (uint64_t)(next >> 64);
                 words[2 * (slot ^ 1) + 1] = (uint64_t)next;
                 words[W_CONSUMED] += consumed;
@@ -257,8 +304,8 @@ __global__ void __launch_bounds__(kEmitThreads) np_emit_kernel(uint64_t *words, 
     for (int64_t k = threadIdx.x; k < n_here; k += kEmitThreads) out[p_first + k] = stage[k];
 }
 
-__global__ void np_seed_kernel(uint64_t *words, int slot, uint64_t s_hi, uint64_t s_lo, uint64_t i_hi,
-                               uint64_t i_lo) {
+// the seed: state, increment and the jump table (multiplier, increment) of 2^k steps, k = 0..63
+__global__ void np_seed_kernel(uint64_t *words, int slot, uint64_t s_hi, uint64_t s_lo, uint64_t i_hi, uint64_t i_lo) {
     words[2 * slot] = s_hi;
     words[2 * slot + 1] = s_lo;
     words[W_INC] = i_hi;
@@ -266,6 +313,15 @@ __global__ void np_seed_kernel(uint64_t *words, int slot, uint64_t s_hi, uint64_
     words[W_CONSUMED] = 0;
     words[W_STATUS] = ST_OK;
     words[W_REWALKS] = 0;
+    u128 mult = pcg_multiplier(), plus = make_u128(i_hi, i_lo);
+    for (int k = 0; k < 64; ++k) {
+        words[W_JUMP + 4 * k] = (uint64_t)(mult >> 64);
+        words[W_JUMP + 4 * k + 1] = (uint64_t)mult;
+        words[W_JUMP + 4 * k + 2] = (uint64_t)(plus >> 64);
+        words[W_JUMP + 4 * k + 3] = (uint64_t)plus;
+        plus = (mult + 1) * plus;
+        mult *= mult;
+    }
 }
 
 static int64_t window_chunks(int64_t count) {
@@ -299,8 +355,8 @@ static int reserve(Stream *h, int64_t n_chunks, cudaStream_t stream) {
     cudaError_t err = cudaMalloc(&h->recs, sizeof(uint64_t) * chunks);
     if (err == cudaSuccess) err = cudaMalloc(&h->entry, sizeof(uint32_t) * chunks);
     if (err == cudaSuccess) err = cudaMalloc(&h->prefix, sizeof(int64_t) * (chunks + 1));
-    if (err == cudaSuccess) err = cudaMalloc(&h->table, sizeof(uint2) * supers * kChunk);
-    if (err == cudaSuccess) err = cudaMalloc(&h->super_in, sizeof(uint2) * supers);
+    if (err == cudaSuccess) err = cudaMalloc(&h->table, sizeof(uint32_t) * supers * kChunk);
+    if (err == cudaSuccess) err = cudaMalloc(&h->super_in, sizeof(uint32_t) * supers);
     if (err == cudaSuccess) err = cudaMalloc(&h->super_prefix, sizeof(int64_t) * (supers + 1));
     if (err != cudaSuccess) {
         release_scratch(h);
@@ -396,12 +452,11 @@ int tmd_npstream_normals(void *handle, double *out, int64_t count, tmd_stream_t 
         count_launch();
         TMD_LAUNCH(np_canon_kernel, (unsigned)((n_chunks + 127) / 128), 128, s)(h->words, h->slot, h->fused, h->recs, n_chunks);
         count_launch();
-        TMD_LAUNCH(np_super_kernel, (unsigned)((n_supers * kChunk + 127) / 128), 128, s)(h->words, h->slot, h->fused, h->recs,
-                                                                                 h->table, n_supers);
+        TMD_LAUNCH(np_super_kernel, (unsigned)n_supers, 256, s)(h->words, h->slot, h->fused, h->recs, h->table);
         count_launch();
-        TMD_LAUNCH(np_chain_kernel, 1, 256, s)(h->words, h->table, h->super_in, h->super_prefix, n_supers, now);
+        TMD_LAUNCH(np_chain_kernel, 1, 1024, s)(h->words, h->table, h->super_in, h->super_prefix, n_supers, now);
         count_launch();
-        TMD_LAUNCH(np_resolve_kernel, (unsigned)((n_supers + 127) / 128), 128, s)(h->words, h->slot, h->fused, h->recs,
+        TMD_LAUNCH(np_resolve_kernel, (unsigned)n_supers, 256, s)(h->words, h->slot, h->fused, h->recs,
                                                                            h->super_in, h->super_prefix, h->entry,
                                                                            h->prefix, n_supers);
         count_launch();
@@ -418,7 +473,7 @@ int tmd_npstream_state(void *handle, uint64_t *state, uint64_t *words_consumed, 
                        tmd_stream_t stream) {
     Stream *h = static_cast<Stream *>(handle);
     TMD_REQUIRE(h != nullptr && h->seeded, "stream is NULL or was never seeded");
-    uint64_t host[W_COUNT];
+    uint64_t host[W_JUMP];  // everything but the jump table
     TMD_CUDA(cudaMemcpyAsync(host, h->words, sizeof(host), cudaMemcpyDeviceToHost, as_stream(stream)));
     TMD_CUDA(cudaStreamSynchronize(as_stream(stream)));
     if (host[W_STATUS] != ST_OK) {

@@ -180,32 +180,48 @@ TMD_HD double next_double(Pcg64 &g, uint32_t &used) {
     return TMD_MUL((double)(pcg_next(g) >> 11), 1.0 / 9007199254740992.0);
 }
 
-// One standard normal (random_standard_normal of distributions.c); `used` counts the 64-bit words it consumed.
-TMD_HD double standard_normal(Pcg64 &g, const ZigTables &t, uint32_t &used) {
+// random_standard_normal of distributions.c in two pieces, so that a kernel can run the common case of many lanes in
+// lock step and gather the rare remainder.
+// Piece 1: the candidate x of word r, and whether it is accepted on the spot (98.8 % of the words).
+TMD_HD bool zig_fast(uint64_t r, const ZigTables &t, double &x) {
+    const int idx = (int)(r & 0xff);
+    const uint64_t rabs = (r >> 9) & 0x000fffffffffffffull;
+    x = TMD_MUL((double)rabs, t.wi[idx]);
+    if ((r >> 8) & 0x1) x = -x;
+    return rabs < t.ki[idx];
+}
+
+// Piece 2: word r was not accepted on the spot; the wedge test (one more word) or the tail (two words per attempt), and
+// after a rejected wedge the whole procedure again from a fresh word.  `used` counts the words drawn here.
+TMD_HD double zig_slow(Pcg64 &g, const ZigTables &t, uint64_t r, double x, uint32_t &used) {
     const double nor_r = 3.6541528853610087963519472518, nor_inv_r = 0.27366123732975827203338247596;
     for (;;) {
-        uint64_t r = pcg_next(g);
-        ++used;
         const int idx = (int)(r & 0xff);
-        r >>= 8;
-        const int sign = (int)(r & 0x1);
-        const uint64_t rabs = (r >> 1) & 0x000fffffffffffffull;
-        double x = TMD_MUL((double)rabs, t.wi[idx]);
-        if (sign) x = -x;
-        if (rabs < t.ki[idx]) return x;  // 98.8 % of the words
         if (idx == 0) {
+            const uint64_t rabs = (r >> 9) & 0x000fffffffffffffull;
             for (;;) {
                 const double xx = TMD_MUL(-nor_inv_r, log1p_glibc(-next_double(g, used), t.fused_log1p));
                 const double yy = -log1p_glibc(-next_double(g, used), t.fused_log1p);
                 if (TMD_ADD(yy, yy) > TMD_MUL(xx, xx))
                     return ((rabs >> 8) & 0x1) ? -TMD_ADD(nor_r, xx) : TMD_ADD(nor_r, xx);
             }
-        } else {
-            const double u = next_double(g, used);
-            const double lhs = TMD_ADD(TMD_MUL(TMD_SUB(t.fi[idx - 1], t.fi[idx]), u), t.fi[idx]);
-            if (lhs < exp(TMD_MUL(TMD_MUL(-0.5, x), x))) return x;
         }
+        const double u = next_double(g, used);
+        const double lhs = TMD_ADD(TMD_MUL(TMD_SUB(t.fi[idx - 1], t.fi[idx]), u), t.fi[idx]);
+        if (lhs < exp(TMD_MUL(TMD_MUL(-0.5, x), x))) return x;
+        r = pcg_next(g);
+        ++used;
+        if (zig_fast(r, t, x)) return x;
     }
+}
+
+// One standard normal; `used` counts the 64-bit words it consumed.
+TMD_HD double standard_normal(Pcg64 &g, const ZigTables &t, uint32_t &used) {
+    const uint64_t r = pcg_next(g);
+    ++used;
+    double x;
+    if (zig_fast(r, t, x)) return x;
+    return zig_slow(g, t, r, x, used);
 }
 
 }  // namespace npy
