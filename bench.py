@@ -9,6 +9,8 @@ Prints ONE JSON line (rank 0).  Workloads (BASELINE.json configs):
   lj32k     configs[1]: LJ fluid N=32 000, all-pairs kernel
   lj1m_cells  same as lj1m with the stateless cell-list kernel
   lj1m_langevin  configs[3]: the same fluid under LangevinInertia(gamma=0.3, T=0.8), in-kernel Philox noise
+  lj1m_langevin_default_rng  the same as a stock script writes it, LangevinInertia(seed=0): the reference's
+            numpy default_rng(0) continued on the device (bit-exact PCG64 + ziggurat, csrc/npy_normal.cu)
   dimer256k   configs[4]: N=256 000 fluid, two bonded atoms of type 1 (DoubleWellPair) in LJ solvent
   replicas  configs[2]: 1M DoubleWell LangevinInertia replicas (replica-steps/s)
 For --gpus N > 1 (launched by torch.distributed.run) the LJ workloads are atom-decomposed with an
@@ -23,7 +25,7 @@ e2e       the same step through the public Python API with HOST arrays: every st
 roofline  the dominant kernel against the FP64 pipe (all-pairs, cells) or HBM (replicas)
 cpu_baseline  the CPU oracle (NumPy restatement of the reference, 1 core) on a bounded sample
 configs   (N = 1, default workload only) one short device-resident measurement of every other BASELINE.json
-          configuration -- lj32k, lj256k, dimer256k, lj1m_langevin, replicas -- so that none of them is a
+          configuration -- lj32k, lj256k, dimer256k, lj1m_langevin (+ _default_rng), replicas -- so that none is a
           builder-run claim: value, ms_per_step, roofline.frac, clocks each
 parity    (N > 1) after the timed loop rank 0 repeats the same number of steps on ONE GPU from the same
           initial state and compares positions, velocities, forces, V and W with the decomposed run
@@ -58,6 +60,10 @@ WORKLOADS = {
     "lj1m": dict(rep=63, method="nlist", dt=0.005, unit="atom-steps/s"),
     "lj1m_cells": dict(rep=63, method="cells", dt=0.005, unit="atom-steps/s"),
     "lj1m_langevin": dict(rep=63, method="nlist", dt=0.005, unit="atom-steps/s", integrator="langevin"),
+    # the same under LangevinInertia(seed=0) as a stock TurtleMD script writes it: the reference's default_rng(0),
+    # continued on the device (tmd_npstream_*, csrc/npy_normal.cu) -- the reference's own noise, bit for bit
+    "lj1m_langevin_default_rng": dict(rep=63, method="nlist", dt=0.005, unit="atom-steps/s", integrator="langevin",
+                                      rgen="default_rng"),
     "dimer256k": dict(rep=40, method="nlist", dt=0.005, unit="atom-steps/s", dimer=True),
     "replicas": dict(n=1_000_000, dt=0.002, unit="replica-steps/s"),
 }
@@ -210,6 +216,8 @@ def build_lj(cfg, skin=None):
         describe = " + DoubleWellPair dimer (types 0/1)"
     describe += (", LangevinInertia gamma=0.3 T=0.8" if cfg.get("integrator") == "langevin"
                  else f", VelocityVerlet dt={cfg['dt']}")
+    if cfg.get("rgen") == "default_rng":
+        describe += ", rgen = numpy default_rng(0) continued on the device (PCG64 + ziggurat, bit-exact)"
 
     def make():
         pot = LennardJonesCut(dim=3, shift=True, method=cfg["method"], **extra)
@@ -222,7 +230,9 @@ def build_lj(cfg, skin=None):
         else:
             pot.set_parameters(SINGLE)
         system = System(Box(low=size[:, 0], high=size[:, 1]), Particles.from_arrays(pos, vel=vel, ptype=ptype), pots)
-        if cfg.get("integrator") == "langevin":
+        if cfg.get("rgen") == "default_rng":
+            integ = LangevinInertia(timestep=cfg["dt"], gamma=0.3, beta=1.0 / 0.8, seed=0)  # integrators.py:216
+        elif cfg.get("integrator") == "langevin":
             integ = LangevinInertia(timestep=cfg["dt"], gamma=0.3, beta=1.0 / 0.8, rgen=PhiloxNormal(key=0))
         else:
             integ = VelocityVerlet(cfg["dt"])
@@ -897,7 +907,7 @@ def reference_replicas(args, cfg, world, cores, total_steps):
     }
 
 
-OTHER_CONFIGS = ("lj32k", "lj256k", "dimer256k", "lj1m_langevin", "replicas")
+OTHER_CONFIGS = ("lj32k", "lj256k", "dimer256k", "lj1m_langevin", "lj1m_langevin_default_rng", "replicas")
 OTHER_CONFIGS_MULTI = ("lj1m_langevin", "dimer256k", "replicas")  # BASELINE.json configs[3], [4], [2] on N > 1 GPUs
 
 

@@ -12,6 +12,7 @@ One JSON object per line:
 from __future__ import annotations
 
 import json
+import os
 import pathlib
 import sys
 import time
@@ -68,7 +69,10 @@ def main():
     cfg = bench.WORKLOADS["lj1m_langevin"]
     pos, vel, size, n, describe, make = bench.build_lj(cfg)
     rows = {}
+    skip_host = os.environ.get("TMD_PROF_SKIP_HOST") == "1"  # (measured once: 435 ms per step)
     for label, steps in (("device_stream", 20), ("philox", 20), ("host_draw", 3)):
+        if skip_host and label == "host_draw":
+            continue
         system, integ, pot = make()
         if label != "philox":
             integ = LangevinInertia(timestep=cfg["dt"], gamma=0.3, beta=1.0 / 0.8, seed=0)
@@ -88,6 +92,8 @@ def main():
     nrep = 1_000_000
     reps = {}
     for label, steps in (("device_stream", 20), ("host_draw", 3)):
+        if skip_host and label == "host_draw":
+            continue
         x0 = np.full((nrep, 1), -1.0)
         system = System(Box(periodic=[False]), Particles.from_arrays(x0), [DoubleWell(a=1.0, b=2.0, c=0.0)])
         system.potential_and_force()

@@ -75,15 +75,6 @@ struct SmemTables {
     double wi[256], fi[256];
 };
 
-__device__ __forceinline__ void load_tables(SmemTables &t) {
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) {
-        t.ki[k] = g_ki[k];
-        t.wi[k] = g_wi[k];
-        t.fi[k] = g_fi[k];
-    }
-    __syncthreads();
-}
-
 // the state `delta` words ahead: one multiply-add of 128 bits per set bit of delta (the maps commute)
 __device__ __forceinline__ u128 jump_ahead(const uint64_t *words, u128 state, uint64_t delta) {
     const uint64_t *jump = words + W_JUMP;
@@ -92,6 +83,34 @@ __device__ __forceinline__ u128 jump_ahead(const uint64_t *words, u128 state, ui
             state = state * make_u128(jump[4 * k], jump[4 * k + 1]) + make_u128(jump[4 * k + 2], jump[4 * k + 3]);
     }
     return state;
+}
+
+struct SmemBlock {
+    SmemTables tab;
+    uint64_t base[2];  // generator state at the first word of the block's first chunk
+};
+
+// the ziggurat tables into shared memory; thread 0 meanwhile jumps to the block's first word, so that every thread is a
+// short jump (its chunk within the block) away from its own
+__device__ __forceinline__ void load_block(SmemBlock &b, const uint64_t *words, int slot, uint64_t block_word) {
+    if (threadIdx.x == 0) {
+        const u128 s = jump_ahead(words, make_u128(words[2 * slot], words[2 * slot + 1]), block_word);
+        b.base[0] = (uint64_t)(s >> 64);
+        b.base[1] = (uint64_t)s;
+    }
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+        b.tab.ki[k] = g_ki[k];
+        b.tab.wi[k] = g_wi[k];
+        b.tab.fi[k] = g_fi[k];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ Pcg64 generator_in_block(const SmemBlock &b, const uint64_t *words, uint64_t local_word) {
+    Pcg64 g;
+    g.inc = make_u128(words[W_INC], words[W_INC + 1]);
+    g.state = jump_ahead(words, make_u128(b.base[0], b.base[1]), local_word);
+    return g;
 }
 
 __device__ __forceinline__ Pcg64 generator_at(const uint64_t *words, int slot, uint64_t word_index) {
@@ -147,14 +166,14 @@ __device__ __forceinline__ void walk_chunk(Pcg64 g, const ZigTables &t, uint32_t
 
 __global__ void __launch_bounds__(128) np_canon_kernel(const uint64_t *words, int slot, bool fused,
                                                        uint64_t *__restrict__ recs, int64_t n_chunks) {
-    __shared__ SmemTables tab;
-    load_tables(tab);
+    __shared__ SmemBlock sm;
+    load_block(sm, words, slot, (uint64_t)blockIdx.x * blockDim.x * kChunk);
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chunks) return;
-    const ZigTables t = {tab.ki, tab.wi, tab.fi, fused};
+    const ZigTables t = {sm.tab.ki, sm.tab.wi, sm.tab.fi, fused};
     uint32_t mask, count, exit_offset, unused = 0;
-    walk_chunk<false>(generator_at(words, slot, (uint64_t)c * kChunk), t, 0u, mask, count, exit_offset, nullptr, -1,
-                      unused);
+    walk_chunk<false>(generator_in_block(sm, words, (uint64_t)threadIdx.x * kChunk), t, 0u, mask, count, exit_offset,
+                      nullptr, -1, unused);
     recs[c] = (uint64_t)mask | ((uint64_t)exit_offset << 32);
 }
 
@@ -271,24 +290,24 @@ __global__ void __launch_bounds__(kEmitThreads) np_emit_kernel(uint64_t *words, 
                                                                const int64_t *__restrict__ prefix,
                                                                double *__restrict__ out, int64_t count,
                                                                int64_t n_chunks) {
-    __shared__ SmemTables tab;
+    __shared__ SmemBlock sm;
     __shared__ double stage[kEmitThreads * kChunk];
     const int64_t c_first = (int64_t)blockIdx.x * kEmitThreads;
     const int64_t p_first = prefix[c_first];
     if (p_first >= count) return;  // the whole block lies behind the last normal asked for
-    load_tables(tab);
+    load_block(sm, words, slot, (uint64_t)c_first * kChunk);
     const int64_t c_end = (c_first + kEmitThreads < n_chunks) ? c_first + kEmitThreads : n_chunks;
     const int64_t p_end = prefix[c_end];
     const int64_t c = c_first + threadIdx.x;
     if (c < n_chunks) {
         const int64_t p = prefix[c];
         if (p < count) {
-            const ZigTables t = {tab.ki, tab.wi, tab.fi, fused};
+            const ZigTables t = {sm.tab.ki, sm.tab.wi, sm.tab.fi, fused};
             const uint32_t e = min(entry[c], (uint32_t)(kChunk - 1));
             uint32_t mask, produced, exit_offset, words_at_stop = 0;
             const int64_t stop_at = count - 1 - p;  // index, within this chunk, of the last normal asked for
-            walk_chunk<true>(generator_at(words, slot, (uint64_t)c * kChunk + e), t, e, mask, produced, exit_offset,
-                             stage + (p - p_first), stop_at, words_at_stop);
+            walk_chunk<true>(generator_in_block(sm, words, (uint64_t)threadIdx.x * kChunk + e), t, e, mask, produced,
+                             exit_offset, stage + (p - p_first), stop_at, words_at_stop);
             if (stop_at < (int64_t)produced && words[W_STATUS] == ST_OK) {
                 // this thread made the last normal of the call: the stream continues right behind it
                 const uint64_t consumed = (uint64_t)c * kChunk + words_at_stop;
