@@ -418,9 +418,9 @@ int tmd_host_philox_raw_fill(uint64_t *out, int64_t count, uint64_t key, uint64_
  * restated for the tail (csrc/npy_normal.h, csrc/npy_normal.cu).  The generator state lives on the device; a
  * stock script keeps its trajectory without a host draw or an upload per step.
  *   seed:    state_inc = {state hi, state lo, inc hi, inc lo} of bit_generator.state (PCG64);
- *   normals: out[count] (device) <- the next `count` standard normals; enqueues five kernels, reads nothing back;
+ *   normals: out[count] (device) <- the next `count` standard normals; enqueues four kernels, reads nothing back;
  *   state:   waits for the stream, returns the generator state {hi, lo}, the 64-bit words consumed since the
- *            seed and (tests) the chunks walked off the canonical chain; TMD_ERR_INVALID if a call's word
+ *            seed and (tests) counters[2] = chunks walked again off the canonical chain by any pass, chunks placed off it; TMD_ERR_INVALID if a call's word
  *            window was too short (never observed: > 100 sigma) -- the normals of that call are then not valid;
  *   libm_variant: which glibc log1p build this process runs (1: FMA build, 0: baseline, -1: neither -- then
  *            create() refuses and callers draw on the host).                                              */
@@ -429,7 +429,7 @@ int tmd_npstream_create(void **handle);
 int tmd_npstream_destroy(void *handle);
 int tmd_npstream_seed(void *handle, const uint64_t *state_inc, tmd_stream_t stream);
 int tmd_npstream_normals(void *handle, double *out, int64_t count, tmd_stream_t stream);
-int tmd_npstream_state(void *handle, uint64_t *state, uint64_t *words_consumed, uint64_t *rewalks,
+int tmd_npstream_state(void *handle, uint64_t *state, uint64_t *words_consumed, uint64_t *counters,
                        tmd_stream_t stream);
 /* the same stream on the HOST by the same source (no device needed); state_inc is advanced in place */
 int tmd_host_npstream_normals(uint64_t *state_inc, double *out, int64_t count, uint64_t *words_consumed);

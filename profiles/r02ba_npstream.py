@@ -60,11 +60,11 @@ def main():
     pinned = torch.from_numpy(host).pin_memory()
     dev = torch.empty(count, dtype=torch.float64, device="cuda")
     t_up = device_ms(lambda: dev.copy_(pinned, non_blocking=True), 5)
-    words, rewalks = stream.stats()
+    words, rewalks, off_chain = stream.stats()
     print(json.dumps({"what": "generator", "normals_per_call": count, "bit_exact_vs_numpy": exact,
                       "device_ms_per_call": ms, "device_normals_per_s": count / ms * 1e3,
                       "out_bytes_per_s": 8 * count / ms * 1e3, "host_numpy_ms": t_host, "h2d_pinned_ms": t_up,
-                      "words_per_normal": words / (24.0 * count), "rewalks": rewalks}), flush=True)
+                      "words_per_normal": words / (24.0 * count), "rewalks": rewalks, "chunks_placed_off_chain": off_chain}), flush=True)
 
     cfg = bench.WORKLOADS["lj1m_langevin"]
     pos, vel, size, n, describe, make = bench.build_lj(cfg)

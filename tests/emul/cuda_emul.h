@@ -39,6 +39,7 @@ struct uint2 {
 };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
     return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
@@ -47,7 +48,7 @@ using std::min;
 
 namespace emul {
 static std::unique_ptr<std::barrier<>> g_barrier;
-static thread_local bool g_dropped = false;
+static std::vector<std::unique_ptr<std::barrier<>>> g_warp_barriers;  // __syncwarp: the 32 threads of a warp
 
 template <class F>
 static void run(unsigned grid, unsigned block, F body) {
@@ -56,6 +57,9 @@ static void run(unsigned grid, unsigned block, F body) {
     for (unsigned b = 0; b < grid; ++b) {
         blockIdx.x = b;
         g_barrier = std::make_unique<std::barrier<>>((std::ptrdiff_t)block);
+        g_warp_barriers.clear();
+        for (unsigned w = 0; w < block; w += 32)
+            g_warp_barriers.push_back(std::make_unique<std::barrier<>>((std::ptrdiff_t)std::min(32u, block - w)));
         std::vector<std::thread> threads;
         threads.reserve(block);
         for (unsigned t = 0; t < block; ++t)
@@ -63,6 +67,7 @@ static void run(unsigned grid, unsigned block, F body) {
                 threadIdx.x = t;
                 body();
                 g_barrier->arrive_and_drop();  // a thread that has returned no longer takes part in later barriers
+                g_warp_barriers[t / 32]->arrive_and_drop();
             });
         for (auto &th : threads) th.join();
     }
@@ -84,6 +89,7 @@ static Bound<K> bind(K kernel, unsigned grid, unsigned block) {
 }  // namespace emul
 
 static inline void __syncthreads() { emul::g_barrier->arrive_and_wait(); }
+static inline void __syncwarp() { emul::g_warp_barriers[threadIdx.x / 32]->arrive_and_wait(); }
 #define TMD_LAUNCH(kernel, grid, block, stream) ::emul::bind(kernel, (grid), (block))
 
 // ---- the slice of the runtime API / library plumbing the file uses ---------------------------------------------

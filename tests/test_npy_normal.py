@@ -132,8 +132,8 @@ def test_pcg_jump_ahead_is_numpy_advance(emul):
 def test_device_passes_reproduce_numpy(emul):
     handle = C.c_void_p()
     assert emul.tmd_npstream_create(C.byref(handle)) == 0
-    rewalks_seen = 0
-    for seed, counts in ((0, [6, 1, 0, 7, 100, 4097, 50_000, 3]), (3, [120_000, 13]), (2 ** 63 + 5, [33_000, 33_000])):
+    rewalks_seen = off_chain_seen = 0
+    for seed, counts in ((0, [6, 1, 0, 7, 100, 4097, 50_000, 3]), (3, [400_000, 13]), (2 ** 63 + 5, [33_000, 33_000])):
         rgen = np.random.default_rng(seed)
         words = state_words(rgen)
         assert emul.tmd_npstream_seed(handle, _ptr(words), None) == 0
@@ -145,14 +145,34 @@ def test_device_passes_reproduce_numpy(emul):
             assert same_bits(out[:n], ref), (seed, n)
             assert (out[n:] == -77.0).all()  # nothing written behind the normals asked for
             state = np.zeros(2, dtype=np.uint64)
-            used, rewalks = C.c_uint64(0), C.c_uint64(0)
-            rc = emul.tmd_npstream_state(handle, _ptr(state), C.byref(used), C.byref(rewalks), None)
+            used, counters = C.c_uint64(0), np.zeros(2, dtype=np.uint64)
+            rc = emul.tmd_npstream_state(handle, _ptr(state), C.byref(used), _ptr(counters), None)
             assert rc == 0, emul.emul_last_error()
             assert np.array_equal(state, state_words(rgen)[:2]), (seed, n)  # the stream continues where NumPy stands
             assert used.value >= total_words + n
             total_words = used.value
-        rewalks_seen += rewalks.value
-    assert rewalks_seen > 0  # chains off the canonical one were met and re-walked
+        rewalks_seen += int(counters[0])
+        off_chain_seen += int(counters[1])
+    assert rewalks_seen > 0  # chains off the canonical one were met and walked again ...
+    assert off_chain_seen > 0  # ... also by the pass that places the normals (a true entry off the canonical chain)
+    assert emul.tmd_npstream_destroy(handle) == 0
+
+
+def test_device_passes_many_short_calls(emul):
+    """The stream picked up again and again at arbitrary places (every call ends inside some chunk, the next one starts
+    there): outputs and generator state after each of 30 calls of random length."""
+    handle = C.c_void_p()
+    assert emul.tmd_npstream_create(C.byref(handle)) == 0
+    rgen = np.random.default_rng(99)
+    assert emul.tmd_npstream_seed(handle, _ptr(state_words(rgen)), None) == 0
+    for n in np.random.default_rng(1).integers(1, 3000, size=30):
+        n = int(n)
+        out = np.full(n + 4, -77.0)
+        assert emul.tmd_npstream_normals(handle, _ptr(out), C.c_int64(n), None) == 0, emul.emul_last_error()
+        assert same_bits(out[:n], rgen.standard_normal(n)) and (out[n:] == -77.0).all()
+        state = np.zeros(2, dtype=np.uint64)
+        assert emul.tmd_npstream_state(handle, _ptr(state), None, None, None) == 0, emul.emul_last_error()
+        assert np.array_equal(state, state_words(rgen)[:2])
     assert emul.tmd_npstream_destroy(handle) == 0
 
 
@@ -226,7 +246,7 @@ def test_gpu_stream_is_numpy_bit_for_bit():
     stream.end()
     assert same_bits(a, twin.standard_normal(1000)) and same_bits(b, twin.standard_normal(50))
     assert rgen.bit_generator.state == twin.bit_generator.state
-    words, rewalks = stream.stats()
+    words, rewalks, off_chain = stream.stats()
     assert words > 1050 and rewalks > 0
 
 

@@ -162,7 +162,7 @@ PROTOTYPES = {
     "tmd_npstream_destroy": [_P],
     "tmd_npstream_seed": [_P, _P, _P],
     "tmd_npstream_normals": [_P, _P, _I64, _P],
-    "tmd_npstream_state": [_P, _P, C.POINTER(_U64), C.POINTER(_U64), _P],
+    "tmd_npstream_state": [_P, _P, C.POINTER(_U64), _P, _P],
     "tmd_host_npstream_normals": [_P, _P, _I64, C.POINTER(_U64)],
     "tmd_langevin_inertia_doublewell": [_P, _P, _P, _P, _I64, _I32, _D, _D, _D, _LC, _RNG, _I64, _I64, _I32, _P, _P],
     "tmd_counter_add": [_P, _U64, _P],

@@ -5,25 +5,26 @@
 // the normals take more than one word -- but PCG64 can jump ahead in O(log) and "which words start a normal" is a chain
 // that re-synchronises at once: if a normal is ASSUMED to start at word w, its length is a function of the words from w on
 // alone, and 98.8 % of the words are whole normals.  So:
-//   canon    one thread per chunk of 32 words jumps to its chunk and walks it as if a normal started at word 0: a 32-bit
-//            mask of the words where normals start on that (canonical) chain and the exit offset, i.e. how many words of
-//            the next chunk its last normal eats;
-//   super    chunks are grouped 1024 to a super-chunk, one block each with the records in shared memory; lane e of its
-//            first warp follows the super-chunk from entry offset e = 0..31 -- a chain that enters a chunk at a word the
-//            canonical chain also starts at IS the canonical chain from there on: count = popc(mask >> e); otherwise
-//            (about one chunk in 3000) that chunk is re-walked from e -- and leaves (normals produced, exit offset) in a
-//            32-entry row per super-chunk;
-//   chain    one thread runs the rows from entry 0 (the stream position): entry offset and number of normals before
-//            every super-chunk;
-//   resolve  one block per super-chunk repeats the walk from the true entry: entry offset and output index per chunk;
-//   emit     one thread per chunk walks its words from the true entry and stores the normals through shared memory
-//            (coalesced); the thread that produces normal `count` - 1 leaves the generator state behind it.
-// The words are never stored: canon and emit regenerate them from the jump (a table of the 64 maps "2^k steps ahead",
-// written with the seed, makes a jump one 128-bit multiply-add per set bit).  Nothing is read back: the state lives on
-// the device (two slots, flipped by the host per call) until tmd_npstream_state asks for it.
-// An entry offset of 32 or more (one normal eating a whole chunk: probability < 1e-45) or a window that turns out too
-// short (the window is count * 1.025 + 4096 words against a measured mean of 1.02204 per normal, > 100 sigma) raise a
-// sticky status instead of producing a wrong stream.
+//   canon    one thread per chunk of 32 words jumps to its chunk and walks it as if a normal started at word 0: the
+//            normals of that (canonical) chain into the chunk's slot of a scratch buffer, a 32-bit mask of the words
+//            where they start and the exit offset, i.e. how many words of the next chunk the last one eats;
+//   super    1024 chunks make a super-chunk (one block, records in shared memory), 128 a segment (one warp): lane e
+//            follows its segment from entry offset e = 0..31 -- a chain that enters a chunk at a word the canonical chain
+//            also starts at IS the canonical chain from there on: count = popc(mask >> e); otherwise (about one chunk
+//            in 3000) that chunk is walked again from e -- and leaves (normals produced, exit offset); the first warp
+//            then composes the eight segment rows into the row of the super-chunk;
+//   chain    one thread runs the super-chunk rows from entry 0 (the stream position): entry offset and number of normals
+//            before every super-chunk;
+//   place    one block per super-chunk: the true entry through the segment rows, eight threads through their segments
+//            (entry offset and output index of every chunk), then every warp moves whole chunks from the scratch buffer
+//            to their place in the output -- the canonical normals from the entry word on; a chunk entered off the
+//            canonical chain is generated again.  The thread that places normal `count` - 1 leaves the generator state
+//            behind it.
+// A jump is one 128-bit multiply-add per set bit (a table of the 64 maps "2^k steps ahead" is written with the seed).
+// Nothing is read back: the state lives on the device (two slots, flipped by the host per call) until tmd_npstream_state
+// asks for it.  An entry offset of 32 or more (one normal eating a whole chunk: probability < 1e-45) or a window that
+// turns out too short (the window is count * 1.025 + 4096 words against a measured mean of 1.02204 per normal, > 100
+// sigma) raise a sticky status instead of producing a wrong stream.
 #if defined(TMD_NPY_EMULATE)
 #include "cuda_emul.h"  // tests/emul: the kernels below run as host threads, one block at a time (CPU test of the passes)
 #else
@@ -35,10 +36,13 @@
 namespace tmd {
 namespace npy {
 
-constexpr int kChunk = 32;         // words per chunk (= bits of the start mask)
-constexpr int kSuper = 1024;       // chunks per super-chunk
-constexpr int kEmitThreads = 128;  // chunks per block of the emit pass
-constexpr int kChainTile = 256;    // super-chunk rows staged per tile of the chain pass
+constexpr int kChunk = 32;        // words per chunk (= bits of the start mask)
+constexpr int kSeg = 128;         // chunks per segment (one warp of the super pass)
+constexpr int kSegs = 8;          // segments per super-chunk
+constexpr int kSuper = kSeg * kSegs;  // chunks per super-chunk
+constexpr int kChainTile = 256;   // super-chunk rows staged per tile of the chain pass
+constexpr int kPlaceThreads = 1024;
+constexpr unsigned kOffChain = 0x80u;  // entry byte: the chunk is entered off the canonical chain
 
 __device__ const uint64_t g_ki[256] = {TMD_NPY_KI_VALUES};
 __device__ const double g_wi[256] = {TMD_NPY_WI_VALUES};
@@ -48,9 +52,10 @@ static const double h_wi[256] = {TMD_NPY_WI_VALUES};
 static const double h_fi[256] = {TMD_NPY_FI_VALUES};
 
 // device words of a stream: state of slot 0 (hi, lo), state of slot 1 (hi, lo), increment (hi, lo), words consumed since
-// the seed, status, chunks re-walked off the canonical chain (a coverage counter for the tests); then the jump table of
-// the generator: (multiplier, increment) of the map "2^k steps ahead", k = 0..63, four words each (written by the seed)
-enum { W_STATE0 = 0, W_STATE1 = 2, W_INC = 4, W_CONSUMED = 6, W_STATUS = 7, W_REWALKS = 8, W_JUMP = 16,
+// the seed, status, chunks walked again off the canonical chain by any pass and chunks PLACED off it (coverage counters
+// for the tests); then the jump table
+// of the generator: (multiplier, increment) of the map "2^k steps ahead", k = 0..63, four words each (written by the seed)
+enum { W_STATE0 = 0, W_STATE1 = 2, W_INC = 4, W_CONSUMED = 6, W_STATUS = 7, W_REWALKS = 8, W_OFFCHAIN = 9, W_JUMP = 16,
        W_COUNT = W_JUMP + 4 * 64 };
 enum { ST_OK = 0, ST_WINDOW = 1, ST_ENTRY = 2 };
 
@@ -63,9 +68,9 @@ struct Stream {
     // scratch, grown on demand
     int64_t cap_chunks = 0;
     uint64_t *recs = nullptr;         // canonical record per chunk: start mask | exit << 32
-    uint32_t *entry = nullptr;        // true entry offset per chunk
-    int64_t *prefix = nullptr;        // normals before the chunk (+ one closing element)
-    uint32_t *table = nullptr;        // per super-chunk and entry offset: normals | exit offset << 16
+    double *canon = nullptr;          // canonical normals, 32 slots per chunk
+    uint32_t *segtab = nullptr;       // per segment and entry offset: normals | exit offset << 16
+    uint32_t *table = nullptr;        // the same per super-chunk
     uint32_t *super_in = nullptr;     // per super-chunk: true entry offset ...
     int64_t *super_prefix = nullptr;  // ... and normals before it
 };
@@ -165,62 +170,81 @@ __device__ __forceinline__ void walk_chunk(Pcg64 g, const ZigTables &t, uint32_t
 }
 
 __global__ void __launch_bounds__(128) np_canon_kernel(const uint64_t *words, int slot, bool fused,
-                                                       uint64_t *__restrict__ recs, int64_t n_chunks) {
+                                                       uint64_t *__restrict__ recs, double *__restrict__ canon,
+                                                       int64_t n_chunks) {
     __shared__ SmemBlock sm;
     load_block(sm, words, slot, (uint64_t)blockIdx.x * blockDim.x * kChunk);
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chunks) return;
     const ZigTables t = {sm.tab.ki, sm.tab.wi, sm.tab.fi, fused};
     uint32_t mask, count, exit_offset, unused = 0;
-    walk_chunk<false>(generator_in_block(sm, words, (uint64_t)threadIdx.x * kChunk), t, 0u, mask, count, exit_offset,
-                      nullptr, -1, unused);
+    walk_chunk<true>(generator_in_block(sm, words, (uint64_t)threadIdx.x * kChunk), t, 0u, mask, count, exit_offset,
+                     canon + c * kChunk, -1, unused);
     recs[c] = (uint64_t)mask | ((uint64_t)exit_offset << 32);
 }
 
-// a chunk entered at a word the canonical chain does not start at: walked again from there (about one chunk in 3000)
-__device__ __noinline__ void rewalk_chunk(uint64_t *words, int slot, bool fused, int64_t chunk, uint32_t &e,
-                                          uint32_t &produced) {
+// a chunk entered at a word the canonical chain does not start at is walked again from there (about one chunk in 3000);
+// returns normals produced | exit offset << 16
+__device__ __noinline__ uint32_t rewalk_chunk(uint64_t *words, int slot, bool fused, int64_t chunk, uint32_t e) {
     const ZigTables t = {g_ki, g_wi, g_fi, fused};
-    uint32_t mask, exit_offset, unused = 0;
+    uint32_t mask, produced, exit_offset, unused = 0;
     atomicAdd(reinterpret_cast<unsigned long long *>(words + W_REWALKS), 1ull);
     walk_chunk<false>(generator_at(words, slot, (uint64_t)chunk * kChunk + e), t, e, mask, produced, exit_offset,
                       nullptr, -1, unused);
-    e = exit_offset;
-}
-
-// one chunk of a chain that enters it at word `e`: the normals it produces there and the entry offset of the next chunk
-__device__ __forceinline__ uint32_t follow_chunk(uint64_t *words, int slot, bool fused, uint64_t rec, int64_t chunk,
-                                                 uint32_t &e) {
-    if (e >= (uint32_t)kChunk) {  // a normal longer than a chunk: flagged, the stream is not used
+    if (exit_offset >= (uint32_t)kChunk) {  // a normal longer than a chunk: flagged, the stream is not used
         words[W_STATUS] = ST_ENTRY;
-        e = kChunk - 1;
+        exit_offset = kChunk - 1;
     }
-    const uint32_t mask = (uint32_t)rec;
-    uint32_t produced;
-    if ((mask >> e) & 1u) {  // on the canonical chain from here on (always so for e == 0)
-        produced = (uint32_t)__popc(mask >> e);
-        e = (uint32_t)(rec >> 32);
-    } else {
-        rewalk_chunk(words, slot, fused, chunk, e, produced);
-    }
-    return produced;
+    return produced | (exit_offset << 16);
 }
 
-// one block per super-chunk: its 1024 records staged in shared memory, lane e of the first warp follows them from entry e
+// one chunk of a chain that enters it at word e < 32: normals produced | exit offset << 16 (| kOffChain << 24 when the
+// chunk had to be walked again)
+__device__ __forceinline__ uint32_t follow_chunk(uint64_t *words, int slot, bool fused, uint64_t rec, int64_t chunk,
+                                                 uint32_t e) {
+    const uint32_t mask = (uint32_t)rec;
+    if ((mask >> e) & 1u) {  // on the canonical chain from here on (always so for e == 0)
+        uint32_t exit_offset = (uint32_t)(rec >> 32);
+        if (exit_offset >= (uint32_t)kChunk) {
+            words[W_STATUS] = ST_ENTRY;
+            exit_offset = kChunk - 1;
+        }
+        return (uint32_t)__popc(mask >> e) | (exit_offset << 16);
+    }
+    return rewalk_chunk(words, slot, fused, chunk, e) | (kOffChain << 24);
+}
+
+// one block per super-chunk: warp w, lane e follows segment w from entry e; then lane e of warp 0 composes the segments
 __global__ void __launch_bounds__(256) np_super_kernel(uint64_t *words, int slot, bool fused,
-                                                       const uint64_t *__restrict__ recs, uint32_t *__restrict__ table) {
+                                                       const uint64_t *__restrict__ recs, uint32_t *__restrict__ segtab,
+                                                       uint32_t *__restrict__ table) {
     __shared__ uint64_t rec_s[kSuper];
+    __shared__ uint32_t seg_s[kSegs * kChunk];
     const int64_t c0 = (int64_t)blockIdx.x * kSuper;
     for (int k = threadIdx.x; k < kSuper; k += blockDim.x) rec_s[k] = recs[c0 + k];
     __syncthreads();
-    if (threadIdx.x >= (unsigned)kChunk) return;
-    uint32_t e = threadIdx.x, produced = 0;
-    for (int k = 0; k < kSuper; ++k) produced += follow_chunk(words, slot, fused, rec_s[k], c0 + k, e);
-    if (e >= (uint32_t)kChunk) {
-        words[W_STATUS] = ST_ENTRY;
-        e = kChunk - 1;
+    {
+        const int w = threadIdx.x / kChunk;
+        uint32_t e = threadIdx.x % kChunk, produced = 0;
+        for (int k = w * kSeg; k < (w + 1) * kSeg; ++k) {
+            const uint32_t step = follow_chunk(words, slot, fused, rec_s[k], c0 + k, e);
+            produced += step & 0xffffu;
+            e = (step >> 16) & 0xffu;
+        }
+        const uint32_t row = produced | (e << 16);  // produced <= 128 * 32
+        seg_s[threadIdx.x] = row;
+        segtab[(int64_t)blockIdx.x * (kSegs * kChunk) + threadIdx.x] = row;
     }
-    table[(int64_t)blockIdx.x * kChunk + threadIdx.x] = produced | (e << 16);  // produced <= 32768
+    __syncthreads();
+    if (threadIdx.x < (unsigned)kChunk) {
+        uint32_t e = threadIdx.x, produced = 0;
+        for (int w = 0; w < kSegs; ++w) {
+            const uint32_t row = seg_s[w * kChunk + e];
+            produced += row & 0xffffu;
+            e = row >> 16;
+        }
+        table[(int64_t)blockIdx.x * kChunk + threadIdx.x] = produced | (e << 16);  // produced <= 32768
+    }
 }
 
 // one block: the rows of the super-chunks staged a tile at a time, thread 0 runs the chain from entry 0
@@ -252,75 +276,93 @@ __global__ void __launch_bounds__(1024) np_chain_kernel(uint64_t *words, const u
     }
 }
 
-// one block per super-chunk: thread 0 repeats the walk from the true entry, the block stores entry offset and output
-// index of every chunk
-__global__ void __launch_bounds__(256) np_resolve_kernel(uint64_t *words, int slot, bool fused,
-                                                         const uint64_t *__restrict__ recs,
-                                                         const uint32_t *__restrict__ super_in,
-                                                         const int64_t *__restrict__ super_prefix,
-                                                         uint32_t *__restrict__ entry, int64_t *__restrict__ prefix,
-                                                         int64_t n_supers) {
-    __shared__ uint64_t rec_s[kSuper];
-    __shared__ uint32_t rel_s[kSuper];
-    __shared__ unsigned char entry_s[kSuper];
-    __shared__ uint32_t total_s;
-    const int64_t c0 = (int64_t)blockIdx.x * kSuper;
-    for (int k = threadIdx.x; k < kSuper; k += blockDim.x) rec_s[k] = recs[c0 + k];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t e = super_in[blockIdx.x], produced = 0;
-        for (int k = 0; k < kSuper; ++k) {
-            entry_s[k] = (unsigned char)(e < (uint32_t)kChunk ? e : kChunk - 1);
-            rel_s[k] = produced;
-            produced += follow_chunk(words, slot, fused, rec_s[k], c0 + k, e);
-        }
-        total_s = produced;
-    }
-    __syncthreads();
-    const int64_t p0 = super_prefix[blockIdx.x];
-    for (int k = threadIdx.x; k < kSuper; k += blockDim.x) {
-        entry[c0 + k] = entry_s[k];
-        prefix[c0 + k] = p0 + rel_s[k];
-    }
-    if (threadIdx.x == 0 && (int64_t)blockIdx.x == n_supers - 1) prefix[n_supers * kSuper] = p0 + total_s;
+// the word behind canonical normal number q of a chunk: the start of canonical normal q + 1, or the chunk's end + exit
+__device__ __forceinline__ uint32_t word_behind(uint64_t rec, uint32_t q) {
+    uint32_t m = (uint32_t)rec;
+    for (uint32_t k = 0; k <= q; ++k) m &= m - 1;  // drop the starts of normals 0 .. q
+    return m ? (uint32_t)(__ffs((int)m) - 1) : (uint32_t)kChunk + (uint32_t)(rec >> 32);
 }
 
-__global__ void __launch_bounds__(kEmitThreads) np_emit_kernel(uint64_t *words, int slot, bool fused,
-                                                               const uint32_t *__restrict__ entry,
-                                                               const int64_t *__restrict__ prefix,
-                                                               double *__restrict__ out, int64_t count,
-                                                               int64_t n_chunks) {
-    __shared__ SmemBlock sm;
-    __shared__ double stage[kEmitThreads * kChunk];
-    const int64_t c_first = (int64_t)blockIdx.x * kEmitThreads;
-    const int64_t p_first = prefix[c_first];
-    if (p_first >= count) return;  // the whole block lies behind the last normal asked for
-    load_block(sm, words, slot, (uint64_t)c_first * kChunk);
-    const int64_t c_end = (c_first + kEmitThreads < n_chunks) ? c_first + kEmitThreads : n_chunks;
-    const int64_t p_end = prefix[c_end];
-    const int64_t c = c_first + threadIdx.x;
-    if (c < n_chunks) {
-        const int64_t p = prefix[c];
-        if (p < count) {
-            const ZigTables t = {sm.tab.ki, sm.tab.wi, sm.tab.fi, fused};
-            const uint32_t e = min(entry[c], (uint32_t)(kChunk - 1));
-            uint32_t mask, produced, exit_offset, words_at_stop = 0;
-            const int64_t stop_at = count - 1 - p;  // index, within this chunk, of the last normal asked for
-            walk_chunk<true>(generator_in_block(sm, words, (uint64_t)threadIdx.x * kChunk + e), t, e, mask, produced,
-                             exit_offset, stage + (p - p_first), stop_at, words_at_stop);
-            if (stop_at < (int64_t)produced && words[W_STATUS] == ST_OK) {
-                // this thread made the last normal of the call: the stream continues right behind it
-                const uint64_t consumed = (uint64_t)c * kChunk + words_at_stop;
-                const u128 next = jump_ahead(words, make_u128(words[2 * slot], words[2 * slot + 1]), consumed);
-                words[2 * (slot ^ 1)] = (uint64_t)(next >> 64);
-                words[2 * (slot ^ 1) + 1] = (uint64_t)next;
-                words[W_CONSUMED] += consumed;
-            }
+__global__ void __launch_bounds__(kPlaceThreads) np_place_kernel(uint64_t *words, int slot, bool fused,
+                                                                 const uint64_t *__restrict__ recs,
+                                                                 const double *__restrict__ canon,
+                                                                 const uint32_t *__restrict__ segtab,
+                                                                 const uint32_t *__restrict__ super_in,
+                                                                 const int64_t *__restrict__ super_prefix,
+                                                                 double *__restrict__ out, int64_t count) {
+    __shared__ uint64_t rec_s[kSuper];
+    __shared__ uint32_t seg_s[kSegs * kChunk];
+    __shared__ uint32_t rel_s[kSuper + 1];     // normals of this super-chunk before each chunk (+ the total)
+    __shared__ unsigned char entry_s[kSuper];  // true entry offset | kOffChain
+    __shared__ uint32_t seg_entry[kSegs], seg_rel[kSegs + 1];
+    __shared__ double again_s[kPlaceThreads / 32][kChunk];  // per warp: a chunk generated again
+    const int64_t p0 = super_prefix[blockIdx.x];
+    if (p0 >= count) return;  // the whole super-chunk lies behind the last normal asked for
+    const int64_t c0 = (int64_t)blockIdx.x * kSuper;
+    for (int k = threadIdx.x; k < kSuper; k += blockDim.x) rec_s[k] = recs[c0 + k];
+    if (threadIdx.x < (unsigned)(kSegs * kChunk))
+        seg_s[threadIdx.x] = segtab[(int64_t)blockIdx.x * (kSegs * kChunk) + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {  // the true entry through the segment rows
+        uint32_t e = super_in[blockIdx.x], produced = 0;
+        for (int w = 0; w < kSegs; ++w) {
+            seg_entry[w] = e;
+            seg_rel[w] = produced;
+            const uint32_t row = seg_s[w * kChunk + e];
+            produced += row & 0xffffu;
+            e = row >> 16;
+        }
+        seg_rel[kSegs] = produced;
+        rel_s[kSuper] = produced;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31u) == 0 && threadIdx.x / 32 < (unsigned)kSegs) {  // one thread per segment, each in its own warp
+        const int w = threadIdx.x / 32;
+        uint32_t e = seg_entry[w], produced = seg_rel[w];
+        for (int k = w * kSeg; k < (w + 1) * kSeg; ++k) {
+            const uint32_t step = follow_chunk(words, slot, fused, rec_s[k], c0 + k, e);
+            entry_s[k] = (unsigned char)(e | (step >> 24));
+            rel_s[k] = produced;
+            produced += step & 0xffffu;
+            e = (step >> 16) & 0xffu;
         }
     }
     __syncthreads();
-    const int64_t n_here = ((p_end < count) ? p_end : count) - p_first;
-    for (int64_t k = threadIdx.x; k < n_here; k += kEmitThreads) out[p_first + k] = stage[k];
+    // every warp moves whole chunks: lane j takes normal j of the chunk
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    for (int k = warp; k < kSuper; k += kPlaceThreads / 32) {
+        const int64_t p = p0 + rel_s[k];
+        if (p >= count) break;  // (the same for all lanes; later chunks of this warp lie further behind)
+        const uint32_t n = rel_s[k + 1] - rel_s[k];
+        const uint32_t e = entry_s[k] & 31u;
+        const uint64_t rec = rec_s[k];
+        const bool last_here = count - 1 - p < (int64_t)n;  // normal count - 1 is one of this chunk's
+        uint32_t behind = 0;                                // words of the chunk consumed up to and including it
+        if (entry_s[k] & kOffChain) {
+            if (lane == 0) {
+                const ZigTables t = {g_ki, g_wi, g_fi, fused};
+                uint32_t mask, produced, exit_offset;
+                atomicAdd(reinterpret_cast<unsigned long long *>(words + W_OFFCHAIN), 1ull);
+                walk_chunk<true>(generator_at(words, slot, (uint64_t)(c0 + k) * kChunk + e), t, e, mask, produced,
+                                 exit_offset, again_s[warp], count - 1 - p, behind);
+            }
+            __syncwarp();
+            if ((uint32_t)lane < n && p + lane < count) out[p + lane] = again_s[warp][lane];
+            __syncwarp();
+        } else {
+            const uint32_t skip = (uint32_t)__popc((uint32_t)rec & ((1u << e) - 1u));  // canonical normals before word e
+            if ((uint32_t)lane < n && p + lane < count) out[p + lane] = canon[(c0 + k) * kChunk + skip + lane];
+            if (last_here && lane == 0) behind = word_behind(rec, skip + (uint32_t)(count - 1 - p));
+        }
+        if (last_here && lane == 0 && words[W_STATUS] == ST_OK) {
+            // this chunk holds the last normal of the call: the stream continues right behind it
+            const uint64_t consumed = (uint64_t)(c0 + k) * kChunk + behind;
+            const u128 next = jump_ahead(words, make_u128(words[2 * slot], words[2 * slot + 1]), consumed);
+            words[2 * (slot ^ 1)] = (uint64_t)(next >> 64);
+            words[2 * (slot ^ 1) + 1] = (uint64_t)next;
+            words[W_CONSUMED] += consumed;
+        }
+    }
 }
 
 // the seed: state, increment and the jump table (multiplier, increment) of 2^k steps, k = 0..63
@@ -332,6 +374,7 @@ __global__ void np_seed_kernel(uint64_t *words, int slot, uint64_t s_hi, uint64_
     words[W_CONSUMED] = 0;
     words[W_STATUS] = ST_OK;
     words[W_REWALKS] = 0;
+    words[W_OFFCHAIN] = 0;
     u128 mult = pcg_multiplier(), plus = make_u128(i_hi, i_lo);
     for (int k = 0; k < 64; ++k) {
         words[W_JUMP + 4 * k] = (uint64_t)(mult >> 64);
@@ -351,14 +394,14 @@ static int64_t window_chunks(int64_t count) {
 
 static void release_scratch(Stream *h) {
     cudaFree(h->recs);
-    cudaFree(h->entry);
-    cudaFree(h->prefix);
+    cudaFree(h->canon);
+    cudaFree(h->segtab);
     cudaFree(h->table);
     cudaFree(h->super_in);
     cudaFree(h->super_prefix);
     h->recs = nullptr;
-    h->entry = nullptr;
-    h->prefix = nullptr;
+    h->canon = nullptr;
+    h->segtab = nullptr;
     h->table = nullptr;
     h->super_in = nullptr;
     h->super_prefix = nullptr;
@@ -369,11 +412,11 @@ static int reserve(Stream *h, int64_t n_chunks, cudaStream_t stream) {
     if (n_chunks <= h->cap_chunks) return TMD_OK;
     TMD_CUDA(cudaStreamSynchronize(stream));  // launches of earlier calls may still read the old scratch
     release_scratch(h);
-    const int64_t want = n_chunks + n_chunks / 4;
+    const int64_t want = n_chunks + n_chunks / 8;
     const int64_t chunks = ((want + kSuper - 1) / kSuper) * kSuper, supers = chunks / kSuper;
     cudaError_t err = cudaMalloc(&h->recs, sizeof(uint64_t) * chunks);
-    if (err == cudaSuccess) err = cudaMalloc(&h->entry, sizeof(uint32_t) * chunks);
-    if (err == cudaSuccess) err = cudaMalloc(&h->prefix, sizeof(int64_t) * (chunks + 1));
+    if (err == cudaSuccess) err = cudaMalloc(&h->canon, sizeof(double) * chunks * kChunk);
+    if (err == cudaSuccess) err = cudaMalloc(&h->segtab, sizeof(uint32_t) * supers * kSegs * kChunk);
     if (err == cudaSuccess) err = cudaMalloc(&h->table, sizeof(uint32_t) * supers * kChunk);
     if (err == cudaSuccess) err = cudaMalloc(&h->super_in, sizeof(uint32_t) * supers);
     if (err == cudaSuccess) err = cudaMalloc(&h->super_prefix, sizeof(int64_t) * (supers + 1));
@@ -463,24 +506,22 @@ int tmd_npstream_normals(void *handle, double *out, int64_t count, tmd_stream_t 
     TMD_REQUIRE(h != nullptr && h->seeded, "stream is NULL or was never seeded");
     TMD_REQUIRE(count >= 0 && (count == 0 || out != nullptr), "count must be >= 0 and out non-NULL");
     cudaStream_t s = as_stream(stream);
-    const int64_t kMaxPerCall = (int64_t)1 << 24;  // bounds the scratch and the serial chain pass
+    const int64_t kMaxPerCall = (int64_t)1 << 23;  // bounds the scratch (264 B per 32 words) and the serial chain pass
     for (int64_t done = 0; done < count;) {
         const int64_t now = (count - done < kMaxPerCall) ? count - done : kMaxPerCall;
         const int64_t n_chunks = window_chunks(now), n_supers = n_chunks / kSuper;
         TMD_CHECK(reserve(h, n_chunks, s));
         count_launch();
-        TMD_LAUNCH(np_canon_kernel, (unsigned)((n_chunks + 127) / 128), 128, s)(h->words, h->slot, h->fused, h->recs, n_chunks);
+        TMD_LAUNCH(np_canon_kernel, (unsigned)((n_chunks + 127) / 128), 128, s)(h->words, h->slot, h->fused, h->recs,
+                                                                                  h->canon, n_chunks);
         count_launch();
-        TMD_LAUNCH(np_super_kernel, (unsigned)n_supers, 256, s)(h->words, h->slot, h->fused, h->recs, h->table);
+        TMD_LAUNCH(np_super_kernel, (unsigned)n_supers, 256, s)(h->words, h->slot, h->fused, h->recs, h->segtab, h->table);
         count_launch();
         TMD_LAUNCH(np_chain_kernel, 1, 1024, s)(h->words, h->table, h->super_in, h->super_prefix, n_supers, now);
         count_launch();
-        TMD_LAUNCH(np_resolve_kernel, (unsigned)n_supers, 256, s)(h->words, h->slot, h->fused, h->recs,
-                                                                           h->super_in, h->super_prefix, h->entry,
-                                                                           h->prefix, n_supers);
-        count_launch();
-        TMD_LAUNCH(np_emit_kernel, (unsigned)((n_chunks + kEmitThreads - 1) / kEmitThreads), kEmitThreads, s)(
-            h->words, h->slot, h->fused, h->entry, h->prefix, out + done, now, n_chunks);
+        TMD_LAUNCH(np_place_kernel, (unsigned)n_supers, kPlaceThreads, s)(h->words, h->slot, h->fused, h->recs, h->canon,
+                                                                            h->segtab, h->super_in, h->super_prefix,
+                                                                            out + done, now);
         TMD_CUDA(cudaGetLastError());
         h->slot ^= 1;
         done += now;
@@ -488,7 +529,7 @@ int tmd_npstream_normals(void *handle, double *out, int64_t count, tmd_stream_t 
     return TMD_OK;
 }
 
-int tmd_npstream_state(void *handle, uint64_t *state, uint64_t *words_consumed, uint64_t *rewalks,
+int tmd_npstream_state(void *handle, uint64_t *state, uint64_t *words_consumed, uint64_t *counters,
                        tmd_stream_t stream) {
     Stream *h = static_cast<Stream *>(handle);
     TMD_REQUIRE(h != nullptr && h->seeded, "stream is NULL or was never seeded");
@@ -506,7 +547,10 @@ int tmd_npstream_state(void *handle, uint64_t *state, uint64_t *words_consumed, 
         state[1] = host[2 * h->slot + 1];
     }
     if (words_consumed) *words_consumed = host[W_CONSUMED];
-    if (rewalks) *rewalks = host[W_REWALKS];
+    if (counters) {
+        counters[0] = host[W_REWALKS];
+        counters[1] = host[W_OFFCHAIN];
+    }
     return TMD_OK;
 }
 

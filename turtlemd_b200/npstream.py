@@ -103,8 +103,9 @@ class NumpyStream:
         self._known = (st["state"]["state"], st["state"]["inc"])
         self._open = False
 
-    def stats(self) -> tuple[int, int]:
-        """(64-bit words consumed since the last seed, chunks walked off the canonical chain)."""
-        used, rewalks = C.c_uint64(0), C.c_uint64(0)
-        _lib.call("tmd_npstream_state", self._handle, None, C.byref(used), C.byref(rewalks), _device.stream_ptr())
-        return used.value, rewalks.value
+    def stats(self) -> tuple[int, int, int]:
+        """(64-bit words consumed since the last seed, chunks walked again off the canonical chain by any pass, chunks
+        whose normals were placed off the canonical chain)."""
+        used, counters = C.c_uint64(0), np.zeros(2, dtype=np.uint64)
+        _lib.call("tmd_npstream_state", self._handle, None, C.byref(used), _lib.hptr(counters), _device.stream_ptr())
+        return used.value, int(counters[0]), int(counters[1])
