@@ -66,6 +66,8 @@ def main():
                       "out_bytes_per_s": 8 * count / ms * 1e3, "host_numpy_ms": t_host, "h2d_pinned_ms": t_up,
                       "words_per_normal": words / (24.0 * count), "rewalks": rewalks, "chunks_placed_off_chain": off_chain}), flush=True)
 
+    if os.environ.get("TMD_PROF_ONLY_GENERATOR") == "1":
+        return
     cfg = bench.WORKLOADS["lj1m_langevin"]
     pos, vel, size, n, describe, make = bench.build_lj(cfg)
     rows = {}

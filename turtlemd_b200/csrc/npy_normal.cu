@@ -80,9 +80,9 @@ struct SmemTables {
     double wi[256], fi[256];
 };
 
-// the state `delta` words ahead: one multiply-add of 128 bits per set bit of delta (the maps commute)
-__device__ __forceinline__ u128 jump_ahead(const uint64_t *words, u128 state, uint64_t delta) {
-    const uint64_t *jump = words + W_JUMP;
+// the state `delta` words ahead: one multiply-add of 128 bits per set bit of delta (the maps commute); `jump` is the
+// table of the stream, which the kernels keep in shared memory (a jump is a chain of dependent table reads)
+__device__ __forceinline__ u128 jump_ahead(const uint64_t *jump, u128 state, uint64_t delta) {
     for (int k = 0; delta != 0; ++k, delta >>= 1) {
         if (delta & 1ull)
             state = state * make_u128(jump[4 * k], jump[4 * k + 1]) + make_u128(jump[4 * k + 2], jump[4 * k + 3]);
@@ -90,23 +90,34 @@ __device__ __forceinline__ u128 jump_ahead(const uint64_t *words, u128 state, ui
     return state;
 }
 
+struct SmemJump {
+    uint64_t map[4 * 64];
+};
+
+__device__ __forceinline__ void load_jump(SmemJump &j, const uint64_t *words) {  // (the caller synchronises)
+    for (int k = threadIdx.x; k < 4 * 64; k += blockDim.x) j.map[k] = words[W_JUMP + k];
+}
+
 struct SmemBlock {
     SmemTables tab;
+    SmemJump jump;
     uint64_t base[2];  // generator state at the first word of the block's first chunk
 };
 
-// the ziggurat tables into shared memory; thread 0 meanwhile jumps to the block's first word, so that every thread is a
-// short jump (its chunk within the block) away from its own
+// the ziggurat tables and the jump table into shared memory; thread 0 then jumps to the block's first word, so that
+// every thread is a short jump (its chunk within the block) away from its own
 __device__ __forceinline__ void load_block(SmemBlock &b, const uint64_t *words, int slot, uint64_t block_word) {
-    if (threadIdx.x == 0) {
-        const u128 s = jump_ahead(words, make_u128(words[2 * slot], words[2 * slot + 1]), block_word);
-        b.base[0] = (uint64_t)(s >> 64);
-        b.base[1] = (uint64_t)s;
-    }
+    load_jump(b.jump, words);
     for (int k = threadIdx.x; k < 256; k += blockDim.x) {
         b.tab.ki[k] = g_ki[k];
         b.tab.wi[k] = g_wi[k];
         b.tab.fi[k] = g_fi[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const u128 s = jump_ahead(b.jump.map, make_u128(words[2 * slot], words[2 * slot + 1]), block_word);
+        b.base[0] = (uint64_t)(s >> 64);
+        b.base[1] = (uint64_t)s;
     }
     __syncthreads();
 }
@@ -114,15 +125,29 @@ __device__ __forceinline__ void load_block(SmemBlock &b, const uint64_t *words, 
 __device__ __forceinline__ Pcg64 generator_in_block(const SmemBlock &b, const uint64_t *words, uint64_t local_word) {
     Pcg64 g;
     g.inc = make_u128(words[W_INC], words[W_INC + 1]);
-    g.state = jump_ahead(words, make_u128(b.base[0], b.base[1]), local_word);
+    g.state = jump_ahead(b.jump.map, make_u128(b.base[0], b.base[1]), local_word);
     return g;
 }
 
-__device__ __forceinline__ Pcg64 generator_at(const uint64_t *words, int slot, uint64_t word_index) {
+__device__ __forceinline__ Pcg64 generator_at(const uint64_t *words, const uint64_t *jump, int slot,
+                                              uint64_t word_index) {
     Pcg64 g;
     g.inc = make_u128(words[W_INC], words[W_INC + 1]);
-    g.state = jump_ahead(words, make_u128(words[2 * slot], words[2 * slot + 1]), word_index);
+    g.state = jump_ahead(jump, make_u128(words[2 * slot], words[2 * slot + 1]), word_index);
     return g;
+}
+
+// four normals to out[0..3], out 32-byte aligned: one 256-bit store (a thread fills its chunk's slot front to back, the
+// lanes of a warp are 256 bytes apart: every store instruction is one transaction per lane whatever its width)
+__device__ __forceinline__ void store4(double *out, double a, double b, double c, double d) {
+#if defined(TMD_NPY_EMULATE)
+    out[0] = a;
+    out[1] = b;
+    out[2] = c;
+    out[3] = d;
+#else
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(out), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#endif
 }
 
 // Walk one chunk from word `entry`: the start mask of the chain, how many normals start in the chunk and how far the
@@ -131,10 +156,25 @@ __device__ __forceinline__ Pcg64 generator_at(const uint64_t *words, int slot, u
 // The inner loop takes the words that are accepted on the spot -- all lanes of a warp in lock step -- and is left at a
 // wedge or tail word; the lanes that have one finish it together behind the loop (zig_slow is 5-10x a fast word, and
 // with one chunk per lane some lane meets one in a third of the iterations).
-template <bool EMIT>
+enum { EMIT_NONE = 0, EMIT_EACH = 1, EMIT_BY_FOUR = 2 };  // EMIT_BY_FOUR: out is global and 32-byte aligned (store4)
+
+template <int EMIT>
+__device__ __forceinline__ void emit_normal(double *out, uint32_t count, double x, double (&q)[4]) {
+    if (EMIT == EMIT_EACH) out[count] = x;
+    if (EMIT == EMIT_BY_FOUR) {  // (selects, not an indexed array: the group stays in registers)
+        const uint32_t j = count & 3u;
+        q[0] = j == 0u ? x : q[0];
+        q[1] = j == 1u ? x : q[1];
+        q[2] = j == 2u ? x : q[2];
+        if (j == 3u) store4(out + (count - 3u), q[0], q[1], q[2], x);
+    }
+}
+
+template <int EMIT>
 __device__ __forceinline__ void walk_chunk(Pcg64 g, const ZigTables &t, uint32_t entry, uint32_t &mask, uint32_t &count,
                                            uint32_t &exit_offset, double *out, int64_t stop_at, uint32_t &words_at_stop) {
     uint32_t pos = entry;
+    double q[4] = {0.0, 0.0, 0.0, 0.0};
     mask = 0;
     count = 0;
     while (pos < (uint32_t)kChunk) {
@@ -149,8 +189,8 @@ __device__ __forceinline__ void walk_chunk(Pcg64 g, const ZigTables &t, uint32_t
                 pending = true;
                 break;
             }
-            if (EMIT) {
-                out[count] = x;
+            if (EMIT != EMIT_NONE) {
+                emit_normal<EMIT>(out, count, x, q);
                 if ((int64_t)count == stop_at) words_at_stop = pos;
             }
             ++count;
@@ -159,13 +199,15 @@ __device__ __forceinline__ void walk_chunk(Pcg64 g, const ZigTables &t, uint32_t
             uint32_t used = 0;
             x = zig_slow(g, t, r, x, used);
             pos += used;
-            if (EMIT) {
-                out[count] = x;
+            if (EMIT != EMIT_NONE) {
+                emit_normal<EMIT>(out, count, x, q);
                 if ((int64_t)count == stop_at) words_at_stop = pos;
             }
             ++count;
         }
     }
+    if (EMIT == EMIT_BY_FOUR && (count & 3u) != 0u)  // the last, partial group (the slot holds 32 normals: room enough)
+        store4(out + (count & ~3u), q[0], q[1], q[2], q[3]);
     exit_offset = pos - (uint32_t)kChunk;
 }
 
@@ -178,19 +220,20 @@ __global__ void __launch_bounds__(128) np_canon_kernel(const uint64_t *words, in
     if (c >= n_chunks) return;
     const ZigTables t = {sm.tab.ki, sm.tab.wi, sm.tab.fi, fused};
     uint32_t mask, count, exit_offset, unused = 0;
-    walk_chunk<true>(generator_in_block(sm, words, (uint64_t)threadIdx.x * kChunk), t, 0u, mask, count, exit_offset,
-                     canon + c * kChunk, -1, unused);
+    walk_chunk<EMIT_BY_FOUR>(generator_in_block(sm, words, (uint64_t)threadIdx.x * kChunk), t, 0u, mask, count,
+                             exit_offset, canon + c * kChunk, -1, unused);
     recs[c] = (uint64_t)mask | ((uint64_t)exit_offset << 32);
 }
 
 // a chunk entered at a word the canonical chain does not start at is walked again from there (about one chunk in 3000);
 // returns normals produced | exit offset << 16
-__device__ __noinline__ uint32_t rewalk_chunk(uint64_t *words, int slot, bool fused, int64_t chunk, uint32_t e) {
+__device__ __noinline__ uint32_t rewalk_chunk(uint64_t *words, const uint64_t *jump, int slot, bool fused,
+                                              int64_t chunk, uint32_t e) {
     const ZigTables t = {g_ki, g_wi, g_fi, fused};
     uint32_t mask, produced, exit_offset, unused = 0;
     atomicAdd(reinterpret_cast<unsigned long long *>(words + W_REWALKS), 1ull);
-    walk_chunk<false>(generator_at(words, slot, (uint64_t)chunk * kChunk + e), t, e, mask, produced, exit_offset,
-                      nullptr, -1, unused);
+    walk_chunk<EMIT_NONE>(generator_at(words, jump, slot, (uint64_t)chunk * kChunk + e), t, e, mask, produced,
+                          exit_offset, nullptr, -1, unused);
     if (exit_offset >= (uint32_t)kChunk) {  // a normal longer than a chunk: flagged, the stream is not used
         words[W_STATUS] = ST_ENTRY;
         exit_offset = kChunk - 1;
@@ -200,8 +243,8 @@ __device__ __noinline__ uint32_t rewalk_chunk(uint64_t *words, int slot, bool fu
 
 // one chunk of a chain that enters it at word e < 32: normals produced | exit offset << 16 (| kOffChain << 24 when the
 // chunk had to be walked again)
-__device__ __forceinline__ uint32_t follow_chunk(uint64_t *words, int slot, bool fused, uint64_t rec, int64_t chunk,
-                                                 uint32_t e) {
+__device__ __forceinline__ uint32_t follow_chunk(uint64_t *words, const uint64_t *jump, int slot, bool fused,
+                                                 uint64_t rec, int64_t chunk, uint32_t e) {
     const uint32_t mask = (uint32_t)rec;
     if ((mask >> e) & 1u) {  // on the canonical chain from here on (always so for e == 0)
         uint32_t exit_offset = (uint32_t)(rec >> 32);
@@ -211,7 +254,7 @@ __device__ __forceinline__ uint32_t follow_chunk(uint64_t *words, int slot, bool
         }
         return (uint32_t)__popc(mask >> e) | (exit_offset << 16);
     }
-    return rewalk_chunk(words, slot, fused, chunk, e) | (kOffChain << 24);
+    return rewalk_chunk(words, jump, slot, fused, chunk, e) | (kOffChain << 24);
 }
 
 // one block per super-chunk: warp w, lane e follows segment w from entry e; then lane e of warp 0 composes the segments
@@ -220,14 +263,16 @@ __global__ void __launch_bounds__(256) np_super_kernel(uint64_t *words, int slot
                                                        uint32_t *__restrict__ table) {
     __shared__ uint64_t rec_s[kSuper];
     __shared__ uint32_t seg_s[kSegs * kChunk];
+    __shared__ SmemJump jump_s;
     const int64_t c0 = (int64_t)blockIdx.x * kSuper;
     for (int k = threadIdx.x; k < kSuper; k += blockDim.x) rec_s[k] = recs[c0 + k];
+    load_jump(jump_s, words);
     __syncthreads();
     {
         const int w = threadIdx.x / kChunk;
         uint32_t e = threadIdx.x % kChunk, produced = 0;
         for (int k = w * kSeg; k < (w + 1) * kSeg; ++k) {
-            const uint32_t step = follow_chunk(words, slot, fused, rec_s[k], c0 + k, e);
+            const uint32_t step = follow_chunk(words, jump_s.map, slot, fused, rec_s[k], c0 + k, e);
             produced += step & 0xffffu;
             e = (step >> 16) & 0xffu;
         }
@@ -296,12 +341,14 @@ __global__ void __launch_bounds__(kPlaceThreads) np_place_kernel(uint64_t *words
     __shared__ unsigned char entry_s[kSuper];  // true entry offset | kOffChain
     __shared__ uint32_t seg_entry[kSegs], seg_rel[kSegs + 1];
     __shared__ double again_s[kPlaceThreads / 32][kChunk];  // per warp: a chunk generated again
+    __shared__ SmemJump jump_s;
     const int64_t p0 = super_prefix[blockIdx.x];
     if (p0 >= count) return;  // the whole super-chunk lies behind the last normal asked for
     const int64_t c0 = (int64_t)blockIdx.x * kSuper;
     for (int k = threadIdx.x; k < kSuper; k += blockDim.x) rec_s[k] = recs[c0 + k];
     if (threadIdx.x < (unsigned)(kSegs * kChunk))
         seg_s[threadIdx.x] = segtab[(int64_t)blockIdx.x * (kSegs * kChunk) + threadIdx.x];
+    load_jump(jump_s, words);
     __syncthreads();
     if (threadIdx.x == 0) {  // the true entry through the segment rows
         uint32_t e = super_in[blockIdx.x], produced = 0;
@@ -320,7 +367,7 @@ __global__ void __launch_bounds__(kPlaceThreads) np_place_kernel(uint64_t *words
         const int w = threadIdx.x / 32;
         uint32_t e = seg_entry[w], produced = seg_rel[w];
         for (int k = w * kSeg; k < (w + 1) * kSeg; ++k) {
-            const uint32_t step = follow_chunk(words, slot, fused, rec_s[k], c0 + k, e);
+            const uint32_t step = follow_chunk(words, jump_s.map, slot, fused, rec_s[k], c0 + k, e);
             entry_s[k] = (unsigned char)(e | (step >> 24));
             rel_s[k] = produced;
             produced += step & 0xffffu;
@@ -328,36 +375,63 @@ __global__ void __launch_bounds__(kPlaceThreads) np_place_kernel(uint64_t *words
         }
     }
     __syncthreads();
-    // every warp moves whole chunks: lane j takes normal j of the chunk
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    // every warp moves whole chunks, lane j normal j of a chunk, four chunks in flight: the canonical normals from the
+    // entry word on
+    for (int k0 = warp; k0 < kSuper; k0 += 4 * (kPlaceThreads / 32)) {
+        double v[4];
+        int64_t dst[4];
+        bool move[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * (kPlaceThreads / 32);
+            move[u] = false;
+            if (k < kSuper) {
+                const int64_t p = p0 + rel_s[k];
+                const uint32_t n = rel_s[k + 1] - rel_s[k];
+                const uint32_t e = entry_s[k];
+                if (!(e & kOffChain) && (uint32_t)lane < n && p + lane < count) {
+                    const uint32_t skip = (uint32_t)__popc((uint32_t)rec_s[k] & ((1u << e) - 1u));  // normals before word e
+                    v[u] = canon[(c0 + k) * kChunk + skip + lane];
+                    dst[u] = p + lane;
+                    move[u] = true;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (move[u]) out[dst[u]] = v[u];
+    }
+    // the rare rest: chunks entered off the canonical chain are generated again, and the chunk that holds normal
+    // `count` - 1 leaves the generator state behind it
     for (int k = warp; k < kSuper; k += kPlaceThreads / 32) {
         const int64_t p = p0 + rel_s[k];
         if (p >= count) break;  // (the same for all lanes; later chunks of this warp lie further behind)
         const uint32_t n = rel_s[k + 1] - rel_s[k];
+        const bool off_chain = (entry_s[k] & kOffChain) != 0;
+        const bool last_here = count - 1 - p < (int64_t)n;  // normal count - 1 is one of this chunk's
+        if (!off_chain && !last_here) continue;
         const uint32_t e = entry_s[k] & 31u;
         const uint64_t rec = rec_s[k];
-        const bool last_here = count - 1 - p < (int64_t)n;  // normal count - 1 is one of this chunk's
-        uint32_t behind = 0;                                // words of the chunk consumed up to and including it
-        if (entry_s[k] & kOffChain) {
+        uint32_t behind = 0;  // words of the chunk consumed up to and including normal count - 1
+        if (off_chain) {
             if (lane == 0) {
                 const ZigTables t = {g_ki, g_wi, g_fi, fused};
                 uint32_t mask, produced, exit_offset;
                 atomicAdd(reinterpret_cast<unsigned long long *>(words + W_OFFCHAIN), 1ull);
-                walk_chunk<true>(generator_at(words, slot, (uint64_t)(c0 + k) * kChunk + e), t, e, mask, produced,
-                                 exit_offset, again_s[warp], count - 1 - p, behind);
+                walk_chunk<EMIT_EACH>(generator_at(words, jump_s.map, slot, (uint64_t)(c0 + k) * kChunk + e), t, e, mask,
+                                      produced, exit_offset, again_s[warp], count - 1 - p, behind);
             }
             __syncwarp();
             if ((uint32_t)lane < n && p + lane < count) out[p + lane] = again_s[warp][lane];
             __syncwarp();
-        } else {
-            const uint32_t skip = (uint32_t)__popc((uint32_t)rec & ((1u << e) - 1u));  // canonical normals before word e
-            if ((uint32_t)lane < n && p + lane < count) out[p + lane] = canon[(c0 + k) * kChunk + skip + lane];
-            if (last_here && lane == 0) behind = word_behind(rec, skip + (uint32_t)(count - 1 - p));
+        } else if (lane == 0) {
+            const uint32_t skip = (uint32_t)__popc((uint32_t)rec & ((1u << e) - 1u));
+            behind = word_behind(rec, skip + (uint32_t)(count - 1 - p));
         }
         if (last_here && lane == 0 && words[W_STATUS] == ST_OK) {
-            // this chunk holds the last normal of the call: the stream continues right behind it
             const uint64_t consumed = (uint64_t)(c0 + k) * kChunk + behind;
-            const u128 next = jump_ahead(words, make_u128(words[2 * slot], words[2 * slot + 1]), consumed);
+            const u128 next = jump_ahead(jump_s.map, make_u128(words[2 * slot], words[2 * slot + 1]), consumed);
             words[2 * (slot ^ 1)] = (uint64_t)(next >> 64);
             words[2 * (slot ^ 1) + 1] = (uint64_t)next;
             words[W_CONSUMED] += consumed;
