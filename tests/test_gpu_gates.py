@@ -87,8 +87,8 @@ def test_langevin_ensemble_matches_the_reference_default_rng_in_distribution():
 
 def test_stock_langevin_script_retraces_the_reference_under_the_same_seed():
     """``LangevinInertia(timestep, gamma, beta, seed=7)`` exactly as a TurtleMD script writes it: the default generator is
-    the reference's ``default_rng(seed)`` (integrators.py:216), drawn on the host in the reference's order (:284-315), and
-    the kernels do the rest.  20 000 particles x 500 steps against the reference's own run (fixture of
+    the reference's ``default_rng(seed)`` (integrators.py:216), continued on the device in the reference's order (:284-315;
+    tmd_npstream_*, csrc/npy_normal.cu: bit-exact PCG64 + ziggurat), and the kernels do the rest.  20 000 particles x 500 steps against the reference's own run (fixture of
     tests/golden/make_golden_r2.py): the same trajectory, not merely the same distribution."""
     from turtlemd_b200.integrators import LangevinInertia
     from turtlemd_b200.potentials import DoubleWell

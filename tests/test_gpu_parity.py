@@ -502,7 +502,8 @@ def test_langevin_inertia_lj_trajectory():
 
 
 def test_langevin_numpy_generator_host_draw_path():
-    """default_rng draws on the host, as in the reference; compare with the oracle fed the same generator."""
+    """A default_rng generator as ``rgen`` (continued on the device since round 2, drawn on the host before; the host-draw
+    path itself is exercised by tests/test_npy_normal.py); compare with the oracle fed the same generator."""
     k = _pkg()
     from oracle import turtle_oracle as to
 
