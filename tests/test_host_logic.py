@@ -482,3 +482,18 @@ def test_vectorised_host_draw_equals_the_per_particle_draws():
     assert pos_f.shape == pos_s.shape == (50, 3)
     assert np.allclose(pos_f, pos_s, rtol=1e-15, atol=0.0) and np.allclose(vel_f, vel_s, rtol=1e-14, atol=1e-18)
     assert fast.rgen.normal() == slow.rgen.normal()  # both streams stand at the same position
+
+
+def test_touch_invalidates_what_the_potentials_derived_from_ptype():
+    """ptype edited IN PLACE + Particles.touch(): the type table of LennardJonesCut is rebuilt (the caches
+    were keyed on the identity of the ptype array alone)."""
+    particles = Particles.from_arrays(np.zeros((4, 3)), ptype=np.zeros(4, dtype=int))
+    pot = LennardJonesCut(dim=3, shift=True)
+    pot.set_parameters({0: {"sigma": 1.0, "epsilon": 1.0, "rcut": 2.5}, 1: {"sigma": 1.2, "epsilon": 0.5, "rcut": 3.0}})
+    types, table, tidx = pot._tables(particles)
+    assert types == [0] and table.shape == (6, 1, 1)
+    particles.ptype[2:] = 1
+    assert pot._tables(particles)[0] == [0]  # same array, no touch(): the cached table (documented behaviour)
+    particles.touch()
+    types, table, tidx = pot._tables(particles)
+    assert types == [0, 1] and table.shape == (6, 2, 2) and tidx.tolist() == [0, 0, 1, 1]

@@ -61,7 +61,7 @@ class LennardJonesCut(Potential):
         self._rcut2: dict = {}
         self._offset: dict = {}
         self.params = {}
-        self._cache = None  # (ptype array, types, table, host tidx)
+        self._cache = None  # (ptype array, types, table, host tidx, particles generation)
 
     def set_parameters(self, parameters: dict[Any, dict[str, float]]):
         """Atom/pair parameters -> the six coefficient tables (lennardjones.py:87-116)."""
@@ -104,7 +104,8 @@ class LennardJonesCut(Potential):
         """
         ptype = particles.ptype
         cache = self._cache
-        if cache is not None and cache[0] is ptype and len(cache[3]) == len(ptype):
+        generation = getattr(particles, "_generation", 0)  # Particles.touch(): ptype was edited in place
+        if cache is not None and cache[0] is ptype and len(cache[3]) == len(ptype) and cache[4] == generation:
             return cache[1], cache[2], cache[3]
         types, tidx, counts = np.unique(np.asarray(ptype), return_inverse=True, return_counts=True)
         types = [int(t) for t in types]
@@ -123,7 +124,7 @@ class LennardJonesCut(Potential):
                 table[:, a, b] = (self._lj1[key], self._lj2[key], self._lj3[key], self._lj4[key],
                                   self._offset[key], self._rcut2[key])
         tidx = np.ascontiguousarray(tidx.reshape(-1), dtype=np.int64)
-        self._cache = (ptype, types, table, tidx)
+        self._cache = (ptype, types, table, tidx, generation)
         return types, table, tidx
 
     def __del__(self):
@@ -188,7 +189,8 @@ class LennardJonesCut(Potential):
         particles = system.particles
         if particles.npart < 2:
             return True
-        key = (particles.npart, tuple(np.asarray(system.box.length, dtype=float).tolist()), id(particles.ptype), self.method)
+        key = (particles.npart, tuple(np.asarray(system.box.length, dtype=float).tolist()), id(particles.ptype), self.method,
+               getattr(particles, "_generation", 0))
         cached = getattr(self, "_pass_cache", None)
         if cached is None or cached[0] != key:
             types, table, _ = self._tables(particles)

@@ -136,12 +136,13 @@ class DoubleWellPair(Potential):
         """Device index lists of the atoms of types[0] / types[1] (cached per ptype array)."""
         ptype = particles.ptype
         cache = self._cache
-        if cache is None or cache[0] is not ptype or cache[1] != len(ptype):
+        generation = getattr(particles, "_generation", 0)  # Particles.touch(): ptype was edited in place
+        if cache is None or cache[0] is not ptype or cache[1] != (len(ptype), generation):
             idx0 = np.where(np.asarray(ptype) == self.types[0])[0].astype(np.int32)
             idx1 = np.where(np.asarray(ptype) == self.types[1])[0].astype(np.int32)
             dev0 = _device.to_device(idx0) if len(idx0) else None
             dev1 = _device.to_device(idx1) if len(idx1) else None
-            cache = self._cache = (ptype, len(ptype), idx0, idx1, dev0, dev1)
+            cache = self._cache = (ptype, (len(ptype), generation), idx0, idx1, dev0, dev1)
         return cache[2:]
 
     def _energy_is_pass_independent(self, system) -> bool:

@@ -39,6 +39,7 @@ class Particles:
         self._vw = None          # device double[10]: V, W(3x3)
         self._vw_fresh = set()   # which of {"v_pot", "virial"} live only on the device
         self._static = {}        # device copies of mass / imass / type indices, keyed by array identity
+        self._generation = 0     # bumped by touch(): caches the potentials keep per ptype array check it
 
     # ---- the mirrored arrays ------------------------------------------------------------------
     @property
@@ -190,8 +191,10 @@ class Particles:
         return self._static_device("mass", self.mass, np.float64)
 
     def touch(self):
-        """Forget cached device copies of mass / imass / ptype after editing them IN PLACE."""
+        """Forget cached device copies of mass / imass / ptype after editing them IN PLACE (also what the potentials
+        derived from ptype: type tables, active-atom lists)."""
         self._static.clear()
+        self._generation += 1
 
 
 def _on_device_only(particles: Particles) -> bool:
