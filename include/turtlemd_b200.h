@@ -422,6 +422,7 @@ int tmd_host_philox_raw_fill(uint64_t *out, int64_t count, uint64_t key, uint64_
  *   state:   waits for the stream, returns the generator state {hi, lo}, the 64-bit words consumed since the
  *            seed and (tests) counters[2] = chunks walked again off the canonical chain by any pass, chunks placed off it; TMD_ERR_INVALID if a call's word
  *            window was too short (never observed: > 100 sigma) -- the normals of that call are then not valid;
+ *   A stream belongs to the device that is current at create() and is used from one CUDA stream at a time.
  *   libm_variant: which glibc log1p build this process runs (1: FMA build, 0: baseline, -1: neither -- then
  *            create() refuses and callers draw on the host).                                              */
 int tmd_npstream_libm_variant(void);

@@ -14,14 +14,19 @@ Any other generator (``MT19937``, the reference tests' fake generators, ...) kee
 from __future__ import annotations
 
 import ctypes as C
+import logging
 
 import numpy as np
 
 from . import _device, _lib
 
+LOGGER = logging.getLogger(__name__)
+LOGGER.addHandler(logging.NullHandler())
+
 _MASK = (1 << 64) - 1
 
 ENABLED = True  # module switch: tests compare the device stream with the host-draw path
+_warned = False
 
 
 def usable(rgen) -> bool:
@@ -30,8 +35,15 @@ def usable(rgen) -> bool:
         return False
     if type(rgen.bit_generator) is not np.random.PCG64:
         return False
+    global _warned
     try:
-        return _lib.load().tmd_npstream_libm_variant() >= 0 and _lib.device_count() > 0
+        if _lib.load().tmd_npstream_libm_variant() < 0:
+            if not _warned:
+                _warned = True
+                LOGGER.warning("this libm's log1p is neither glibc build restated in csrc/npy_normal.h: the NumPy generator "
+                               "cannot be continued on the device bit for bit; Langevin noise is drawn on the host")
+            return False
+        return _lib.device_count() > 0
     except Exception:  # noqa: BLE001 - no library / no driver
         return False
 
